@@ -1,0 +1,146 @@
+/* sb200.h — C ABI of libspades_b200.so: the B200-native (sm_100a) graph-construction front end of SPAdes 3.15.4.
+ *
+ * The reference has no plugin/FFI layer on this path: the boundary is the set of C++ template interfaces its three
+ * callers use (spades-core's Construction stage, spades-gbuilder, spades-kmercount).  Each entry point below names
+ * the reference interface it stands in for (paths relative to /root/reference/assembler/src/common); the C++ adapter
+ * that plugs them back into SPAdes is spades_for_blackbird_b200/host/sb200_adapters.hpp, and INTEGRATION.md shows the
+ * reference-side edit.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every handle is opaque and owned by the caller until its *_free.
+ *   - return value 0 = ok; nonzero = error, message via sb200_last_error(ctx).  The reference aborts with
+ *     FATAL_ERROR / VERIFY on the same conditions (utils/logger/logger.hpp:177-190); the adapter maps nonzero to that.
+ *   - every call is blocking and must come from one host thread per context (the reference calls these interfaces
+ *     from a single stage thread, pipeline/stage.cpp:143-204).
+ *   - there is NO CPU fallback: sb200_create fails when no sm_100 device is present.
+ *   - k-mer records: W = ceil(K/32) little-endian uint64 words, base i (A,C,G,T = 0..3) at bits 2(i%32) of word i/32
+ *     (sequence/rtseq.hpp:34-131).  "File order" = hash bucket (utils/kmer_mph/kmer_buckets.hpp:28-41), then word-wise
+ *     ascending from word 0 (adt/array_vector.hpp:247-256) — the order of KMerDiskStorage's kmers<i> files and of
+ *     final_kmers.
+ */
+#ifndef SB200_H
+#define SB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb200_ctx sb200_ctx;
+typedef struct sb200_reads sb200_reads;       /* packed reads resident in HBM                                        */
+typedef struct sb200_kmers sb200_kmers;       /* kmers::KMerDiskStorage<RtSeq>  (kmer_mph/kmer_index_builder.hpp:48-191) */
+typedef struct sb200_mphf sb200_mphf;         /* kmers::KMerIndex<traits>       (kmer_mph/kmer_index.hpp:25-147)      */
+typedef struct sb200_ext sb200_ext;           /* utils::DeBruijnExtensionIndex<> payload (extension_index/kmer_extension_index.hpp:242-339) */
+typedef struct sb200_unitigs sb200_unitigs;   /* std::vector<Sequence> of UnbranchingPathExtractor                   */
+
+/* ---- context ------------------------------------------------------------------------------------------------------ */
+int  sb200_create(int device, sb200_ctx **out);          /* fails (nonzero, *out = NULL) without an sm_100 GPU      */
+void sb200_destroy(sb200_ctx *ctx);
+const char *sb200_last_error(const sb200_ctx *ctx);      /* ctx may be NULL: error of the last failed sb200_create  */
+int  sb200_synchronize(sb200_ctx *ctx);
+void *sb200_stream(sb200_ctx *ctx);                       /* cudaStream_t all work of this context is launched on    */
+uint64_t sb200_kernel_launches(sb200_ctx *ctx, int reset);/* kernels launched by this library since the last reset   */
+
+/* ---- reads: io::ReadStreamList<io::SingleReadSeq> (io/reads/read_stream.hpp:63-87; binary layout of
+ *      io/reads/single_read.hpp:279-299 / sequence/sequence.hpp:399-428: every read word-aligned, 2 bits per base) -- */
+int  sb200_reads_upload(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off /* n_reads+1 */,
+                        const uint32_t *len, uint64_t n_reads, sb200_reads **out);           /* host -> HBM             */
+int  sb200_reads_wrap_device(sb200_ctx *ctx, const uint64_t *d_words, const uint64_t *d_word_off, const uint32_t *d_len,
+                             uint64_t n_reads, uint64_t n_words, sb200_reads **out);         /* HBM -> HBM copy         */
+void sb200_reads_free(sb200_reads *r);
+
+/* ---- KMerDiskCounter<RtSeq>::Count over DeBruijnReadKMerSplitter (kmer_mph/kmer_index_builder.hpp:241-267,
+ *      kmer_mph/kmer_splitters.hpp:25-41,109-133, kmer_mph/kmer_splitter.hpp:120-167).
+ *      canonical_only = StoringTypeFilter<InvertableStoring> (ph_map/storing_traits.hpp:88-101);
+ *      add_rc = the streams are RC-wrapped (io/dataset_support/read_converter.cpp:212-242).
+ *      gbuilder / spades-core: K = k+1, canonical_only = 1, add_rc = 1, num_buckets = 10*nthreads;
+ *      spades-kmercount (projects/kmercount/main.cpp:186-228): canonical_only = 0, add_rc = 1, num_buckets = 16.
+ *      Fails with the reference's message when no k-mer is extracted (kmer_index_builder.hpp:261-264). ---------------- */
+int  sb200_count(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc,
+                 unsigned num_buckets, sb200_kmers **out);
+/* KMerDiskCounter over DeBruijnKMerKMerSplitter(K_target = K_source-1, add_rc = true)
+ * (kmer_mph/kmer_splitters.hpp:135-204; extension_index/kmer_extension_index_builder.hpp:88-97) */
+int  sb200_derive_kmers(sb200_ctx *ctx, const sb200_kmers *kpomers, unsigned num_buckets, sb200_kmers **out);
+
+/* KMerDiskStorage accessors: k(), num_buckets(), total_kmers(), bucket_size(i), bucket_begin/end(i), final_kmers() */
+unsigned sb200_kmers_k(const sb200_kmers *s);
+unsigned sb200_kmers_words(const sb200_kmers *s);
+unsigned sb200_kmers_num_buckets(const sb200_kmers *s);
+uint64_t sb200_kmers_size(const sb200_kmers *s);
+uint64_t sb200_kmers_instances(const sb200_kmers *s);     /* k-mer instances that went into the count (0 if derived)  */
+int  sb200_kmers_bucket_starts(const sb200_kmers *s, uint64_t *out /* num_buckets+1 */);
+int  sb200_kmers_download(const sb200_kmers *s, uint64_t first, uint64_t count, uint64_t *records_out /* count*words */);
+int  sb200_kmers_counts_download(const sb200_kmers *s, uint64_t first, uint64_t count, uint32_t *counts_out);
+const uint64_t *sb200_kmers_device_records(const sb200_kmers *s);   /* device pointers, for zero-copy consumers        */
+const uint32_t *sb200_kmers_device_counts(const sb200_kmers *s);
+void sb200_kmers_free(sb200_kmers *s);
+
+/* ---- KMerIndexBuilder<Index>::BuildIndex(index, storage) (kmer_mph/kmer_index_builder.hpp:383-433): one BooPHF
+ *      (gamma 4, 25 levels, XXH3_128; ext/include/boomphf/BooPHF.h) per bucket + segment_starts_ ------------------ */
+int  sb200_mphf_build(sb200_ctx *ctx, const sb200_kmers *kmers, sb200_mphf **out);
+uint64_t sb200_mphf_size(const sb200_mphf *m);                                  /* KMerIndex::size()                   */
+uint64_t sb200_mphf_mem_size(const sb200_mphf *m);                              /* KMerIndex::mem_size(), bytes        */
+/* KMerIndex::seq_idx for n host records (kmer_index.hpp:85-90); idx_out[i] = ~0 if the key falls through all levels */
+int  sb200_mphf_lookup(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *records, uint64_t n, uint64_t *idx_out);
+/* KMerIndex::serialize bytes (kmer_index.hpp:99-105); out == NULL: size query */
+int  sb200_mphf_serialize(const sb200_mphf *m, uint8_t *out, uint64_t *size);
+void sb200_mphf_free(sb200_mphf *m);
+
+/* ---- DeBruijnExtensionIndexBuilder::BuildExtensionIndexFromKPOMers, mask part
+ *      (extension_index/kmer_extension_index_builder.hpp:82-106,44-59) ------------------------------------------------ */
+int  sb200_ext_build(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf,
+                     sb200_ext **out);
+int  sb200_ext_masks_download(const sb200_ext *e, uint8_t *masks_out /* size bytes, MPHF-index order = data_ */);
+int  sb200_ext_idx_download(const sb200_ext *e, uint32_t *idx_out /* size, file order */);
+void sb200_ext_free(sb200_ext *e);
+
+/* ---- EarlyTipClipperProcessor(index, length_bound).ClipTips()
+ *      (assembly_graph/construction/early_simplification.hpp:37-160); *removed = its return value -------------------- */
+int  sb200_tipclip(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext,
+                   uint64_t length_bound, uint64_t *removed);
+
+/* ---- UnbranchingPathExtractor(index, k).ExtractUnbranchingPaths / ...AndLoops
+ *      (assembly_graph/construction/debruijn_graph_constructor.hpp:182-388).  Sequences come in the reference's
+ *      output order.  Unlike the reference the masks are left untouched (it isolates every consumed vertex). -------- */
+int  sb200_unitigs_extract(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext,
+                           int with_loops, sb200_unitigs **out);
+uint64_t sb200_unitigs_count(const sb200_unitigs *u);
+uint64_t sb200_unitigs_loops(const sb200_unitigs *u);
+uint64_t sb200_unitigs_total_bases(const sb200_unitigs *u);
+uint64_t sb200_unitigs_total_words(const sb200_unitigs *u);
+/* packed like reads: sequence i = words[word_off[i] .. word_off[i+1]), len[i] bases */
+int  sb200_unitigs_download(const sb200_unitigs *u, uint64_t *words_out, uint64_t *word_off_out /* count+1 */,
+                            uint32_t *len_out);
+void sb200_unitigs_free(sb200_unitigs *u);
+
+/* ---- whole path, host buffers in / host buffers out: what spades-gbuilder does between read conversion and output
+ *      (projects/gbuilder/main.cpp:165-181) and spades-core's Construction stage (stages/construction.cpp:469-483).
+ *      Result buffers are pinned host memory owned by the graph handle. ---------------------------------------------- */
+typedef struct sb200_graph sb200_graph;
+typedef struct {
+    unsigned k;                 /* odd, 1 <= k < 128                                                                   */
+    unsigned num_buckets;       /* 10 * nthreads in the reference                                                      */
+    int      tip_clip;          /* run EarlyTipClipper (spades-core, !gap_closer)                                      */
+    uint64_t tip_length_bound;  /* RL - k (stages/construction.cpp:300-304)                                            */
+    int      with_loops;        /* keep_perfect_loops                                                                  */
+    int      fetch_kmers;       /* copy final_kmers + (k+1)-mers + counts back as well                                 */
+} sb200_construct_params;
+typedef struct {
+    uint64_t n_kpomers, n_kmers, n_unitigs, n_loops, unitig_bases, n_unitig_words, kpomer_instances, clipped;
+    const uint64_t *kpomers; const uint32_t *kpomer_counts; const uint64_t *kpomer_bucket_starts;   /* fetch_kmers */
+    const uint64_t *kmers;   const uint64_t *kmer_bucket_starts;                                     /* fetch_kmers */
+    const uint8_t  *masks;                 /* n_kmers, MPHF-index order                                               */
+    const uint8_t  *index_bytes; uint64_t index_size;   /* KMerIndex::serialize                                      */
+    const uint64_t *unitig_words; const uint64_t *unitig_word_off; const uint32_t *unitig_len;
+    uint64_t h2d_bytes, d2h_bytes;
+} sb200_graph_view;
+int  sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
+                     uint64_t n_reads, const sb200_construct_params *params, sb200_graph **out);
+int  sb200_graph_get(const sb200_graph *g, sb200_graph_view *view);
+void sb200_graph_free(sb200_graph *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,295 @@
+// count.cu — reads -> k-mer instances -> sorted-unique per-bucket k-mer sets with multiplicities.
+//
+// Replaces, for one GPU (reference file:line):
+//   DeBruijnReadKMerSplitter::Split / FillBufferFromSequence     C/utils/kmer_mph/kmer_splitters.hpp:25-41,109-133
+//   KMerSortingSplitter::DumpBuffers                             C/utils/kmer_mph/kmer_splitter.hpp:120-167
+//   KMerDiskCounter::Count / MergeKMers                          C/utils/kmer_mph/kmer_index_builder.hpp:241-365
+//   DeBruijnKMerKMerSplitter::FillBufferFromKMers                C/utils/kmer_mph/kmer_splitters.hpp:159-176
+// The reference streams every read and its reverse complement and keeps a window iff it IsMinimal(); here each
+// forward window emits min(x, rc(x)) once (a self-reverse-complement window counts twice, exactly as both of the
+// reference's streams would count it), so half of the work and none of the RC stream exists.
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "kmer_set.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+enum ExtractMode { MODE_CANON_RC = 0, MODE_ALL_RC = 1, MODE_CANON_FWD = 2, MODE_ALL_FWD = 3 };
+
+__global__ void window_count_kernel(const uint32_t *__restrict__ len, uint64_t n_reads, uint32_t K, uint32_t mult,
+                                    uint64_t *__restrict__ cnt) {
+    uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads) {
+        uint32_t l = len[r];
+        cnt[r] = l >= K ? (uint64_t) (l - K + 1) * mult : 0;
+    }
+}
+
+// One warp per read; lane = window position (stride 32), so the records of a read leave as consecutive,
+// fully coalesced W x 8 byte stores.  The packed read (<= a few dozen words) is served from L1 after first touch.
+template<int W>
+__global__ void __launch_bounds__(256) extract_reads_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
+                                                           const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode,
+                                                           const uint64_t *__restrict__ out_off, uint64_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t) gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = (uint64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_reads; r += warps_total) {
+        uint32_t l = len[r];
+        if (l < (uint32_t) K) continue;
+        uint32_t nwin = l - K + 1;
+        const uint64_t *seq = words + word_off[r];
+        uint32_t nw = (l + 31) >> 5;
+        uint64_t o = out_off[r];
+        for (uint32_t p = lane; p < nwin; p += 32) {
+            uint64_t x[W], y[W];
+            kmer_window<W>(seq, nw, p, K, x);
+            if (mode == MODE_ALL_FWD) {
+                store_rec<W>(out, o + p, x);
+            } else if (mode == MODE_ALL_RC) {
+                kmer_rc<W>(x, K, y);
+                store_rec<W>(out, o + 2ull * p, x);
+                store_rec<W>(out, o + 2ull * p + 1, y);
+            } else {
+                bool minimal = kmer_canonical<W>(x, K, y);
+                if (mode == MODE_CANON_FWD && !minimal) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) y[j] = ~0ULL;   // marker: all-T is never minimal, sorts last
+                }
+                store_rec<W>(out, o + p, y);
+            }
+        }
+    }
+}
+
+// kmer_splitters.hpp:159-176: every stored (k+1)-mer x contributes canon(x[0..k)) and canon(x[1..k]) (its RC
+// contributes the same two canonical k-mers, so add_rc only duplicates and is folded away).
+template<int WS, int W>
+__global__ void __launch_bounds__(256) derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, uint64_t *__restrict__ out) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x[WS], a[W], c[W];
+    load_rec<WS>(kp, i, x);
+    kmer_subwindow<WS, W>(x, 0, k, a);
+    kmer_canonical<W>(a, k, c);
+    store_rec<W>(out, 2 * i, c);
+    kmer_subwindow<WS, W>(x, 1, k, a);
+    kmer_canonical<W>(a, k, c);
+    store_rec<W>(out, 2 * i + 1, c);
+}
+
+// ---- unique --------------------------------------------------------------------------------------------------------
+constexpr int UQ_THREADS = 256;
+constexpr int UQ_ITEMS = 8;
+constexpr int UQ_TILE = UQ_THREADS * UQ_ITEMS;
+
+template<int W>
+__device__ __forceinline__ bool is_head(const uint64_t *__restrict__ recs, uint64_t i) {
+    if (i == 0) return true;
+    uint64_t a[W], b[W];
+    load_rec<W>(recs, i, a);
+    load_rec<W>(recs, i - 1, b);
+    return !kmer_eq<W>(a, b);
+}
+
+template<int W>
+__global__ void __launch_bounds__(UQ_THREADS) unique_count_kernel(const uint64_t *__restrict__ recs, uint64_t n, uint32_t *__restrict__ tile_cnt) {
+    __shared__ uint32_t sm[UQ_THREADS / 32 + 1];
+    uint64_t base = (uint64_t) blockIdx.x * UQ_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < UQ_ITEMS; ++it) {
+        uint64_t i = base + (uint64_t) it * UQ_THREADS + threadIdx.x;
+        if (i < n && is_head<W>(recs, i)) ++c;
+    }
+    uint32_t total;
+    block_exclusive_scan<uint32_t, UQ_THREADS>(c, &total, sm);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+// writes unique records and the position of each run head in the sorted array (head_pos has U+1 entries; the last
+// one, = n, is written by the host wrapper)
+template<int W>
+__global__ void __launch_bounds__(UQ_THREADS) unique_write_kernel(const uint64_t *__restrict__ recs, uint64_t n,
+                                                                 const uint32_t *__restrict__ tile_off, uint64_t *__restrict__ out,
+                                                                 uint32_t *__restrict__ head_pos) {
+    __shared__ uint32_t sm[UQ_THREADS / 32 + 1];
+    uint64_t base = (uint64_t) blockIdx.x * UQ_TILE + (uint64_t) threadIdx.x * UQ_ITEMS;
+    bool h[UQ_ITEMS];
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < UQ_ITEMS; ++it) {
+        uint64_t i = base + it;
+        h[it] = (i < n) && is_head<W>(recs, i);
+        c += h[it];
+    }
+    uint32_t total;
+    uint32_t pos = block_exclusive_scan<uint32_t, UQ_THREADS>(c, &total, sm) + tile_off[blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < UQ_ITEMS; ++it) {
+        if (h[it]) {
+            uint64_t r[W];
+            load_rec<W>(recs, base + it, r);
+            store_rec<W>(out, pos, r);
+            head_pos[pos] = (uint32_t) (base + it);
+            ++pos;
+        }
+    }
+}
+
+// counts[i] = run length; self-reverse-complement records count twice in the fwd+RC canonical mode
+// (coverage_hash_map_builder.hpp:31-36: both streams see the window and both copies are minimal)
+template<int W>
+__global__ void counts_kernel(const uint32_t *__restrict__ head_pos, const uint64_t *__restrict__ recs, uint64_t u, int K,
+                              int double_palindromes, uint32_t *__restrict__ counts) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    uint32_t c = head_pos[i + 1] - head_pos[i];
+    if (double_palindromes) {
+        uint64_t x[W], r[W];
+        load_rec<W>(recs, i, x);
+        kmer_rc<W>(x, K, r);
+        if (kmer_eq<W>(x, r)) c *= 2;
+    }
+    counts[i] = c;
+}
+
+// bucket_starts[b] = index of the first record of bucket b (records are sorted by bucket)
+template<int W>
+__global__ void bucket_starts_kernel(const uint64_t *__restrict__ recs, uint64_t u, uint32_t B, uint64_t *__restrict__ starts) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    uint64_t r[W];
+    load_rec<W>(recs, i, r);
+    uint32_t b = kmer_bucket<W>(r, B);
+    if (i == 0) {
+        for (uint32_t t = 0; t <= b; ++t) starts[t] = 0;
+    } else {
+        uint64_t q[W];
+        load_rec<W>(recs, i - 1, q);
+        uint32_t pb = kmer_bucket<W>(q, B);
+        for (uint32_t t = pb + 1; t <= b; ++t) starts[t] = i;
+    }
+    if (i == u - 1)
+        for (uint32_t t = b + 1; t <= B; ++t) starts[t] = u;
+}
+
+template<int W>
+__global__ void last_is_marker_kernel(const uint64_t *__restrict__ recs, uint64_t u, uint32_t *__restrict__ flag) {
+    uint64_t r[W];
+    load_rec<W>(recs, u - 1, r);
+    bool m = true;
+#pragma unroll
+    for (int j = 0; j < W; ++j) m &= (r[j] == ~0ULL);
+    *flag = m ? 1u : 0u;
+}
+
+// Sort + unique + counts + bucket table.  `inst` (n x W) is consumed.
+template<int W>
+static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
+                               bool double_palindromes, bool drop_marker) {
+    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    DevBuf<uint64_t> scratch(ctx, n * W);
+    uint64_t *sorted = radix_sort_records<W>(ctx, inst.p, scratch.p, n, K, B, drop_marker);
+
+    unsigned tiles = div_up(n, UQ_TILE);
+    DevBuf<uint32_t> tile_cnt(ctx, tiles);
+    DevBuf<uint32_t> total_dev(ctx, 2);
+    LAUNCH(ctx, unique_count_kernel<W>, tiles, UQ_THREADS, 0, sorted, n, tile_cnt.p);
+    exclusive_scan<uint32_t>(ctx, tile_cnt.p, tiles, total_dev.p);
+    uint32_t u32 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&u32, total_dev.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    uint64_t u = u32;
+
+    sb200_kmers *s = new sb200_kmers();
+    s->ctx = ctx; s->k = (unsigned) K; s->words = W; s->num_buckets = B; s->instances = n;
+    s->data.alloc(ctx, u * W);
+    DevBuf<uint32_t> head_pos(ctx, u + 1);
+    LAUNCH(ctx, unique_write_kernel<W>, tiles, UQ_THREADS, 0, sorted, n, tile_cnt.p, s->data.p, head_pos.p);
+    uint32_t n32 = (uint32_t) n;
+    CUDA_CHECK(cudaMemcpyAsync(head_pos.p + u, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (drop_marker) {
+        LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, s->data.p, u, total_dev.p + 1);
+        uint32_t flag = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&flag, total_dev.p + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (flag) {
+            --u;
+            if (u == 0) {
+                delete s;
+                SB200_REQUIRE(false, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+            }
+        }
+    }
+    s->size = u;
+    if (want_counts) {
+        s->counts.alloc(ctx, u);
+        LAUNCH(ctx, counts_kernel<W>, div_up(u, 256), 256, 0, head_pos.p, s->data.p, u, K, double_palindromes ? 1 : 0, s->counts.p);
+    }
+    s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
+    LAUNCH(ctx, bucket_starts_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, B, s->bucket_starts.p);
+    s->bucket_starts_host.resize((size_t) B + 1);
+    CUDA_CHECK(cudaMemcpyAsync(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    inst.release();
+    return s;
+}
+
+template<int W>
+static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc, uint32_t B) {
+    int mode = canonical_only ? (add_rc ? MODE_CANON_RC : MODE_CANON_FWD) : (add_rc ? MODE_ALL_RC : MODE_ALL_FWD);
+    uint32_t mult = (mode == MODE_ALL_RC) ? 2 : 1;
+    DevBuf<uint64_t> off(ctx, rd->n_reads + 1);
+    DevBuf<uint64_t> total_dev(ctx, 1);
+    LAUNCH(ctx, window_count_kernel, div_up(rd->n_reads, 256), 256, 0, rd->len.p, rd->n_reads, (uint32_t) K, mult, off.p);
+    exclusive_scan<uint64_t>(ctx, off.p, rd->n_reads, total_dev.p);
+    uint64_t n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    DevBuf<uint64_t> inst(ctx, n * W);
+    unsigned warps_per_block = 8;
+    unsigned grid = (unsigned) std::min<uint64_t>((rd->n_reads + warps_per_block - 1) / warps_per_block, (uint64_t) ctx->num_sms * 32);
+    LAUNCH(ctx, extract_reads_kernel<W>, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, off.p, inst.p);
+    return finish_set<W>(ctx, inst, n, K, B, true, mode == MODE_CANON_RC, mode == MODE_CANON_FWD);
+}
+
+sb200_kmers *count_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B) {
+    SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
+    SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
+    switch ((K + 31) / 32) {
+        case 1: return count_reads_w<1>(ctx, rd, (int) K, canonical_only, add_rc, B);
+        case 2: return count_reads_w<2>(ctx, rd, (int) K, canonical_only, add_rc, B);
+        case 3: return count_reads_w<3>(ctx, rd, (int) K, canonical_only, add_rc, B);
+        default: return count_reads_w<4>(ctx, rd, (int) K, canonical_only, add_rc, B);
+    }
+}
+
+template<int WS, int W>
+static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) {
+    int k = (int) kp->k - 1;
+    uint64_t n = kp->size * 2;
+    DevBuf<uint64_t> inst(ctx, n * W);
+    auto kfn = derive_kernel<WS, W>;
+    LAUNCH(ctx, kfn, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, inst.p);
+    sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false);
+    s->instances = 0;
+    return s;
+}
+
+sb200_kmers *derive_kmers(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B) {
+    SB200_REQUIRE(kp->k >= 2, "source k-mers too short");
+    SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
+    int WS = (int) kp->words, W = (int) ((kp->k - 1 + 31) / 32);
+    if (WS == 1) return derive_w<1, 1>(ctx, kp, B);
+    if (WS == 2 && W == 1) return derive_w<2, 1>(ctx, kp, B);
+    if (WS == 2) return derive_w<2, 2>(ctx, kp, B);
+    if (WS == 3 && W == 2) return derive_w<3, 2>(ctx, kp, B);
+    if (WS == 3) return derive_w<3, 3>(ctx, kp, B);
+    if (WS == 4 && W == 3) return derive_w<4, 3>(ctx, kp, B);
+    return derive_w<4, 4>(ctx, kp, B);
+}
+
+}  // namespace sb200

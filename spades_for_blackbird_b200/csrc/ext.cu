@@ -1,0 +1,233 @@
+// ext.cu — DeBruijnExtensionIndex payload (one InOutMask byte per k-mer, in MPHF-index order) and EarlyTipClipper.
+//
+// Replaces (reference file:line):
+//   DeBruijnExtensionIndexBuilder::FillExtensionsFromIndex   C/utils/extension_index/kmer_extension_index_builder.hpp:44-59
+//   InOutMask::AddOutgoing / AddIncoming                     C/utils/extension_index/kmer_extension_index.hpp:92-106
+//   InvertableKeyWithHash::CountIdx                          C/utils/ph_map/key_with_hash.hpp:119-127
+//   EarlyTipClipperProcessor / RemoveInconsistentForwardLinks C/assembly_graph/construction/early_simplification.hpp:20-152
+// One thread per stored (k+1)-mer: two canonicalisations, two MPHF lookups (bit-vectors and rank samples are a few
+// tens of MB and stay L2-resident), two byte-wide ORs done as 32-bit atomicOr on the containing word.
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "kmer_set.cuh"
+#include "mphf.cuh"
+#include "radix_sort.cuh"
+
+namespace sb200 {
+
+MphfDev mphf_dev(const sb200_mphf *m);
+
+__device__ __forceinline__ void mask_or(uint8_t *masks, uint64_t idx, uint32_t bit) {
+    atomicOr(reinterpret_cast<unsigned int *>(masks + (idx & ~3ULL)), (1u << bit) << (8 * (idx & 3)));
+}
+__device__ __forceinline__ void mask_and_not(uint8_t *masks, uint64_t idx, uint32_t bits) {
+    atomicAnd(reinterpret_cast<unsigned int *>(masks + (idx & ~3ULL)), ~(bits << (8 * (idx & 3))));
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *__restrict__ idx,
+                                                            uint32_t *__restrict__ inv) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t r[W];
+    load_rec<W>(kmers, i, r);
+    uint32_t id = (uint32_t) mphf_lookup<W>(m, r);
+    idx[i] = id;
+    inv[id] = (uint32_t) i;
+}
+
+template<int WS, int W>
+__global__ void __launch_bounds__(256) fill_masks_kernel(MphfDev m, const uint64_t *__restrict__ kpomers, uint64_t n, int k, uint8_t *__restrict__ masks) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x[WS], a[W];
+    load_rec<WS>(kpomers, i, x);
+    uint32_t pnucl = kmer_base(x, 0), nnucl = kmer_base(x, k);
+    bool minimal;
+    kmer_subwindow<WS, W>(x, 0, k, a);
+    uint64_t ia = mphf_lookup_oriented<W>(m, a, k, &minimal);
+    mask_or(masks, ia, minimal ? nnucl : 7u - nnucl);                 // AddOutgoing(nnucl, as_is)
+    kmer_subwindow<WS, W>(x, 1, k, a);
+    uint64_t ib = mphf_lookup_oriented<W>(m, a, k, &minimal);
+    mask_or(masks, ib, minimal ? pnucl + 4u : 7u - (pnucl + 4u));    // AddIncoming(pnucl, as_is)
+}
+
+template<int WS, int W>
+static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf) {
+    sb200_ext *e = new sb200_ext();
+    e->ctx = ctx; e->k = kmers->k; e->size = kmers->size;
+    uint64_t padded = (kmers->size + 3) & ~3ULL;
+    e->masks.alloc(ctx, padded + 4);
+    e->masks.zero();
+    e->idx.alloc(ctx, kmers->size);
+    e->inv.alloc(ctx, kmers->size);
+    MphfDev m = mphf_dev(mphf);
+    LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p);
+    auto kfn = fill_masks_kernel<WS, W>;
+    LAUNCH(ctx, kfn, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p);
+    return e;
+}
+
+sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf) {
+    SB200_REQUIRE(kpomers->k == kmers->k + 1, "kpomers.k() must equal index.k() + 1");
+    SB200_REQUIRE(mphf->total == kmers->size && mphf->words == kmers->words, "MPHF was not built over this k-mer set");
+    int WS = (int) kpomers->words, W = (int) kmers->words;
+    if (WS == 1) return build_ext_w<1, 1>(ctx, kpomers, kmers, mphf);
+    if (WS == 2 && W == 1) return build_ext_w<2, 1>(ctx, kpomers, kmers, mphf);
+    if (WS == 2) return build_ext_w<2, 2>(ctx, kpomers, kmers, mphf);
+    if (WS == 3 && W == 2) return build_ext_w<3, 2>(ctx, kpomers, kmers, mphf);
+    if (WS == 3) return build_ext_w<3, 3>(ctx, kpomers, kmers, mphf);
+    if (WS == 4 && W == 3) return build_ext_w<4, 3>(ctx, kpomers, kmers, mphf);
+    return build_ext_w<4, 4>(ctx, kpomers, kmers, mphf);
+}
+
+// ---- early tip clipper ---------------------------------------------------------------------------------------------
+// The reference walks the k-mer file sequentially and mutates masks as it goes; a tip's vertices all have a unique
+// predecessor, so they are reachable only from their own junction and no other walk can observe their removal.
+// Deciding every junction on the untouched masks and isolating afterwards therefore gives the reference's
+// single-thread result (tests/test_gpu_parity.py pins it against the -t 1 reference run).
+__constant__ int8_t c_unique_next[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};
+
+__device__ __forceinline__ bool mask_unique(uint32_t nib) { return nib && !(nib & (nib - 1)); }
+
+template<int W>
+__device__ __forceinline__ uint32_t oriented_mask(const MphfDev &m, const uint8_t *masks, const uint64_t *x, int k, uint64_t *id_out) {
+    bool minimal;
+    uint64_t id = mphf_lookup_oriented<W>(m, x, k, &minimal);
+    *id_out = id;
+    uint32_t v = masks[id];
+    return minimal ? v : mask_conj(v);
+}
+
+// Phase 1: for every oriented k-mer with >= 2 outgoing edges walk each branch (<= bound vertices); tips shorter than
+// the longest branch are removed.  Vertices to isolate are recorded in `kill` (one byte per k-mer index) and applied
+// by tipclip_apply_kernel, so that every decision sees the same snapshot.
+template<int W>
+__global__ void __launch_bounds__(128) tipclip_find_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k,
+                                                          const uint8_t *__restrict__ masks, uint32_t bound, uint8_t *__restrict__ kill,
+                                                          uint8_t *__restrict__ tipped /* 2 bits per file index: strand 0/1 */,
+                                                          unsigned long long *__restrict__ removed) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    uint64_t i = t >> 1;
+    int strand = (int) (t & 1);
+    uint64_t y[W], x[W];
+    load_rec<W>(kmers, i, y);
+    if (strand) kmer_rc<W>(y, k, x);
+    else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) x[j] = y[j];
+    }
+    uint64_t id0;
+    uint32_t mask = oriented_mask<W>(m, masks, x, k, &id0);
+    if (__popc(mask & 15u) < 2) return;
+    // pass 1: branch lengths (0 = not a tip)
+    uint32_t len[4] = {0, 0, 0, 0};
+    uint32_t maxlen = 0;
+    for (uint32_t c = 0; c < 4; ++c) {
+        if (!(mask & (1u << c))) continue;
+        uint64_t cur[W], nxt[W];
+        kmer_shl<W>(x, k, c, cur);
+        uint32_t sz = 0;
+        uint64_t id;
+        uint32_t mk = oriented_mask<W>(m, masks, cur, k, &id);
+        while (sz < bound && mask_unique(mk >> 4) && mask_unique(mk & 15u)) {   // FindForward, :110-121
+            ++sz;
+            kmer_shl<W>(cur, k, (uint32_t) c_unique_next[mk & 15u], nxt);
+#pragma unroll
+            for (int j = 0; j < W; ++j) cur[j] = nxt[j];
+            mk = oriented_mask<W>(m, masks, cur, k, &id);
+        }
+        ++sz;
+        if (!mask_unique(mk >> 4) || (mk & 15u) != 0) sz = 0;
+        len[c] = sz;
+        uint32_t l = sz == 0 ? 0xFFFFFFFFu : sz;
+        if (l > maxlen) maxlen = l;
+    }
+    // pass 2: isolate the tips shorter than the longest branch (RemoveTips, :131-139)
+    uint32_t rem = 0;
+    for (uint32_t c = 0; c < 4; ++c) {
+        if (!(mask & (1u << c)) || len[c] == 0 || len[c] >= maxlen) continue;
+        uint64_t cur[W], nxt[W];
+        kmer_shl<W>(x, k, c, cur);
+        for (uint32_t s = 0; s < len[c]; ++s) {
+            uint64_t id;
+            uint32_t mk = oriented_mask<W>(m, masks, cur, k, &id);
+            kill[id] = 1;
+            if (s + 1 < len[c]) {
+                kmer_shl<W>(cur, k, (uint32_t) c_unique_next[mk & 15u], nxt);
+#pragma unroll
+                for (int j = 0; j < W; ++j) cur[j] = nxt[j];
+            }
+        }
+        rem += len[c];
+    }
+    if (rem) {
+        atomicAdd(removed, (unsigned long long) rem);
+        tipped[t] = 1;
+    }
+}
+
+__global__ void tipclip_apply_kernel(uint8_t *__restrict__ masks, const uint8_t *__restrict__ kill, uint64_t n) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && kill[i]) masks[i] = 0;
+}
+
+// Phase 2: RemoveInconsistentForwardLinks (:20-35) on the junctions that lost a tip.
+template<int W>
+__global__ void __launch_bounds__(128) tipclip_links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k, uint8_t *__restrict__ masks,
+                                                           const uint8_t *__restrict__ tipped) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n || !tipped[t]) return;
+    uint64_t i = t >> 1;
+    int strand = (int) (t & 1);
+    uint64_t y[W], x[W];
+    load_rec<W>(kmers, i, y);
+    if (strand) kmer_rc<W>(y, k, x);
+    else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) x[j] = y[j];
+    }
+    bool minimal;
+    uint64_t id0 = mphf_lookup_oriented<W>(m, x, k, &minimal);
+    uint32_t raw = masks[id0];
+    uint32_t mask = minimal ? raw : mask_conj(raw);
+    uint32_t first = kmer_base(x, 0);
+    uint32_t del = 0;
+    for (uint32_t c = 0; c < 4; ++c) {
+        if (!(mask & (1u << c))) continue;
+        uint64_t nx[W], id;
+        kmer_shl<W>(x, k, c, nx);
+        uint32_t nm = oriented_mask<W>(m, masks, nx, k, &id);
+        if (!(nm & (1u << (4 + first)))) del |= 1u << (minimal ? c : 7u - c);   // DeleteOutgoing(kh, c)
+    }
+    if (del) mask_and_not(masks, id0, del);
+}
+
+template<int W>
+static uint64_t tipclip_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound) {
+    uint64_t n = kmers->size;
+    MphfDev m = mphf_dev(mphf);
+    DevBuf<uint8_t> kill(ctx, n + 4), tipped(ctx, 2 * n + 4);
+    DevBuf<unsigned long long> removed(ctx, 1);
+    kill.zero(); tipped.zero(); removed.zero();
+    uint32_t b32 = bound > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t) bound;
+    LAUNCH(ctx, tipclip_find_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, b32, kill.p, tipped.p, removed.p);
+    LAUNCH(ctx, tipclip_apply_kernel, div_up(n, 256), 256, 0, ext->masks.p, kill.p, n);
+    LAUNCH(ctx, tipclip_links_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, tipped.p);
+    unsigned long long r = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&r, removed.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return r;
+}
+
+uint64_t tipclip(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound) {
+    switch (kmers->words) {
+        case 1: return tipclip_w<1>(ctx, kmers, mphf, ext, bound);
+        case 2: return tipclip_w<2>(ctx, kmers, mphf, ext, bound);
+        case 3: return tipclip_w<3>(ctx, kmers, mphf, ext, bound);
+        default: return tipclip_w<4>(ctx, kmers, mphf, ext, bound);
+    }
+}
+
+}  // namespace sb200

@@ -1,0 +1,60 @@
+// kmer_set.cuh — device-resident sorted-unique k-mer sets (the GPU counterpart of kmers::KMerDiskStorage,
+// C/utils/kmer_mph/kmer_index_builder.hpp:48-191) and the handles the C ABI passes around.
+#pragma once
+#include "common.cuh"
+
+struct sb200_reads {
+    sb200_ctx *ctx = nullptr;
+    uint64_t n_reads = 0, n_words = 0, n_bases = 0;
+    uint32_t max_len = 0;
+    DevBuf<uint64_t> words;      // packed bases, every read word-aligned
+    DevBuf<uint64_t> word_off;   // n_reads + 1
+    DevBuf<uint32_t> len;        // n_reads
+};
+
+struct sb200_kmers {
+    sb200_ctx *ctx = nullptr;
+    unsigned k = 0, words = 0, num_buckets = 0;
+    uint64_t size = 0;
+    uint64_t instances = 0;              // window instances that were counted (0 for derived sets)
+    DevBuf<uint64_t> data;               // size x words, file order: bucket, then array_less
+    DevBuf<uint32_t> counts;             // multiplicity per record (empty for derived sets)
+    DevBuf<uint64_t> bucket_starts;      // num_buckets + 1 (device)
+    std::vector<uint64_t> bucket_starts_host;
+};
+
+struct sb200_mphf {
+    sb200_ctx *ctx = nullptr;
+    unsigned num_buckets = 0, words = 0;
+    uint64_t total = 0;
+    // Per (bucket, level) geometry, BooPHF layout: level l of bucket b has domain[b*25+l] bits and
+    // nchar = 1 + domain/64 words starting at word_off[b*25+l]; its rank samples (one per 8 words) start at
+    // rank_off[b*25+l].  A bucket's levels are contiguous, so a running popcount over the bucket's words is
+    // BooPHF's cumulative rank offset.
+    std::vector<uint64_t> domain_host, word_off_host, rank_off_host, bucket_word_start_host;
+    std::vector<uint64_t> segment_starts_host;   // num_buckets + 1, with the reference's last-entry quirk
+    std::vector<uint64_t> lastbitsetrank_host, bucket_sizes_host;
+    uint64_t total_words = 0, total_ranks = 0;
+    DevBuf<uint64_t> domain, word_off, rank_off, segment_starts;   // device copies of the tables
+    DevBuf<uint64_t> bits;    // all bit-vectors
+    DevBuf<uint64_t> ranks;   // all rank samples
+    uint64_t final_level_keys = 0;
+};
+
+struct sb200_ext {   // DeBruijnExtensionIndex payload: masks in MPHF-index order (+ successor links for the walks)
+    sb200_ctx *ctx = nullptr;
+    unsigned k = 0;
+    uint64_t size = 0;
+    DevBuf<uint8_t> masks;      // size bytes (padded to a multiple of 4), PerfectHashMap::data_
+    DevBuf<uint32_t> idx;       // MPHF index of every k-mer in file order
+    DevBuf<uint32_t> inv;       // file position of every MPHF index
+};
+
+struct sb200_unitigs {
+    sb200_ctx *ctx = nullptr;
+    unsigned k = 0;
+    uint64_t count = 0, n_loops = 0, total_bases = 0, total_words = 0;
+    DevBuf<uint64_t> word_off;   // count + 1: unitig i occupies words [word_off[i], word_off[i+1])
+    DevBuf<uint32_t> len;        // count
+    DevBuf<uint64_t> words;      // packed 2-bit, same layout as reads
+};

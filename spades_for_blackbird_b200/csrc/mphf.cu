@@ -1,0 +1,307 @@
+// mphf.cu — BooPHF-identical minimal perfect hash, one per hash bucket, built level-synchronously on the GPU.
+//
+// Replaces KMerIndexBuilder::BuildIndex(index, storage) (C/utils/kmer_mph/kmer_index_builder.hpp:383-433) and
+// boomphf::mphf::build/processLevel/processHash/insertIntoLevel/build_ranks (E/boomphf/BooPHF.h:423-441,677-696,
+// 634-675,626-632,289-301).  All buckets advance through a level together: one kernel per level drops the keys that
+// were placed at the previous level (their bit survived collision clearing), hashes the rest with the level's
+// function and sets bits with atomicOr; a second hit on a bit is recorded in a collision vector instead of being
+// resolved in place, so "placed" is simply bit & ~collision and no pass over the bit-vectors is needed between
+// levels.  The order in which keys reach a level does not influence any bit, hence the active list is compacted
+// with a warp-aggregated atomic append instead of a scan.  Level sizes come from the host in double precision with
+// the reference's own expression, so the bit-vectors, rank samples and indices are bit-exact.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "kmer_set.cuh"
+#include "mphf.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+struct ActiveKey {
+    uint64_t s0, s1;   // BooPHF hash state (levels >= 2 advance it with xorshift128*)
+    uint32_t bucket;
+    uint32_t pad;
+};
+
+// level 0: hash every key, set its level-0 bit, start the active list (all keys, file order)
+template<int W>
+__global__ void __launch_bounds__(256) mphf_level0_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t B,
+                                                         const uint64_t *__restrict__ domain, const uint64_t *__restrict__ word_off,
+                                                         unsigned long long *__restrict__ bits, unsigned long long *__restrict__ coll,
+                                                         ActiveKey *__restrict__ active) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t r[W];
+    load_rec<W>(keys, i, r);
+    ActiveKey a;
+    a.bucket = kmer_bucket<W>(r, B);
+    a.pad = 0;
+    xxh3_128<W>(r, a.s0, a.s1);
+    uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS;
+    uint64_t pos = __umul64hi(a.s0, domain[t]);
+    uint64_t w = word_off[t] + (pos >> 6);
+    unsigned long long bit = 1ULL << (pos & 63);
+    unsigned long long old = atomicOr(&bits[w], bit);
+    if (old & bit) atomicOr(&coll[w], bit);
+    active[i] = a;
+}
+
+// level l >= 1: keep the keys that were not placed at level l-1, insert them into level l (if l is a bit level)
+__global__ void __launch_bounds__(256) mphf_level_kernel(int level, const ActiveKey *__restrict__ in, const uint32_t *__restrict__ n_in,
+                                                        ActiveKey *__restrict__ out, uint32_t *__restrict__ n_out,
+                                                        const uint64_t *__restrict__ domain, const uint64_t *__restrict__ word_off,
+                                                        unsigned long long *__restrict__ bits, unsigned long long *__restrict__ coll) {
+    const uint32_t n = *n_in;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = (uint64_t) blockIdx.x * blockDim.x; base < n; base += (uint64_t) gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool keep = false;
+        ActiveKey a;
+        if (i < n) a = in[i];
+        // Position this key probed at level-1.  For levels >= 2 the hash was xs_next() = new s1 + old s1, and after
+        // that call s0 holds the old s1, so it can be rebuilt from the saved state.
+        uint64_t prev_hash = 0;
+        if (i < n) {
+            if (level - 1 == 0) prev_hash = a.s0;
+            else if (level - 1 == 1) prev_hash = a.s1;
+            else prev_hash = a.s1 + a.s0;   // xs_next returned (new s1 + old s1); after the call s0 == old s1
+            uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS + (level - 1);
+            uint64_t pos = __umul64hi(prev_hash, domain[t]);
+            uint64_t w = word_off[t] + (pos >> 6);
+            unsigned long long bit = 1ULL << (pos & 63);
+            bool placed = (bits[w] & bit) && !(coll[w] & bit);
+            keep = !placed;
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, keep);
+        uint32_t slot = 0;
+        if (m) {
+            if (lane == (__ffs(m) - 1)) slot = atomicAdd(n_out, (uint32_t) __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+        }
+        if (keep) {
+            if (level < MPHF_LEVELS - 1) {
+                uint64_t h = (level == 1) ? a.s1 : xs_next(a.s0, a.s1);
+                uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS + level;
+                uint64_t pos = __umul64hi(h, domain[t]);
+                uint64_t w = word_off[t] + (pos >> 6);
+                unsigned long long bit = 1ULL << (pos & 63);
+                unsigned long long old = atomicOr(&bits[w], bit);
+                if (old & bit) atomicOr(&coll[w], bit);
+            }
+            out[slot + __popc(m & ((1u << lane) - 1u))] = a;
+        }
+    }
+}
+
+__global__ void mphf_clear_popc_kernel(unsigned long long *__restrict__ bits, const unsigned long long *__restrict__ coll, uint64_t nwords,
+                                       uint32_t *__restrict__ pc) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    unsigned long long v = bits[i] & ~coll[i];
+    bits[i] = v;
+    pc[i] = (uint32_t) __popcll(v);
+}
+
+// one block per (bucket, level): rank sample j = set bits in the bucket's words before word 8j of this level
+__global__ void mphf_ranks_kernel(const uint32_t *__restrict__ pc_scan, const uint64_t *__restrict__ word_off,
+                                  const uint64_t *__restrict__ rank_off, const uint64_t *__restrict__ nchar, uint64_t n_levels_total,
+                                  uint64_t *__restrict__ ranks) {
+    uint64_t t = blockIdx.x;
+    if (t >= n_levels_total) return;
+    uint64_t nc = nchar[t];
+    if (nc == 0) return;
+    uint64_t bucket_first = word_off[(t / MPHF_LEVELS) * MPHF_LEVELS];
+    uint32_t base = pc_scan[bucket_first];
+    uint64_t ns = (nc + 7) / 8;
+    for (uint64_t j = threadIdx.x; j < ns; j += blockDim.x)
+        ranks[rank_off[t] + j] = (uint64_t) (pc_scan[word_off[t] + 8 * j] - base);
+}
+
+__global__ void mphf_bucket_ends_kernel(const uint32_t *__restrict__ pc_scan, const uint64_t *__restrict__ word_off, uint32_t B,
+                                        uint64_t total_words, uint32_t *__restrict__ ends) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    ends[b] = pc_scan[b < B ? word_off[(uint64_t) b * MPHF_LEVELS] : total_words];
+}
+
+template<int W>
+static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks) {
+    sb200_mphf *m = new sb200_mphf();
+    m->ctx = ctx;
+    uint32_t B = ks->num_buckets;
+    m->num_buckets = B; m->words = W; m->total = ks->size;
+    SB200_REQUIRE(ks->size < (1ull << 32), "more than 2^32-1 k-mers on one GPU: shard the input");
+    size_t NL = (size_t) B * MPHF_LEVELS;
+    m->domain_host.assign(NL, 0); m->word_off_host.assign(NL, 0); m->rank_off_host.assign(NL, 0);
+    std::vector<uint64_t> nchar(NL, 0);
+    m->segment_starts_host.assign((size_t) B + 1, 0);
+    m->lastbitsetrank_host.assign(B, 0);
+    m->bucket_sizes_host.assign(B, 0);
+    uint64_t words = 0, ranks = 0;
+    for (uint32_t b = 0; b < B; ++b) {
+        uint64_t n = ks->bucket_starts_host[b + 1] - ks->bucket_starts_host[b];
+        m->segment_starts_host[b + 1] = n;
+        m->bucket_sizes_host[b] = n;
+        if (n > 0) {
+            // boomphf::mphf::init + setup, BooPHF.h:409-421,575-588 (gamma = 4.0, kmer_index_builder.hpp:401-404)
+            double gamma = 4.0;
+            uint64_t hash_domain = (uint64_t) (size_t) ceil(double(n) * gamma);
+            double p = 1.0 - pow(((gamma * (double) n - 1) / (gamma * (double) n)), (double) (n - 1));
+            for (int l = 0; l < MPHF_LEVELS; ++l) {
+                uint64_t d = ((uint64_t(hash_domain * pow(p, l)) + 63) / 64) * 64;
+                if (d == 0) d = 64;
+                size_t t = (size_t) b * MPHF_LEVELS + l;
+                m->domain_host[t] = d;
+                nchar[t] = 1 + d / 64;                       // bitVector(n): _nchar = 1 + n/64, BooPHF.h:144-148
+                m->word_off_host[t] = words;
+                m->rank_off_host[t] = ranks;
+                words += nchar[t];
+                ranks += (nchar[t] + 7) / 8;                 // build_ranks: one sample per 512 bits, :289-301
+            }
+        } else {
+            for (int l = 0; l < MPHF_LEVELS; ++l) {
+                size_t t = (size_t) b * MPHF_LEVELS + l;
+                m->word_off_host[t] = words;
+                m->rank_off_host[t] = ranks;
+            }
+        }
+    }
+    // kmer_index_builder.hpp:427-428 — the prefix loop stops at i < segments: the last entry stays a bucket size
+    for (uint32_t i = 1; i < B; ++i) m->segment_starts_host[i] += m->segment_starts_host[i - 1];
+    m->total_words = words; m->total_ranks = ranks;
+
+    m->domain.alloc(ctx, NL); m->word_off.alloc(ctx, NL); m->rank_off.alloc(ctx, NL);
+    m->segment_starts.alloc(ctx, (size_t) B + 1);
+    DevBuf<uint64_t> nchar_dev(ctx, NL);
+    CUDA_CHECK(cudaMemcpyAsync(m->domain.p, m->domain_host.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(m->word_off.p, m->word_off_host.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(m->rank_off.p, m->rank_off_host.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(nchar_dev.p, nchar.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(m->segment_starts.p, m->segment_starts_host.data(), ((size_t) B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    m->bits.alloc(ctx, words + 1); m->bits.zero();
+    m->ranks.alloc(ctx, ranks + 1);
+    DevBuf<uint64_t> coll(ctx, words + 1); coll.zero();
+
+    uint64_t n = ks->size;
+    DevBuf<ActiveKey> act_a(ctx, n), act_b(ctx, n);
+    DevBuf<uint32_t> counters(ctx, MPHF_LEVELS + 1); counters.zero();
+    uint32_t n32 = (uint32_t) n;
+    CUDA_CHECK(cudaMemcpyAsync(counters.p, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
+           (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
+    ActiveKey *src = act_a.p, *dst = act_b.p;
+    unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256), (uint64_t) ctx->num_sms * 16);
+    for (int l = 1; l < MPHF_LEVELS; ++l) {
+        LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p);
+        std::swap(src, dst);
+    }
+    uint32_t final_keys = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&final_keys, counters.p + (MPHF_LEVELS - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+
+    DevBuf<uint32_t> pc(ctx, words + 1);
+    LAUNCH(ctx, mphf_clear_popc_kernel, div_up(words + 1, 256), 256, 0, (unsigned long long *) m->bits.p,
+           (const unsigned long long *) coll.p, words + 1, pc.p);
+    exclusive_scan<uint32_t>(ctx, pc.p, words + 1, nullptr);
+    LAUNCH(ctx, mphf_ranks_kernel, (unsigned) NL, 128, 0, pc.p, m->word_off.p, m->rank_off.p, nchar_dev.p, (uint64_t) NL, m->ranks.p);
+    // _lastbitsetrank per bucket = set bits of the whole bucket
+    std::vector<uint32_t> ends(B + 1, 0);
+    DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
+    LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pc.p, m->word_off.p, B, words, ends_dev.p);
+    CUDA_CHECK(cudaMemcpyAsync(ends.data(), ends_dev.p, ((size_t) B + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];
+    m->final_level_keys = final_keys;
+    if (final_keys != 0) {
+        delete m;
+        SB200_REQUIRE(false, "BooPHF exact-map level reached (probability ~1e-16 per key): not supported on the GPU path");
+    }
+    return m;
+}
+
+sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks) {
+    switch (ks->words) {
+        case 1: return mphf_build_w<1>(ctx, ks);
+        case 2: return mphf_build_w<2>(ctx, ks);
+        case 3: return mphf_build_w<3>(ctx, ks);
+        default: return mphf_build_w<4>(ctx, ks);
+    }
+}
+
+MphfDev mphf_dev(const sb200_mphf *m) {
+    MphfDev d;
+    d.domain = m->domain.p; d.word_off = m->word_off.p; d.rank_off = m->rank_off.p; d.segment_starts = m->segment_starts.p;
+    d.bits = m->bits.p; d.ranks = m->ranks.p; d.num_buckets = m->num_buckets;
+    return d;
+}
+
+template<int W>
+__global__ void mphf_lookup_kernel(MphfDev m, const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict__ out) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t r[W];
+    load_rec<W>(recs, i, r);
+    out[i] = mphf_lookup<W>(m, r);
+}
+
+// KMerIndex::seq_idx for n records resident on the device
+void mphf_lookup_device(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *recs_dev, uint64_t n, uint64_t *out_dev) {
+    MphfDev d = mphf_dev(m);
+    unsigned g = div_up(n, 256);
+    if (n == 0) return;
+    switch (m->words) {
+        case 1: LAUNCH(ctx, mphf_lookup_kernel<1>, g, 256, 0, d, recs_dev, n, out_dev); break;
+        case 2: LAUNCH(ctx, mphf_lookup_kernel<2>, g, 256, 0, d, recs_dev, n, out_dev); break;
+        case 3: LAUNCH(ctx, mphf_lookup_kernel<3>, g, 256, 0, d, recs_dev, n, out_dev); break;
+        default: LAUNCH(ctx, mphf_lookup_kernel<4>, g, 256, 0, d, recs_dev, n, out_dev); break;
+    }
+}
+
+// KMerIndex::serialize (kmer_index.hpp:99-105) of per-bucket mphf::save (BooPHF.h:514-532) of bitVector::save (:316-323)
+uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out) {
+    sb200_ctx *ctx = m->ctx;
+    std::vector<uint64_t> bits(m->total_words + 1), ranks(m->total_ranks + 1);
+    if (out) {
+        CUDA_CHECK(cudaMemcpyAsync(bits.data(), m->bits.p, m->total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(ranks.data(), m->ranks.p, m->total_ranks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t total = 0;
+    uint8_t *p = out;
+    auto put = [&](const void *src, size_t n) {
+        if (p) { memcpy(p, src, n); p += n; }
+        total += n;
+    };
+    uint64_t nseg = m->num_buckets;
+    put(&nseg, 8);
+    for (uint32_t b = 0; b < m->num_buckets; ++b) {
+        double gamma = 4.0;
+        int nb_levels = MPHF_LEVELS;
+        uint64_t nelem = m->bucket_sizes_host[b];
+        put(&gamma, 8);
+        put(&nb_levels, 4);
+        put(&m->lastbitsetrank_host[b], 8);
+        put(&nelem, 8);
+        for (int l = 0; l < MPHF_LEVELS; ++l) {
+            size_t t = (size_t) b * MPHF_LEVELS + l;
+            uint64_t size = m->domain_host[t];
+            uint64_t nchar = size ? 1 + size / 64 : 0;   // empty bucket: default-constructed bit-vectors
+            uint64_t nr = (nchar + 7) / 8;
+            put(&size, 8);
+            put(&nchar, 8);
+            if (nchar) put(bits.data() + m->word_off_host[t], nchar * 8);
+            put(&nr, 8);
+            if (nr) put(ranks.data() + m->rank_off_host[t], nr * 8);
+        }
+        uint64_t nf = 0;
+        put(&nf, 8);
+    }
+    put(m->segment_starts_host.data(), ((size_t) m->num_buckets + 1) * 8);
+    return total;
+}
+
+}  // namespace sb200

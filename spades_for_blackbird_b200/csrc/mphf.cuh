@@ -1,0 +1,66 @@
+// mphf.cuh — device-side lookup in the segmented BooPHF (KMerIndex::seq_idx, C/utils/kmer_mph/kmer_index.hpp:85-90;
+// boomphf::mphf::lookup / getLevel / bitVector::rank, E/boomphf/BooPHF.h:465-487,609-623,303-314).
+#pragma once
+#include "kmer_ops.cuh"
+
+namespace sb200 {
+
+constexpr int MPHF_LEVELS = 25;   // boomphf default nb_levels; level 24 is the exact map (never reached in practice)
+
+struct MphfDev {
+    const uint64_t *domain;          // [B*25] bits per level
+    const uint64_t *word_off;        // [B*25] first word of the level's bit-vector
+    const uint64_t *rank_off;        // [B*25] first rank sample of the level
+    const uint64_t *segment_starts;  // [B+1]
+    const uint64_t *bits;
+    const uint64_t *ranks;
+    uint32_t num_buckets;
+};
+
+// XorshiftHashFunctors::next (BooPHF.h:94-100)
+DEVINL uint64_t xs_next(uint64_t &s0, uint64_t &s1) {
+    uint64_t a = s0;
+    const uint64_t b = s1;
+    s0 = b;
+    a ^= a << 23;
+    s1 = a ^ b ^ (a >> 17) ^ (b >> 26);
+    return s1 + b;
+}
+
+#ifdef __CUDACC__
+// Returns the global index (segment start + rank) or ~0 if the key falls through all bit levels.
+template<int W>
+__device__ __forceinline__ uint64_t mphf_lookup(const MphfDev &m, const uint64_t *rec) {
+    uint32_t b = kmer_bucket<W>(rec, m.num_buckets);
+    uint64_t s0, s1;
+    xxh3_128<W>(rec, s0, s1);   // {high64, low64}: level 0 uses high, level 1 low (kmer_index.hpp:38-39)
+    const uint64_t *dom = m.domain + (uint64_t) b * MPHF_LEVELS;
+    for (int l = 0; l < MPHF_LEVELS - 1; ++l) {
+        uint64_t h = (l == 0) ? s0 : (l == 1) ? s1 : xs_next(s0, s1);
+        uint64_t d = __ldg(dom + l);
+        if (d == 0) return ~0ULL;   // empty bucket: the reference's mphf is "not built"
+        uint64_t pos = __umul64hi(h, d);
+        const uint64_t *bv = m.bits + __ldg(m.word_off + (uint64_t) b * MPHF_LEVELS + l);
+        uint64_t word = __ldg(bv + (pos >> 6));
+        if ((word >> (pos & 63)) & 1ULL) {
+            uint64_t r = __ldg(m.ranks + __ldg(m.rank_off + (uint64_t) b * MPHF_LEVELS + l) + (pos >> 9));
+            uint64_t w0 = (pos >> 9) << 3, w1 = pos >> 6;
+            for (uint64_t w = w0; w < w1; ++w) r += __popcll(__ldg(bv + w));
+            r += __popcll(word & ((1ULL << (pos & 63)) - 1ULL));
+            return __ldg(m.segment_starts + b) + r;
+        }
+    }
+    return ~0ULL;
+}
+
+// Index of a k-mer in reading orientation: canonicalise, look up (InvertableKeyWithHash::CountIdx,
+// C/utils/ph_map/key_with_hash.hpp:119-127).  *minimal tells whether x itself is the stored form.
+template<int W>
+__device__ __forceinline__ uint64_t mphf_lookup_oriented(const MphfDev &m, const uint64_t *x, int k, bool *minimal) {
+    uint64_t c[W];
+    *minimal = kmer_canonical<W>(x, k, c);
+    return mphf_lookup<W>(m, c);
+}
+#endif
+
+}  // namespace sb200

@@ -1,0 +1,182 @@
+// radix_sort.cuh — stable LSD radix sort of fixed-width k-mer records (W uint64 words, AoS) into the reference's
+// file order: hash bucket first (KMerSegmentPolicy), then word-wise from word 0 (array_less).
+//
+// This replaces the reference's per-thread x per-bucket staging cells + libcxx::sort + loser-tree merge
+// (C/utils/kmer_mph/kmer_splitter.hpp:111-167, kmer_index_builder.hpp:281-365) with counting passes over
+// 8-bit digits: one histogram kernel, one scan of the (digit x tile) matrix and one stable scatter kernel per pass.
+// Only the significant 2K bits are visited; the bucket id is recomputed from the record in the last pass(es)
+// instead of being carried as payload, so records stay W words wide end to end.
+#pragma once
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BINS = 256;
+
+template<int W> struct RsItems { static constexpr int value = (W <= 2) ? 16 : 8; };
+
+// digit selector: word >= 0 -> byte `shift/8` of that word; word < 0 -> byte of the bucket id
+struct DigitSel {
+    int word;
+    int shift;
+    uint32_t num_buckets;
+    int marker;   // 1: an all-ones record is the "filtered out" marker and belongs to the last bucket (sorts last)
+};
+
+template<int W>
+__device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &d) {
+    if (d.word >= 0) return (uint32_t) (r[d.word] >> d.shift) & 0xFFu;
+    uint32_t b = kmer_bucket<W>(r, d.num_buckets);
+    if (d.marker) {
+        bool m = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) m &= (r[j] == ~0ULL);
+        if (m) b = d.num_buckets - 1;
+    }
+    return (b >> d.shift) & 0xFFu;
+}
+
+template<int W>
+__device__ __forceinline__ void load_rec(const uint64_t *__restrict__ base, uint64_t idx, uint64_t *r) {
+    if (W == 2) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + idx * 2);
+        r[0] = v.x; r[1] = v.y;
+    } else if (W == 4) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(base + idx * 4);
+        ulonglong2 a = p[0], b = p[1];
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] = base[idx * W + j];
+    }
+}
+
+template<int W>
+__device__ __forceinline__ void store_rec(uint64_t *__restrict__ base, uint64_t idx, const uint64_t *r) {
+    if (W == 2) {
+        *reinterpret_cast<ulonglong2 *>(base + idx * 2) = make_ulonglong2(r[0], r[1]);
+    } else if (W == 4) {
+        ulonglong2 *p = reinterpret_cast<ulonglong2 *>(base + idx * 4);
+        p[0] = make_ulonglong2(r[0], r[1]);
+        p[1] = make_ulonglong2(r[2], r[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) base[idx * W + j] = r[j];
+    }
+}
+
+// tile histogram: hist[bin * num_tiles + tile]
+template<int W>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ in, uint64_t n, DigitSel sel,
+                                                            uint32_t *__restrict__ hist, uint32_t num_tiles) {
+    constexpr int ITEMS = RsItems<W>::value;
+    __shared__ uint32_t sh[RS_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t base = (uint64_t) blockIdx.x * (RS_THREADS * ITEMS);
+#pragma unroll 4
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = base + (uint64_t) i * RS_THREADS + threadIdx.x;
+        if (idx < n) {
+            uint32_t d;
+            if (sel.word >= 0) {
+                d = (uint32_t) (in[idx * W + sel.word] >> sel.shift) & 0xFFu;
+            } else {
+                uint64_t r[W];
+                load_rec<W>(in, idx, r);
+                d = rs_digit<W>(r, sel);
+            }
+            atomicAdd(&sh[d], 1u);
+        }
+    }
+    __syncthreads();
+    hist[(uint64_t) threadIdx.x * num_tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// stable scatter: offsets[bin * num_tiles + tile] = exclusive scan of hist
+template<int W>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+                                                               DigitSel sel, const uint32_t *__restrict__ offsets,
+                                                               uint32_t num_tiles) {
+    constexpr int ITEMS = RsItems<W>::value;
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    uint64_t rec[ITEMS][W];
+    uint32_t dig[ITEMS];
+    uint32_t loc[ITEMS];
+    const uint64_t warp_base = (uint64_t) blockIdx.x * (RS_THREADS * ITEMS) + (uint64_t) warp * (32 * ITEMS);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+        bool ok = idx < n;
+        uint32_t d = 0;
+        if (ok) {
+            load_rec<W>(in, idx, rec[i]);
+            d = rs_digit<W>(rec[i], sel);
+        }
+        uint32_t valid = __ballot_sync(0xffffffffu, ok);
+        uint32_t peers = __match_any_sync(0xffffffffu, d) & valid;
+        uint32_t old = ok ? cnt[warp][d] : 0;
+        __syncwarp();
+        if (ok && (peers & lt_mask) == 0) cnt[warp][d] = old + __popc(peers);
+        __syncwarp();
+        dig[i] = d;
+        loc[i] = old + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    {   // one thread per bin: turn per-warp counts into per-warp global bases
+        uint32_t bin = threadIdx.x;
+        uint32_t base = offsets[(uint64_t) bin * num_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = cnt[w][bin];
+            cnt[w][bin] = base;
+            base += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+        if (idx < n) store_rec<W>(out, (uint64_t) cnt[warp][dig[i]] + loc[i], rec[i]);
+    }
+}
+
+// Sorts recs (n x W words) into (bucket, array_less) order.  `a` holds the input; `b` is scratch of the same size.
+// Returns the buffer (a or b) that holds the result.
+template<int W>
+uint64_t *radix_sort_records(sb200_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, int K, uint32_t num_buckets, bool marker = false) {
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    if (n <= 1) return a;
+    constexpr int ITEMS = RsItems<W>::value;
+    uint32_t num_tiles = div_up(n, RS_THREADS * ITEMS);
+    DevBuf<uint32_t> hist(ctx, (uint64_t) RS_BINS * num_tiles);
+    std::vector<DigitSel> passes;
+    for (int j = W - 1; j >= 0; --j) {
+        int bits = (j == W - 1) ? (2 * K - 64 * (W - 1)) : 64;
+        for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{j, s, 0, 0});
+    }
+    if (num_buckets > 1) {
+        int bbits = 0;
+        while ((1ull << bbits) < num_buckets) ++bbits;
+        for (int s = 0; s < bbits; s += 8) passes.push_back(DigitSel{-1, s, num_buckets, marker ? 1 : 0});
+    }
+    uint64_t *src = a, *dst = b;
+    for (const DigitSel &sel : passes) {
+        LAUNCH(ctx, rs_hist_kernel<W>, num_tiles, RS_THREADS, 0, src, n, sel, hist.p, num_tiles);
+        exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) RS_BINS * num_tiles, nullptr);
+        LAUNCH(ctx, rs_scatter_kernel<W>, num_tiles, RS_THREADS, 0, src, dst, n, sel, hist.p, num_tiles);
+        std::swap(src, dst);
+    }
+    return src;
+}
+
+}  // namespace sb200

