@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — reads -> condensed de Bruijn graph throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE.json configs[1] — synthetic 4.6 Mbp genome, 2x150 paired reads at 100x
+(1 533 333 pairs, 460 Mbp), 0.5 % substitutions, k = 55, 80 hash buckets (= the reference's 10 x 8 threads).
+A step = one pass of the whole hot path over that read set:
+    packed reads -> canonical (k+1)-mers -> sort/dedup(+counts) -> k-mers -> BooPHF MPHF -> extension masks -> unitigs
+`value`  : input bases / device time with the packed reads already resident in HBM (CUDA events on the library's stream)
+`e2e`    : the same through sb200_construct() with pinned HOST buffers on both sides (H2D of the reads and D2H of
+           (k+1)-mers + counts, k-mers, masks, MPHF and unitigs inside the timed region)
+`roofline`: the dominant kernel (LSD radix scatter pass) — algorithmic bytes per launch / its mean launch duration,
+           measured live with CUDA events around every launch of the timed steps
+`cpu_baseline` / --impl reference: the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from /root/reference)
+           on the box's host cores over a bounded sample of the same read set.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from spades_for_blackbird_b200.host import synth  # noqa: E402
+
+METRIC = "reads_to_condensed_dbg_throughput"
+UNIT = "Gbp/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome-len", type=int, default=4_600_000)
+    ap.add_argument("--coverage", type=float, default=100.0)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--k", type=int, default=55)
+    ap.add_argument("--buckets", type=int, default=80)
+    ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel timing table to stderr")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": "synthetic isolate %.1f Mbp genome, 2x%d reads at %.0fx, k=%d (BASELINE configs[1])" % (
+                a.genome_len / 1e6, a.read_len, a.coverage, a.k),
+            "k": a.k, "num_buckets": a.buckets, "genome_len": a.genome_len, "read_len": a.read_len, "coverage": a.coverage,
+            "error_rate": 0.005, "seed": 42, "reads_per_gpu": "all" if n_gpus == 1 else "1/%d" % n_gpus,
+            "l2": "inputs and every intermediate are larger than L2 (>= 115 MB reads, 4.7 GB of k-mer instances)"}
+
+
+def make_reads(a, codes_only=False):
+    n_pairs = int(a.genome_len * a.coverage / (2 * a.read_len))
+    g = synth.random_genome(a.genome_len, 42)
+    chunks_w = []
+    chunk = 200_000
+    first_codes = None
+    for s in range(0, n_pairs, chunk):
+        c = synth.sample_pairs(g, min(chunk, n_pairs - s), a.read_len, 350 if a.read_len <= 150 else 500, 0.005, 1042 + s)
+        if first_codes is None:
+            first_codes = c
+        chunks_w.append(synth.pack_codes(c)[0])
+    words = np.concatenate(chunks_w)
+    n = 2 * n_pairs
+    wpr = (a.read_len + 31) // 32
+    word_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(wpr)
+    lens = np.full(n, a.read_len, dtype=np.uint32)
+    return words, word_off, lens, first_codes
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference_cpu(a, codes, n_reads, cores):
+    """Times the unmodified reference path (KMerDiskCounter -> ExtensionIndex -> UnbranchingPathExtractor) on `n_reads`
+    reads of the workload with `cores` threads.  Returns (Gbp/s, seconds, bases)."""
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(driver):
+        return None
+    reads = synth.codes_to_strings(codes[:n_reads])
+    tmp = tempfile.mkdtemp(prefix="sb200_bench_")
+    try:
+        rp = os.path.join(tmp, "reads.txt")
+        with open(rp, "w") as f:
+            f.write("\n".join(reads) + "\n")
+        out = os.path.join(tmp, "out")
+        subprocess.check_call([driver, "--mode", "gbuilder", "--reads", rp, "--out", out, "-k", str(a.k), "-t", str(cores),
+                               "--quiet", "--no-dump"], stdout=subprocess.DEVNULL)
+        t = {}
+        for line in open(os.path.join(out, "timing.txt")):
+            p = line.split()
+            t[p[0]] = float(p[1])
+        secs = t["path_total"]
+        bases = int(t["bases"])
+        return bases / secs / 1e9, secs, bases
+    finally:
+        subprocess.call(["rm", "-rf", tmp])
+
+
+def reference_arm(a):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_sample = a.cpu_sample_reads
+    args_small = argparse.Namespace(**vars(a))
+    # only the first chunk of the read set is needed for the sample
+    n_pairs_needed = (n_sample + 1) // 2
+    g = synth.random_genome(a.genome_len, 42)
+    codes = synth.sample_pairs(g, min(200_000, max(n_pairs_needed, 1)), a.read_len, 350 if a.read_len <= 150 else 500, 0.005, 1042)
+    n_sample = min(n_sample, len(codes))
+    vals, secs_all = [], []
+    for i in range(a.warmup + a.steps):
+        r = run_reference_cpu(args_small, codes, n_sample, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver is not built (no /root/reference at build time)"}))
+            return 0
+        if i >= a.warmup:
+            vals.append(r[0]); secs_all.append(r[1])
+        bases = r[2]
+    v = float(np.mean(vals))
+    sample = "first %d reads (%.1f Mbp) of the workload; whole reference path incl. its temp-file I/O, -t %d" % (n_sample, bases / 1e6, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * float(np.mean(secs_all)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": workload_config(a, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from spades_for_blackbird_b200.host import binding as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    words, word_off, lens, first_codes = make_reads(a)
+    if world > 1:   # weak scaling: every rank works on its own read set of the full shape (replicas of the workload)
+        pass
+    total_bases = int(lens.astype(np.int64).sum())
+
+    ctx = B.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    streams = B.ReadStreams(ctx, words, word_off, lens)   # resident in HBM before the timed region
+
+    stage_s = {}
+
+    def timed(name, fn):
+        # every stage call is blocking (it ends with a stream synchronise), so host time == device time + launch gaps
+        t0 = time.perf_counter()
+        r = fn()
+        stage_s[name] = stage_s.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
+    def step():
+        # the same call sequence as DeBruijnExtensionIndexBuilder::BuildExtensionIndexFromStream + UnbranchingPathExtractor
+        index = B.DeBruijnExtensionIndex(ctx, a.k)
+        kp = timed("count_kpomers", lambda: B.KMerDiskCounter(ctx, streams, a.k + 1, True, True).Count(a.buckets))
+        index.kmers = timed("count_kmers", lambda: B.KMerDiskCounter(ctx, kp, a.k).Count(a.buckets))
+        index.index = timed("mphf", lambda: B.KMerIndex(ctx, index.kmers))
+        h = B.vp()
+        timed("masks", lambda: ctx.check(ctx.lib.sb200_ext_build(ctx.h, kp.h, index.kmers.h, index.index.h, B.C.byref(h))))
+        index.h = h
+        u = B.vp()
+        timed("unitigs", lambda: ctx.check(ctx.lib.sb200_unitigs_extract(ctx.h, index.kmers.h, index.index.h, index.h, 1, B.C.byref(u))))
+        stats = (kp.total_kmers(), kp.instances, index.size(), ctx.lib.sb200_unitigs_count(u), ctx.lib.sb200_unitigs_total_bases(u))
+        ctx.lib.sb200_unitigs_free(u)
+        index.free(); kp.free()
+        return stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        stats = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stage_s.clear()
+    ctx.kernel_launches(reset=True)
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(a.steps):
+        stats = step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches()
+    report = ctx.profile_report()
+    ctx.profile(False)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = world * total_bases / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    n_kp, n_inst, n_km, n_unitigs, unitig_bases = stats
+    top = report[0] if report else ("none", 1, 0.0)
+    kernel_ms = {name: (n, t) for name, n, t in report}
+    roof = None
+    if "rs_scatter_kernel<W>" in kernel_ms:
+        n_l, t_l = kernel_ms["rs_scatter_kernel<W>"]
+        # Each launch of a pass moves every record once: read W*8 bytes + write W*8 bytes.  Passes run over the
+        # (k+1)-mer instances (I1 records of W1 words) and over the k-mer candidates (2*U1 records of W0 words).
+        W1, W0 = (a.k + 1 + 31) // 32, (a.k + 31) // 32
+        bbits = max(1, int(np.ceil(np.log2(a.buckets)))) if a.buckets > 1 else 0
+        passes1 = (2 * (a.k + 1) + 7) // 8 if W1 == 1 else sum(((64 if j < W1 - 1 else 2 * (a.k + 1) - 64 * (W1 - 1)) + 7) // 8 for j in range(W1))
+        passes0 = sum(((64 if j < W0 - 1 else 2 * a.k - 64 * (W0 - 1)) + 7) // 8 for j in range(W0))
+        passes1 += (bbits + 7) // 8
+        passes0 += (bbits + 7) // 8
+        bytes_total = a.steps * (passes1 * n_inst * W1 * 16 + passes0 * 2 * n_kp * W0 * 16)
+        achieved = bytes_total / (t_l * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "rs_scatter_kernel (stable LSD radix scatter pass)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches": n_l, "mean_launch_ms": t_l / n_l, "share_of_step": t_l / ms,
+                "algorithmic_bytes_per_launch": bytes_total / n_l}
+    breakdown = [{"kernel": name, "launches": n // a.steps if a.steps else n, "ms_per_step": t / a.steps} for name, n, t in report[:12]]
+    if a.breakdown and rank == 0:
+        for name, n, t in report:
+            print("%-40s %6d launches %10.3f ms/step" % (name, n // a.steps, t / a.steps), file=sys.stderr)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        pw = torch.from_numpy(words.view(np.int64)).pin_memory()
+        po = torch.from_numpy(word_off.view(np.int64)).pin_memory()
+        pl = torch.from_numpy(lens.view(np.int32)).pin_memory()
+        hw, ho, hl = pw.numpy().view(np.uint64), po.numpy().view(np.uint64), pl.numpy().view(np.uint32)
+        g = B.construct(ctx, hw, ho, hl, a.k, a.buckets, fetch_kmers=True)   # warm-up (also sizes the pinned result pool)
+        h2d, d2h = g.view.h2d_bytes, g.view.d2h_bytes
+        g.free()
+        for _ in range(max(a.warmup - 1, 0)):
+            B.construct(ctx, hw, ho, hl, a.k, a.buckets, fetch_kmers=True).free()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(a.steps):
+            B.construct(ctx, hw, ho, hl, a.k, a.buckets, fetch_kmers=True).free()
+        e1.record(stream)
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        wall_e = (time.perf_counter() - t0) * 1e3
+        ms_e = max(ms_e, wall_e)   # host-side work (pinned allocation, serialisation) is part of the call
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * total_bases / (ms_e / a.steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
+               "returns": "(k+1)-mers + counts, k-mers, masks, KMerIndex bytes, packed unitigs"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = run_reference_cpu(a, first_codes, min(a.cpu_sample_reads, len(first_codes)), cores)
+        if r:
+            cpu = {"value": r[0], "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "first %d reads (%.1f Mbp) of the workload, whole reference path in %.1f s, -t %d" % (
+                       min(a.cpu_sample_reads, len(first_codes)), r[2] / 1e6, r[1], cores)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": workload_config(a, world), "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "kmers_counted_per_s": world * n_inst / (stage_s["count_kpomers"] / a.steps),
+                "stage_ms": {k_: 1e3 * v_ / a.steps for k_, v_ in stage_s.items()},
+                "counts": {"kpomer_instances": int(n_inst), "kpomers": int(n_kp), "kmers": int(n_km), "unitigs": int(n_unitigs),
+                           "unitig_bases": int(unitig_bases), "input_bases": total_bases},
+                "breakdown": breakdown}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

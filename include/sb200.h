@@ -41,6 +41,9 @@ const char *sb200_last_error(const sb200_ctx *ctx);      /* ctx may be NULL: err
 int  sb200_synchronize(sb200_ctx *ctx);
 void *sb200_stream(sb200_ctx *ctx);                       /* cudaStream_t all work of this context is launched on    */
 uint64_t sb200_kernel_launches(sb200_ctx *ctx, int reset);/* kernels launched by this library since the last reset   */
+/* Per-kernel device timing: CUDA events around every launch on the context's stream (measurement aid for bench.py).  */
+int  sb200_profile(sb200_ctx *ctx, int enable);           /* clears collected records                                 */
+int  sb200_profile_report(sb200_ctx *ctx, char *out, uint64_t cap, uint64_t *needed);  /* "name\tlaunches\tms\n" lines */
 
 /* ---- reads: io::ReadStreamList<io::SingleReadSeq> (io/reads/read_stream.hpp:63-87; binary layout of
  *      io/reads/single_read.hpp:279-299 / sequence/sequence.hpp:399-428: every read word-aligned, 2 bits per base) -- */

@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libspades_b200.so (include/sb200.h): argument checking, error mapping, host<->device copies.
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/sb200.h"
@@ -110,6 +111,44 @@ uint64_t sb200_kernel_launches(sb200_ctx *ctx, int reset) {
     uint64_t v = ctx->kernel_launches;
     if (reset) ctx->kernel_launches = 0;
     return v;
+}
+
+int sb200_profile(sb200_ctx *ctx, int enable) {
+    return guarded(ctx, [&] {
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (auto &r : ctx->prof) { ctx->event_pool.push_back(r.a); ctx->event_pool.push_back(r.b); }
+        ctx->prof.clear();
+        ctx->profiling = enable != 0;
+    });
+}
+
+// "name\tlaunches\ttotal_ms\n" per kernel, sorted by total time; returns the number of bytes needed
+int sb200_profile_report(sb200_ctx *ctx, char *out, uint64_t cap, uint64_t *needed) {
+    return guarded(ctx, [&] {
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        std::vector<std::pair<std::string, std::pair<uint64_t, double>>> agg;
+        for (auto &r : ctx->prof) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+            bool found = false;
+            for (auto &a : agg)
+                if (a.first == r.name) { a.second.first++; a.second.second += ms; found = true; break; }
+            if (!found) agg.push_back({r.name, {1, ms}});
+        }
+        std::sort(agg.begin(), agg.end(), [](const auto &x, const auto &y) { return x.second.second > y.second.second; });
+        std::string s;
+        for (auto &a : agg) {
+            char line[256];
+            snprintf(line, sizeof line, "%s\t%llu\t%.6f\n", a.first.c_str(), (unsigned long long) a.second.first, a.second.second);
+            s += line;
+        }
+        *needed = s.size() + 1;
+        if (out && cap) {
+            size_t n = std::min<size_t>(cap - 1, s.size());
+            memcpy(out, s.data(), n);
+            out[n] = 0;
+        }
+    });
 }
 
 // ---- reads ---------------------------------------------------------------------------------------------------------------

@@ -40,6 +40,25 @@ struct sb200_ctx {
     int num_sms = 148;
     std::string last_error;
     uint64_t kernel_launches = 0;   // launches of OUR kernels since the last reset (bench.py "gpu_launches")
+
+    // Optional per-kernel device timing (bench.py's live roofline numbers): a CUDA event pair around every launch on
+    // the launching stream, aggregated by kernel name in sb200_profile_report().
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; double bytes; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event() {
+        cudaEvent_t e;
+        if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_begin(const char *name) {
+        ProfRec r{name, get_event(), get_event(), 0.0};
+        cudaEventRecord(r.a, stream);
+        prof.push_back(r);
+    }
+    void prof_end() { cudaEventRecord(prof.back().b, stream); }
 };
 
 // Stream-ordered device array.
@@ -76,7 +95,9 @@ static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned) ((a + 
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
     do {                                                                    \
+        if ((ctx)->profiling) (ctx)->prof_begin(#kernel);                   \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+        if ((ctx)->profiling) (ctx)->prof_end();                            \
         (ctx)->kernel_launches++;                                           \
         CUDA_CHECK(cudaGetLastError());                                     \
     } while (0)

@@ -13,6 +13,7 @@
 #include "kmer_set.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "segsort.cuh"
 
 namespace sb200 {
 
@@ -185,10 +186,165 @@ __global__ void last_is_marker_kernel(const uint64_t *__restrict__ recs, uint64_
     *flag = m ? 1u : 0u;
 }
 
+template<int W>
+__global__ void double_palindromes_kernel(const uint64_t *__restrict__ recs, uint64_t u, int K, uint32_t *__restrict__ counts) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    uint64_t x[W], r[W];
+    load_rec<W>(recs, i, x);
+    kmer_rc<W>(x, K, r);
+    if (kmer_eq<W>(x, r)) counts[i] *= 2;
+}
+
+// Generic path for a dirty range of the segmented sort: full LSD sort + unique (+ run lengths) of recs[0..m) into
+// side_recs / side_cnts; returns the number of unique records (host value).
+template<int W>
+static uint32_t lsd_unique_range(sb200_ctx *ctx, uint64_t *recs, uint64_t m, int K, uint32_t B, bool marker, bool want_counts,
+                                 uint64_t *side_recs, uint32_t *side_cnts) {
+    DevBuf<uint64_t> scratch(ctx, m * W);
+    uint64_t *sorted = radix_sort_records<W>(ctx, recs, scratch.p, m, K, B, marker);
+    unsigned tiles = div_up(m, UQ_TILE);
+    DevBuf<uint32_t> tile_cnt(ctx, tiles);
+    DevBuf<uint32_t> total_dev(ctx, 1);
+    LAUNCH(ctx, unique_count_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p);
+    exclusive_scan<uint32_t>(ctx, tile_cnt.p, tiles, total_dev.p);
+    uint32_t u = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&u, total_dev.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    DevBuf<uint32_t> head_pos(ctx, (uint64_t) u + 1);
+    LAUNCH(ctx, unique_write_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p, side_recs, head_pos.p);
+    if (want_counts) {
+        uint32_t m32 = (uint32_t) m;
+        CUDA_CHECK(cudaMemcpyAsync(head_pos.p + u, &m32, 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, counts_kernel<W>, div_up(u, 256), 256, 0, head_pos.p, side_recs, (uint64_t) u, K, 0, side_cnts);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return u;
+}
+
+template<int W>
+static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B) {
+    s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
+    LAUNCH(ctx, bucket_starts_kernel<W>, div_up(s->size, 256), 256, 0, s->data.p, s->size, B, s->bucket_starts.p);
+    s->bucket_starts_host.resize((size_t) B + 1);
+    CUDA_CHECK(cudaMemcpyAsync(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+template<int W>
+static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
+                                   bool double_palindromes, bool drop_marker);
+
 // Sort + unique + counts + bucket table.  `inst` (n x W) is consumed.
+//   1. three stable counting passes group the instances by (bucket, 16-bit value prefix)            radix_sort.cuh
+//   2. one shared-memory pass ranks, deduplicates and counts inside every group and writes the unique records to
+//      their final place (decoupled look-back for the offsets)                                        segsort.cuh
 template<int W>
 static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
                                bool double_palindromes, bool drop_marker) {
+    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    if (2 * K < 24) return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+    using Cfg = SegCfg<W>;
+    DevBuf<uint64_t> scratch(ctx, n * W);
+    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, prefix_passes(W, K, B, drop_marker));
+    uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
+
+    PrefixKey pk{prefix_shift(W, K), B, drop_marker ? 1 : 0};
+    DevBuf<uint32_t> hb(ctx, (n + 31) / 32 + 2);
+    LAUNCH(ctx, seg_heads_kernel<W>, div_up(n, 256), 256, 0, grouped, n, pk, hb.p);
+    uint32_t n_chunks = div_up(n, Cfg::C);
+    DevBuf<ChunkRange> ranges(ctx, n_chunks);
+    DevBuf<uint32_t> dirty_list(ctx, n_chunks);
+    DevBuf<uint32_t> ctrl(ctx, 4);   // [0] n_dirty  [1] tile counter
+    DevBuf<unsigned long long> total_dev(ctx, 1);
+    ctrl.zero();
+    LAUNCH(ctx, seg_ranges_kernel<W>, div_up(n_chunks, 128), 128, 0, hb.p, n, n_chunks, ranges.p, dirty_list.p, ctrl.p);
+    uint32_t n_dirty = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_dirty, ctrl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+
+    DevBuf<uint64_t> side_recs;
+    DevBuf<uint32_t> side_cnts;
+    if (n_dirty) {   // oversize segments: sort their chunks' ranges with the generic LSD path first
+        std::vector<uint32_t> dl(n_dirty);
+        CUDA_CHECK(cudaMemcpyAsync(dl.data(), dirty_list.p, (size_t) n_dirty * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        std::vector<ChunkRange> cr(n_dirty);
+        uint64_t side_total = 0;
+        for (uint32_t i = 0; i < n_dirty; ++i) {
+            CUDA_CHECK(cudaMemcpyAsync(&cr[i], ranges.p + dl[i], sizeof(ChunkRange), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < n_dirty; ++i) side_total += cr[i].e - cr[i].s;
+        side_recs.alloc(ctx, side_total * W);
+        side_cnts.alloc(ctx, side_total);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < n_dirty; ++i) {
+            uint64_t m = cr[i].e - cr[i].s;
+            uint32_t u = lsd_unique_range<W>(ctx, grouped + (uint64_t) cr[i].s * W, m, K, B, drop_marker, want_counts,
+                                             side_recs.p + off * W, side_cnts.p + off);
+            cr[i].side_off = (uint32_t) off;
+            cr[i].side_cnt = u;
+            off += m;
+            CUDA_CHECK(cudaMemcpyAsync(ranges.p + dl[i], &cr[i], sizeof(ChunkRange), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+
+    DevBuf<unsigned long long> status(ctx, n_chunks);
+    status.zero();
+    DevBuf<uint32_t> cnt_full;
+    if (want_counts) cnt_full.alloc(ctx, n);
+    size_t smem = seg_chunk_smem<W>();
+    if (want_counts) {
+        auto seg_chunk_kernel_ = seg_chunk_kernel<W, true>;
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
+               cnt_full.p, total_dev.p, n_chunks);
+    } else {
+        auto seg_chunk_kernel_ = seg_chunk_kernel<W, false>;
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
+               (uint32_t *) nullptr, total_dev.p, n_chunks);
+    }
+    unsigned long long u64 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&u64, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    uint64_t u = u64;
+
+    sb200_kmers *s = new sb200_kmers();
+    s->ctx = ctx; s->k = (unsigned) K; s->words = W; s->num_buckets = B; s->instances = n;
+    if (drop_marker) {
+        uint32_t flag = 0;
+        DevBuf<uint32_t> fl(ctx, 1);
+        LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, other, u, fl.p);
+        CUDA_CHECK(cudaMemcpyAsync(&flag, fl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (flag) --u;
+        if (u == 0) {
+            delete s;
+            SB200_REQUIRE(false, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+        }
+    }
+    s->size = u;
+    s->data.alloc(ctx, u * W);   // right-sized copy; the instance-sized ping-pong buffers go back to the pool
+    CUDA_CHECK(cudaMemcpyAsync(s->data.p, other, u * W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (want_counts) {
+        s->counts.alloc(ctx, u);
+        CUDA_CHECK(cudaMemcpyAsync(s->counts.p, cnt_full.p, u * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (double_palindromes && (K % 2 == 0))
+            LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
+    }
+    finish_tables<W>(ctx, s, B);
+    inst.release();
+    return s;
+}
+
+// First version of the path: full LSD sort of every significant byte.  Kept for very short k-mers (2K < 24 bits), as
+// the fallback of oversize segments, and as the reference point for the profile in profiles/.
+template<int W>
+static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
+                                   bool double_palindromes, bool drop_marker) {
     SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     DevBuf<uint64_t> scratch(ctx, n * W);
     uint64_t *sorted = radix_sort_records<W>(ctx, inst.p, scratch.p, n, K, B, drop_marker);
@@ -272,8 +428,8 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
     int k = (int) kp->k - 1;
     uint64_t n = kp->size * 2;
     DevBuf<uint64_t> inst(ctx, n * W);
-    auto kfn = derive_kernel<WS, W>;
-    LAUNCH(ctx, kfn, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, inst.p);
+    auto derive_kernel_ = derive_kernel<WS, W>;
+    LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, inst.p);
     sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false);
     s->instances = 0;
     return s;

@@ -63,8 +63,8 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     e->inv.alloc(ctx, kmers->size);
     MphfDev m = mphf_dev(mphf);
     LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p);
-    auto kfn = fill_masks_kernel<WS, W>;
-    LAUNCH(ctx, kfn, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p);
+    auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
+    LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p);
     return e;
 }
 

@@ -152,23 +152,45 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
 
 // Sorts recs (n x W words) into (bucket, array_less) order.  `a` holds the input; `b` is scratch of the same size.
 // Returns the buffer (a or b) that holds the result.
-template<int W>
-uint64_t *radix_sort_records(sb200_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, int K, uint32_t num_buckets, bool marker = false) {
-    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
-    if (n <= 1) return a;
-    constexpr int ITEMS = RsItems<W>::value;
-    uint32_t num_tiles = div_up(n, RS_THREADS * ITEMS);
-    DevBuf<uint32_t> hist(ctx, (uint64_t) RS_BINS * num_tiles);
-    std::vector<DigitSel> passes;
-    for (int j = W - 1; j >= 0; --j) {
-        int bits = (j == W - 1) ? (2 * K - 64 * (W - 1)) : 64;
-        for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{j, s, 0, 0});
-    }
+inline void append_bucket_passes(std::vector<DigitSel> &passes, uint32_t num_buckets, bool marker) {
     if (num_buckets > 1) {
         int bbits = 0;
         while ((1ull << bbits) < num_buckets) ++bbits;
         for (int s = 0; s < bbits; s += 8) passes.push_back(DigitSel{-1, s, num_buckets, marker ? 1 : 0});
     }
+}
+
+// every significant byte of the record, least significant first, then the bucket id: the complete file order
+inline std::vector<DigitSel> full_passes(int W, int K, uint32_t num_buckets, bool marker) {
+    std::vector<DigitSel> passes;
+    for (int j = W - 1; j >= 0; --j) {
+        int bits = (j == W - 1) ? (2 * K - 64 * (W - 1)) : 64;
+        for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{j, s, 0, 0});
+    }
+    append_bucket_passes(passes, num_buckets, marker);
+    return passes;
+}
+
+// bit offset of the 16-bit value prefix (the two most significant bytes' worth of bits of word 0)
+inline int prefix_shift(int W, int K) { return (W == 1 ? 2 * K : 64) - 16; }
+
+// only the 16 most significant bits of word 0, then the bucket id: groups records into (bucket, prefix) segments
+inline std::vector<DigitSel> prefix_passes(int W, int K, uint32_t num_buckets, bool marker) {
+    std::vector<DigitSel> passes;
+    int sh = prefix_shift(W, K);
+    passes.push_back(DigitSel{0, sh, 0, 0});
+    passes.push_back(DigitSel{0, sh + 8, 0, 0});
+    append_bucket_passes(passes, num_buckets, marker);
+    return passes;
+}
+
+template<int W>
+uint64_t *radix_sort_passes(sb200_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, const std::vector<DigitSel> &passes) {
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    if (n <= 1) return a;
+    constexpr int ITEMS = RsItems<W>::value;
+    uint32_t num_tiles = div_up(n, RS_THREADS * ITEMS);
+    DevBuf<uint32_t> hist(ctx, (uint64_t) RS_BINS * num_tiles);
     uint64_t *src = a, *dst = b;
     for (const DigitSel &sel : passes) {
         LAUNCH(ctx, rs_hist_kernel<W>, num_tiles, RS_THREADS, 0, src, n, sel, hist.p, num_tiles);
@@ -177,6 +199,11 @@ uint64_t *radix_sort_records(sb200_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t 
         std::swap(src, dst);
     }
     return src;
+}
+
+template<int W>
+uint64_t *radix_sort_records(sb200_ctx *ctx, uint64_t *a, uint64_t *b, uint64_t n, int K, uint32_t num_buckets, bool marker = false) {
+    return radix_sort_passes<W>(ctx, a, b, n, full_passes(W, K, num_buckets, marker));
 }
 
 }  // namespace sb200

@@ -1,0 +1,337 @@
+// segsort.cuh — sort + deduplicate + count in ONE pass over records that are already grouped by a short key prefix.
+//
+// After three stable counting passes (two bytes of the most significant record word, then the hash bucket) the
+// instance array is ordered by (bucket, 16-bit value prefix).  A "segment" is a maximal run of records sharing that
+// prefix: a few dozen records for the BASELINE workloads.  Finishing the order with twelve more full-array LSD passes
+// (what round-1's first version did) moves every record 12 more times through HBM; instead each CTA stages a run of
+// whole segments (<= CAP records) in shared memory and ranks every record inside its own segment by direct
+// comparison (rank = #smaller + #equal-before), which also yields "am I the first of my value" and the multiplicity.
+// Representatives are compacted with a block scan and written straight to their final position: the global offset of
+// a CTA comes from a decoupled look-back over per-CTA unique counts, so the array is read once and only the unique
+// records are written.  Segments too long for shared memory (highly repeated k-mers, low-complexity sequence) make
+// their CTA "dirty"; dirty ranges are sorted by the generic LSD path first and the CTA merely copies the result.
+#pragma once
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+template<int W> struct SegCfg {
+    static constexpr int CAP = (W == 1) ? 8192 : (W == 2) ? 4096 : 2048;   // records staged per CTA (64 KB of keys)
+    static constexpr int C = CAP / 2;        // a CTA owns the segments that START in its C-record window
+    static constexpr int MAXSEG = CAP / 2;   // longest segment the shared-memory path accepts
+    static constexpr int THREADS = 256;
+};
+
+struct PrefixKey {   // what defines a segment
+    int shift;           // prefix = (word0 >> shift) & 0xFFFF
+    uint32_t num_buckets;
+    int marker;
+};
+
+template<int W>
+__device__ __forceinline__ uint64_t seg_key(const uint64_t *r, const PrefixKey &pk) {
+    uint32_t b = kmer_bucket<W>(r, pk.num_buckets);
+    if (pk.marker) {
+        bool m = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) m &= (r[j] == ~0ULL);
+        if (m) b = pk.num_buckets - 1;
+    }
+    return ((uint64_t) b << 16) | ((r[0] >> pk.shift) & 0xFFFFu);
+}
+
+// head bit i = record i starts a segment.  One warp writes one 32-bit word.
+template<int W>
+__global__ void __launch_bounds__(256) seg_heads_kernel(const uint64_t *__restrict__ recs, uint64_t n, PrefixKey pk, uint32_t *__restrict__ hb) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    uint64_t key = ~0ULL;
+    if (i < n) {
+        uint64_t r[W];
+        load_rec<W>(recs, i, r);
+        key = seg_key<W>(r, pk);
+    }
+    uint64_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (lane == 0) {
+        prev = ~0ULL;
+        if (i > 0 && i < n) {
+            uint64_t r[W];
+            load_rec<W>(recs, i - 1, r);
+            prev = seg_key<W>(r, pk);
+        }
+    }
+    bool head = (i < n) && (i == 0 || key != prev);
+    uint32_t word = __ballot_sync(0xffffffffu, head);
+    if (lane == 0 && (i >> 5) < ((n + 31) >> 5)) hb[i >> 5] = word;
+}
+
+// first head position >= from (searching bits up to `limit`, exclusive); returns limit if none
+__device__ __forceinline__ uint64_t next_head(const uint32_t *__restrict__ hb, uint64_t from, uint64_t limit) {
+    if (from >= limit) return limit;
+    uint64_t w = from >> 5;
+    uint32_t bits = hb[w] & (0xFFFFFFFFu << (from & 31));
+    uint64_t last_w = (limit - 1) >> 5;
+    while (true) {
+        if (bits) {
+            uint64_t p = (w << 5) + (__ffs((int) bits) - 1);
+            return p < limit ? p : limit;
+        }
+        if (w == last_w) return limit;
+        ++w;
+        bits = hb[w];
+    }
+}
+
+struct ChunkRange {
+    uint32_t s, e;      // records [s, e) = all segments that start inside the CTA's window (s == e: owns nothing)
+    uint32_t dirty;     // 1: some owned segment is longer than MAXSEG -> handled by the LSD fallback
+    uint32_t side_off;  // dirty only: where the pre-sorted unique records sit in the side buffer
+    uint32_t side_cnt;  // dirty only: how many
+};
+
+// one thread per CTA window: owned range and whether every owned segment fits
+template<int W>
+__global__ void seg_ranges_kernel(const uint32_t *__restrict__ hb, uint64_t n, uint32_t n_chunks, ChunkRange *__restrict__ ranges,
+                                  uint32_t *__restrict__ dirty_list, uint32_t *__restrict__ n_dirty) {
+    constexpr int C = SegCfg<W>::C, MAXSEG = SegCfg<W>::MAXSEG;
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_chunks) return;
+    uint64_t lo = (uint64_t) b * C, hi = lo + C < n ? lo + C : n;
+    ChunkRange cr;
+    cr.dirty = 0; cr.side_off = 0; cr.side_cnt = 0;
+    uint64_t s = next_head(hb, lo, hi);
+    if (s >= hi) {   // no segment starts here
+        cr.s = cr.e = (uint32_t) hi;
+        ranges[b] = cr;
+        return;
+    }
+    // walk the owned heads, checking segment lengths
+    bool dirty = false;
+    uint64_t cur = s, e = hi;
+    while (true) {
+        uint64_t limit = cur + 1 + MAXSEG < n ? cur + 1 + MAXSEG : n;
+        uint64_t nx = next_head(hb, cur + 1, limit);
+        if (nx == limit && limit < n) {   // no head within MAXSEG records: oversize segment
+            dirty = true;
+            nx = next_head(hb, limit, n);   // its true end (unbounded scan; rare)
+        } else if (nx == limit && limit == n) {
+            if (n - cur > (uint64_t) MAXSEG) dirty = true;
+            nx = n;
+        }
+        if (nx >= hi) { e = nx; break; }
+        cur = nx;
+    }
+    cr.s = (uint32_t) s; cr.e = (uint32_t) e; cr.dirty = dirty ? 1u : 0u;
+    ranges[b] = cr;
+    if (dirty) dirty_list[atomicAdd(n_dirty, 1u)] = b;
+}
+
+// decoupled look-back status word: bits 62-63 flag (0 empty, 1 aggregate, 2 inclusive prefix), bits 0-61 value
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long flag, unsigned long long v) { return (flag << 62) | v; }
+
+// Shared memory of seg_chunk_kernel, in bytes
+template<int W>
+constexpr size_t seg_chunk_smem() {
+    return (size_t) SegCfg<W>::CAP * W * 8      // keys of the warp-tile representatives
+           + (size_t) SegCfg<W>::CAP * 4         // their multiplicities
+           + (size_t) SegCfg<W>::CAP * 4         // representative flag by sorted position, then its exclusive scan
+           + (size_t) SegCfg<W>::CAP             // segment-head flag per representative
+           + (size_t) (SegCfg<W>::CAP / 32 + 1) * 4;   // representatives per warp tile, then its exclusive scan
+}
+
+// Two levels.  (1) Every warp tile of 32 consecutive records is deduplicated with match.any on the record words: equal
+// records elect their lowest lane, which keeps the value and the number of copies — the bulk of the input (copies of the
+// same genomic k-mer) disappears here at a cost of W match instructions per 32 records.  (2) The survivors of the CTA
+// (kept in order, hence still grouped by segment) are ranked inside their segment by direct comparison; equal survivors
+// from different tiles merge their counts.  A block scan over "first of its value" flags in sorted position and a
+// decoupled look-back over CTAs give every unique record its final place.
+template<int W, bool COUNTS>
+__global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uint64_t *__restrict__ recs, uint64_t n,
+                                                                      const uint32_t *__restrict__ hb, const ChunkRange *__restrict__ ranges,
+                                                                      const uint64_t *__restrict__ side_recs, const uint32_t *__restrict__ side_cnts,
+                                                                      unsigned long long *__restrict__ status, uint32_t *__restrict__ tile_counter,
+                                                                      uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt,
+                                                                      unsigned long long *__restrict__ total_out, uint32_t n_chunks) {
+    constexpr int CAP = SegCfg<W>::CAP, THREADS = SegCfg<W>::THREADS;
+    constexpr int NT = CAP / 32;               // warp tiles per CTA
+    constexpr int TPW = NT / (THREADS / 32);   // warp tiles per warp
+    constexpr uint32_t PER = CAP / THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *pkey = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *pcnt = reinterpret_cast<uint32_t *>(pkey + (size_t) CAP * W);
+    uint32_t *sflag = pcnt + CAP;
+    uint8_t *phead = reinterpret_cast<uint8_t *>(sflag + CAP);
+    uint32_t *tileoff = reinterpret_cast<uint32_t *>(phead + CAP);
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_np;
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_scan[THREADS / 32 + 1];
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t b = s_tile;
+    if (b >= n_chunks) return;
+    const ChunkRange cr = ranges[b];
+    const uint32_t s = cr.s, cnt = cr.dirty ? 0u : cr.e - cr.s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- level 1: warp-tile deduplication, records straight from global memory into registers ---------------------------
+    uint64_t rec[TPW][W];
+    uint32_t mult[TPW];
+    uint32_t rep_bits = 0, head_bits = 0;   // bit t: my record of tile t is a tile representative / starts a segment
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+        const uint32_t tile = warp * TPW + t;
+        const uint32_t p = tile * 32 + lane;
+        const bool ok = p < cnt;
+#pragma unroll
+        for (int j = 0; j < W; ++j) rec[t][j] = 0;
+        uint32_t peers = 0xFFFFFFFFu;
+        if (tile * 32 < cnt) {   // warp-uniform
+            if (ok) {
+                load_rec<W>(recs, (uint64_t) s + p, rec[t]);
+                const uint64_t g = (uint64_t) s + p;
+                if ((hb[g >> 5] >> (g & 31)) & 1u) head_bits |= 1u << t;
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) peers &= __match_any_sync(0xffffffffu, rec[t][j]);
+            peers &= __ballot_sync(0xffffffffu, ok);
+        }
+        const bool is_rep = ok && ((uint32_t) lane == (uint32_t) (__ffs((int) peers) - 1));
+        mult[t] = (uint32_t) __popc(peers);
+        if (is_rep) rep_bits |= 1u << t;
+        const uint32_t m = __ballot_sync(0xffffffffu, is_rep);
+        if (lane == 0) tileoff[tile] = (uint32_t) __popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of NT (<= 256) tile counts by one warp
+        uint32_t carry = 0;
+        for (int base = 0; base < NT; base += 32) {
+            uint32_t v = tileoff[base + lane];
+            uint32_t inc = warp_inclusive_scan(v);
+            tileoff[base + lane] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_np = carry;
+    }
+    __syncthreads();
+    const uint32_t np = s_np;
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+        const uint32_t tile = warp * TPW + t;
+        const bool is_rep = (rep_bits >> t) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, is_rep);
+        if (is_rep) {
+            const uint32_t o = tileoff[tile] + (uint32_t) __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int j = 0; j < W; ++j) pkey[(size_t) o * W + j] = rec[t][j];
+            pcnt[o] = mult[t];
+            phead[o] = (uint8_t) ((head_bits >> t) & 1u);
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < np; i += THREADS) sflag[i] = 0;
+    __syncthreads();
+
+    // ---- level 2: rank the survivors inside their segment ------------------------------------------------------------------
+    uint32_t rep_pos[PER];   // sorted position if I am the first survivor of my value, else ~0
+    uint32_t rep_cnt[PER];   // total multiplicity of the value
+#pragma unroll
+    for (uint32_t i = 0; i < PER; ++i) {
+        rep_pos[i] = 0xFFFFFFFFu;
+        rep_cnt[i] = 0;
+        const uint32_t p = threadIdx.x + i * THREADS;
+        if (p >= np) continue;
+        uint32_t sb = p;
+        while (!phead[sb]) --sb;             // entry 0 is a head by construction
+        uint32_t se = p + 1;
+        while (se < np && !phead[se]) ++se;
+        uint64_t me[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) me[j] = pkey[(size_t) p * W + j];
+        uint32_t less = 0, eq_before = 0, total = 0;
+        for (uint32_t q = sb; q < se; ++q) {
+            uint64_t o[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) o[j] = pkey[(size_t) q * W + j];
+            const bool lt = rec_less<W>(o, me);
+            const bool eq = kmer_eq<W>(o, me);
+            less += lt ? 1u : 0u;
+            eq_before += (eq && q < p) ? 1u : 0u;
+            if (COUNTS) total += eq ? pcnt[q] : 0u;
+        }
+        if (eq_before == 0) {
+            rep_pos[i] = sb + less;
+            rep_cnt[i] = total;
+            sflag[sb + less] = 1u;
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the flags in sorted order, in place
+    uint32_t v[PER];
+    uint32_t local_sum = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < PER; ++i) {
+        const uint32_t p = threadIdx.x * PER + i;
+        v[i] = (p < np) ? sflag[p] : 0u;
+        local_sum += v[i];
+    }
+    uint32_t total_u;
+    uint32_t pre = block_exclusive_scan<uint32_t, THREADS>(local_sum, &total_u, s_scan);
+#pragma unroll
+    for (uint32_t i = 0; i < PER; ++i) {
+        const uint32_t p = threadIdx.x * PER + i;
+        if (p < np) sflag[p] = pre;
+        pre += v[i];
+    }
+    const uint32_t my_total = cr.dirty ? cr.side_cnt : total_u;
+
+    // ---- decoupled look-back for this CTA's global offset ------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        unsigned long long excl = 0;
+        if (b == 0) {
+            atomicExch(&status[0], lb_pack(2, my_total));
+        } else {
+            atomicExch(&status[b], lb_pack(1, my_total));
+            long long p = (long long) b - 1;
+            while (true) {
+                unsigned long long sv = atomicAdd(&status[p], 0ULL);
+                unsigned long long flag = sv >> 62;
+                if (flag == 0) continue;
+                excl += sv & ((1ULL << 62) - 1);
+                if (flag == 2) break;
+                --p;
+            }
+            atomicExch(&status[b], lb_pack(2, excl + my_total));
+        }
+        s_base = excl;
+        if (b == n_chunks - 1) *total_out = excl + my_total;
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+
+    if (cr.dirty) {
+        for (uint32_t i = threadIdx.x; i < cr.side_cnt; i += THREADS) {
+            uint64_t r[W];
+            load_rec<W>(side_recs, (uint64_t) cr.side_off + i, r);
+            store_rec<W>(out, base + i, r);
+            if (COUNTS) out_cnt[base + i] = side_cnts[cr.side_off + i];
+        }
+        return;
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < PER; ++i) {
+        if (rep_pos[i] == 0xFFFFFFFFu) continue;
+        const uint32_t p = threadIdx.x + i * THREADS;
+        uint64_t r[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] = pkey[(size_t) p * W + j];
+        const unsigned long long dst = base + sflag[rep_pos[i]];
+        store_rec<W>(out, dst, r);
+        if (COUNTS) out_cnt[dst] = rep_cnt[i];
+    }
+}
+
+}  // namespace sb200

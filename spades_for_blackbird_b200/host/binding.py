@@ -55,6 +55,8 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_synchronize": (C.c_int, [vp]),
     "sb200_stream": (vp, [vp]),
     "sb200_kernel_launches": (C.c_uint64, [vp, C.c_int]),
+    "sb200_profile": (C.c_int, [vp, C.c_int]),
+    "sb200_profile_report": (C.c_int, [vp, C.c_char_p, C.c_uint64, u64p]),
     "sb200_reads_upload": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, C.POINTER(vp)]),
     "sb200_reads_wrap_device": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "sb200_reads_free": (None, [vp]),
@@ -140,6 +142,21 @@ class Context:
 
     def kernel_launches(self, reset=False):
         return self.lib.sb200_kernel_launches(self.h, int(reset))
+
+    def profile(self, enable=True):
+        self.check(self.lib.sb200_profile(self.h, int(enable)))
+
+    def profile_report(self):
+        """[(kernel name, launches, total ms)] sorted by time, measured with CUDA events on the launching stream"""
+        need = C.c_uint64()
+        self.check(self.lib.sb200_profile_report(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 16)
+        self.check(self.lib.sb200_profile_report(self.h, buf, need.value + 16, C.byref(need)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            rows.append((name, int(n), float(ms)))
+        return rows
 
     def close(self):
         if self.h:
