@@ -38,23 +38,7 @@ static int guarded(sb200_ctx *ctx, F &&f) {
     }
 }
 
-struct sb200_graph {
-    sb200_ctx *ctx = nullptr;
-    sb200_graph_view view;
-    std::vector<void *> pinned;
-    std::vector<uint8_t> index_bytes;
-    std::vector<uint64_t> kp_starts, km_starts;
-    template<class T>
-    T *pin(size_t n) {
-        void *p = nullptr;
-        CUDA_CHECK(cudaMallocHost(&p, (n ? n : 1) * sizeof(T)));
-        pinned.push_back(p);
-        return (T *) p;
-    }
-    ~sb200_graph() {
-        for (void *p : pinned) cudaFreeHost(p);
-    }
-};
+#include "graph.cuh"
 
 extern "C" {
 
@@ -77,6 +61,8 @@ int sb200_create(int device, sb200_ctx **out) {
         sb200_ctx *ctx = new sb200_ctx();
         ctx->device = device;
         ctx->num_sms = prop.multiProcessorCount;
+        ctx->trace = getenv("SB200_TRACE") != nullptr;
+        ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
@@ -96,9 +82,18 @@ void sb200_destroy(sb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    delete ctx;
+    cudaStreamSynchronize(ctx->copy_stream);
+    ctx->dev_trim();
+    ctx->pinned_free_all();
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    ctx->event_pool.clear();
+    // Handles created from this context may outlive it (garbage-collected wrappers): their device blocks are still
+    // registered, so the small context record is kept alive for them and only the streams go away when nothing is left.
+    if (ctx->dev_block_size.empty()) {
+        cudaStreamDestroy(ctx->stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        delete ctx;
+    }
 }
 
 const char *sb200_last_error(const sb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
@@ -335,8 +330,9 @@ void sb200_unitigs_free(sb200_unitigs *u) {
     delete u;
 }
 
-// ---- whole path -------------------------------------------------------------------------------------------------------------
-int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+// ---- whole path: see construct.cu ------------------------------------------------------------------------------------------
+#if 0
+int sb200_construct_v0(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
                     const sb200_construct_params *p, sb200_graph **out) {
     *out = nullptr;
     sb200_reads *reads = nullptr;
@@ -413,6 +409,7 @@ int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_
     if (rc && g) { delete g; }
     return rc;
 }
+#endif
 
 int sb200_graph_get(const sb200_graph *g, sb200_graph_view *view) {
     *view = g->view;

@@ -7,8 +7,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+#include <map>
 #include <string>
 #include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 #define SB200_MAX_WORDS 4
@@ -59,35 +63,125 @@ struct sb200_ctx {
         prof.push_back(r);
     }
     void prof_end() { cudaEventRecord(prof.back().b, stream); }
+
+    // SB200_TRACE=1: host-side wall time between trace points (each point drains the stream first), to stderr
+    bool trace = false;
+    double trace_t0 = 0;
+    static double now_s() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+    }
+    void trace_point(const char *label) {
+        if (!trace) return;
+        cudaStreamSynchronize(stream);
+        double t = now_s();
+        fprintf(stderr, "[sb200] %-34s %9.3f ms\n", label, (t - trace_t0) * 1e3);
+        trace_t0 = now_s();
+    }
+
+    // Caching device allocator.  All kernels of a context run on one stream, so a block released by the host can be handed
+    // out again immediately: work that still uses it was enqueued earlier on the same stream.  (sb200_construct, which also
+    // copies on a second stream, keeps its buffers until both streams have drained.)  Requests are rounded up to 256 B and
+    // served from the smallest cached block that is large enough but not more than 25 % larger; otherwise cudaMalloc.
+    std::multimap<size_t, void *> dev_free_blocks;
+    std::unordered_map<void *, size_t> dev_block_size;
+    size_t dev_bytes_total = 0;
+    void *dev_alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t) 255;
+        auto it = dev_free_blocks.lower_bound(bytes);
+        if (it != dev_free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+            void *p = it->second;
+            dev_free_blocks.erase(it);
+            return p;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {   // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            dev_trim();
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            char b[160];
+            snprintf(b, sizeof b, "sb200: out of device memory allocating %zu bytes (%zu bytes held): %s", bytes, dev_bytes_total,
+                     cudaGetErrorString(e));
+            cudaGetLastError();
+            throw sb200_error(2, b);
+        }
+        dev_block_size[p] = bytes;
+        dev_bytes_total += bytes;
+        return p;
+    }
+    void dev_free(void *p) {
+        auto it = dev_block_size.find(p);
+        if (it != dev_block_size.end()) dev_free_blocks.insert({it->second, p});
+    }
+    void dev_trim() {   // release every cached (currently unused) block
+        cudaStreamSynchronize(stream);
+        cudaStreamSynchronize(copy_stream);
+        for (auto &kv : dev_free_blocks) {
+            cudaFree(kv.second);
+            dev_bytes_total -= kv.first;
+            dev_block_size.erase(kv.second);
+        }
+        dev_free_blocks.clear();
+    }
+
+    // Pinned host buffers for results that go back to the caller (sb200_construct): cudaMallocHost of gigabytes costs
+    // hundreds of milliseconds, so blocks are recycled across calls (grow-only, freed with the context).
+    struct PinnedBlock { void *p; size_t cap; bool used; };
+    std::vector<PinnedBlock> pinned_pool;
+    void *pinned_get(size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        PinnedBlock *best = nullptr;
+        for (auto &b : pinned_pool)
+            if (!b.used && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+        if (best) { best->used = true; return best->p; }
+        void *p = nullptr;
+        size_t cap = bytes + bytes / 16;   // a little slack so that run-to-run size jitter still hits the pool
+        if (cudaMallocHost(&p, cap) != cudaSuccess) throw sb200_error(2, "cudaMallocHost failed for result buffer");
+        pinned_pool.push_back({p, cap, true});
+        return p;
+    }
+    void pinned_put(void *p) {
+        for (auto &b : pinned_pool)
+            if (b.p == p) { b.used = false; return; }
+    }
+    void pinned_free_all() {
+        for (auto &b : pinned_pool) cudaFreeHost(b.p);
+        pinned_pool.clear();
+    }
 };
 
-// Stream-ordered device array.
+// Device array from the context's caching allocator (sb200_ctx::dev_alloc): blocks are recycled in stream order on the
+// context's compute stream, so a steady-state run of the path makes no driver allocation calls at all.
 template<class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    cudaStream_t s = nullptr;
+    sb200_ctx *c = nullptr;
     DevBuf() {}
     DevBuf(sb200_ctx *ctx, size_t count) { alloc(ctx, count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), c(o.c) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; c = o.c; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(sb200_ctx *ctx, size_t count) {
         release();
-        s = ctx->stream;
+        c = ctx;
         n = count;
-        CUDA_CHECK(cudaMallocAsync((void **) &p, (count ? count : 1) * sizeof(T), s));
+        p = (T *) ctx->dev_alloc((count ? count : 1) * sizeof(T));
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) c->dev_free(p);
         p = nullptr; n = 0;
     }
-    void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), c->stream)); }
     size_t bytes() const { return n * sizeof(T); }
 };
 

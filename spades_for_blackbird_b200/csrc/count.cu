@@ -246,7 +246,9 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     if (2 * K < 24) return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
     using Cfg = SegCfg<W>;
     DevBuf<uint64_t> scratch(ctx, n * W);
+    ctx->trace_point("  instances ready");
     uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, prefix_passes(W, K, B, drop_marker));
+    ctx->trace_point("  prefix passes");
     uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
 
     PrefixKey pk{prefix_shift(W, K), B, drop_marker ? 1 : 0};
@@ -262,6 +264,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     uint32_t n_dirty = 0;
     CUDA_CHECK(cudaMemcpyAsync(&n_dirty, ctrl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->trace_point("  heads + ranges");
 
     DevBuf<uint64_t> side_recs;
     DevBuf<uint32_t> side_cnts;
@@ -300,17 +303,18 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         auto seg_chunk_kernel_ = seg_chunk_kernel<W, true>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
-               cnt_full.p, total_dev.p, n_chunks);
+               cnt_full.p, total_dev.p, n_chunks, pk.shift);
     } else {
         auto seg_chunk_kernel_ = seg_chunk_kernel<W, false>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
-               (uint32_t *) nullptr, total_dev.p, n_chunks);
+               (uint32_t *) nullptr, total_dev.p, n_chunks, pk.shift);
     }
     unsigned long long u64 = 0;
     CUDA_CHECK(cudaMemcpyAsync(&u64, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     uint64_t u = u64;
+    ctx->trace_point("  chunk kernel");
 
     sb200_kmers *s = new sb200_kmers();
     s->ctx = ctx; s->k = (unsigned) K; s->words = W; s->num_buckets = B; s->instances = n;
@@ -337,6 +341,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     }
     finish_tables<W>(ctx, s, B);
     inst.release();
+    ctx->trace_point("  shrink + tables");
     return s;
 }
 

@@ -36,20 +36,28 @@ __global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const ui
     inv[id] = (uint32_t) i;
 }
 
+// Besides the two mask bits, every (k+1)-mer x = y -> z also records the link itself: succ[y] = z and, for the other
+// strand, succ[rc(z)] = rc(y) (oriented vertex = 2 * index + strand).  A vertex with a single outgoing edge receives
+// exactly one such write, so the unitig stage gets its successor links without a second round of MPHF lookups;
+// vertices with several outgoing edges receive several (racing) writes and never read the slot.
 template<int WS, int W>
-__global__ void __launch_bounds__(256) fill_masks_kernel(MphfDev m, const uint64_t *__restrict__ kpomers, uint64_t n, int k, uint8_t *__restrict__ masks) {
+__global__ void __launch_bounds__(256) fill_masks_kernel(MphfDev m, const uint64_t *__restrict__ kpomers, uint64_t n, int k, uint8_t *__restrict__ masks,
+                                                        uint32_t *__restrict__ succ) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t x[WS], a[W];
     load_rec<WS>(kpomers, i, x);
     uint32_t pnucl = kmer_base(x, 0), nnucl = kmer_base(x, k);
-    bool minimal;
+    bool min_a, min_b;
     kmer_subwindow<WS, W>(x, 0, k, a);
-    uint64_t ia = mphf_lookup_oriented<W>(m, a, k, &minimal);
-    mask_or(masks, ia, minimal ? nnucl : 7u - nnucl);                 // AddOutgoing(nnucl, as_is)
+    uint64_t ia = mphf_lookup_oriented<W>(m, a, k, &min_a);
+    mask_or(masks, ia, min_a ? nnucl : 7u - nnucl);                 // AddOutgoing(nnucl, as_is)
     kmer_subwindow<WS, W>(x, 1, k, a);
-    uint64_t ib = mphf_lookup_oriented<W>(m, a, k, &minimal);
-    mask_or(masks, ib, minimal ? pnucl + 4u : 7u - (pnucl + 4u));    // AddIncoming(pnucl, as_is)
+    uint64_t ib = mphf_lookup_oriented<W>(m, a, k, &min_b);
+    mask_or(masks, ib, min_b ? pnucl + 4u : 7u - (pnucl + 4u));    // AddIncoming(pnucl, as_is)
+    uint32_t vy = 2u * (uint32_t) ia + (min_a ? 0u : 1u), vz = 2u * (uint32_t) ib + (min_b ? 0u : 1u);
+    succ[vy] = vz;
+    succ[vz ^ 1u] = vy ^ 1u;
 }
 
 template<int WS, int W>
@@ -61,10 +69,14 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     e->masks.zero();
     e->idx.alloc(ctx, kmers->size);
     e->inv.alloc(ctx, kmers->size);
+    SB200_REQUIRE(2 * kmers->size < 0xFFFFFFF0ull, "more than 2^31 k-mers on one GPU: shard the input");
+    e->succ.alloc(ctx, 2 * kmers->size + 2);
+    e->succ_valid = true;
     MphfDev m = mphf_dev(mphf);
     LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p);
     auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
-    LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p);
+    LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,
+           e->succ.p);
     return e;
 }
 
@@ -218,6 +230,7 @@ static uint64_t tipclip_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_
     unsigned long long r = 0;
     CUDA_CHECK(cudaMemcpyAsync(&r, removed.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (r) ext->succ_valid = false;   // a junction that lost a tip may now have a single successor the racing writes did not keep
     return r;
 }
 

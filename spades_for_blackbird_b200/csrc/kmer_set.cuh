@@ -48,6 +48,8 @@ struct sb200_ext {   // DeBruijnExtensionIndex payload: masks in MPHF-index orde
     DevBuf<uint8_t> masks;      // size bytes (padded to a multiple of 4), PerfectHashMap::data_
     DevBuf<uint32_t> idx;       // MPHF index of every k-mer in file order
     DevBuf<uint32_t> inv;       // file position of every MPHF index
+    DevBuf<uint32_t> succ;      // successor of every oriented vertex with one outgoing edge (2 * size entries)
+    bool succ_valid = false;    // false once the masks were edited (tip clipping): links are then recomputed by lookup
 };
 
 struct sb200_unitigs {

@@ -262,14 +262,23 @@ void mphf_lookup_device(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *rec
 }
 
 // KMerIndex::serialize (kmer_index.hpp:99-105) of per-bucket mphf::save (BooPHF.h:514-532) of bitVector::save (:316-323)
+uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, const uint64_t *ranks_host, uint8_t *out);
+
 uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out) {
     sb200_ctx *ctx = m->ctx;
-    std::vector<uint64_t> bits(m->total_words + 1), ranks(m->total_ranks + 1);
+    std::vector<uint64_t> bits, ranks;
     if (out) {
+        bits.resize(m->total_words + 1); ranks.resize(m->total_ranks + 1);
         CUDA_CHECK(cudaMemcpyAsync(bits.data(), m->bits.p, m->total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(ranks.data(), m->ranks.p, m->total_ranks * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
+    return mphf_serialize_host(m, bits.data(), ranks.data(), out);
+}
+
+// bits_host / ranks_host: host copies of the device arrays (only read when out != nullptr)
+uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, const uint64_t *ranks_host, uint8_t *out) {
+    struct { const uint64_t *b; const uint64_t *data() const { return b; } } bits{bits_host}, ranks{ranks_host};
     uint64_t total = 0;
     uint8_t *p = out;
     auto put = [&](const void *src, size_t n) {

@@ -108,28 +108,38 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
 
-    uint64_t rec[ITEMS][W];
-    uint32_t dig[ITEMS];
-    uint32_t loc[ITEMS];
+    // Only (digit, in-warp offset) is kept per record — 16 registers instead of the 16 records themselves — so that six
+    // CTAs fit on an SM; the record is read again when it is moved (the tile was just read: an L1/L2 hit, not HBM).
+    uint32_t info[ITEMS];   // bits 0-7 digit, bits 8-31 offset among the warp's records with the same digit
     const uint64_t warp_base = (uint64_t) blockIdx.x * (RS_THREADS * ITEMS) + (uint64_t) warp * (32 * ITEMS);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t dg[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {   // all loads of the tile first (memory-level parallelism), ranking afterwards
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+        dg[i] = 0;
+        if (idx < n) {
+            if (sel.word >= 0) {
+                dg[i] = (uint32_t) (in[idx * W + sel.word] >> sel.shift) & 0xFFu;
+            } else {
+                uint64_t r[W];
+                load_rec<W>(in, idx, r);
+                dg[i] = rs_digit<W>(r, sel);
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
         bool ok = idx < n;
-        uint32_t d = 0;
-        if (ok) {
-            load_rec<W>(in, idx, rec[i]);
-            d = rs_digit<W>(rec[i], sel);
-        }
+        uint32_t d = dg[i];
         uint32_t valid = __ballot_sync(0xffffffffu, ok);
         uint32_t peers = __match_any_sync(0xffffffffu, d) & valid;
         uint32_t old = ok ? cnt[warp][d] : 0;
         __syncwarp();
         if (ok && (peers & lt_mask) == 0) cnt[warp][d] = old + __popc(peers);
         __syncwarp();
-        dig[i] = d;
-        loc[i] = old + __popc(peers & lt_mask);
+        info[i] = d | ((old + __popc(peers & lt_mask)) << 8);
     }
     __syncthreads();
     {   // one thread per bin: turn per-warp counts into per-warp global bases
@@ -146,7 +156,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
-        if (idx < n) store_rec<W>(out, (uint64_t) cnt[warp][dig[i]] + loc[i], rec[i]);
+        if (idx < n) {
+            uint64_t r[W];
+            load_rec<W>(in, idx, r);
+            store_rec<W>(out, (uint64_t) cnt[warp][info[i] & 0xFFu] + (info[i] >> 8), r);
+        }
     }
 }
 

@@ -3,13 +3,18 @@
 // After three stable counting passes (two bytes of the most significant record word, then the hash bucket) the
 // instance array is ordered by (bucket, 16-bit value prefix).  A "segment" is a maximal run of records sharing that
 // prefix: a few dozen records for the BASELINE workloads.  Finishing the order with twelve more full-array LSD passes
-// (what round-1's first version did) moves every record 12 more times through HBM; instead each CTA stages a run of
-// whole segments (<= CAP records) in shared memory and ranks every record inside its own segment by direct
-// comparison (rank = #smaller + #equal-before), which also yields "am I the first of my value" and the multiplicity.
-// Representatives are compacted with a block scan and written straight to their final position: the global offset of
-// a CTA comes from a decoupled look-back over per-CTA unique counts, so the array is read once and only the unique
-// records are written.  Segments too long for shared memory (highly repeated k-mers, low-complexity sequence) make
-// their CTA "dirty"; dirty ranges are sorted by the generic LSD path first and the CTA merely copies the result.
+// (what round-1's first version did) moves every record 12 more times through HBM; instead each CTA takes a run of
+// whole segments (<= CAP records) and
+//   (1) deduplicates every warp tile of 32 consecutive records with match.any on the record words — equal records elect
+//       their lowest lane, which keeps the value and the number of copies; the bulk of the input (copies of the same
+//       genomic k-mer) disappears here at a cost of W match instructions per 32 records;
+//   (2) ranks the survivors (kept in order in shared memory, hence still grouped by segment) inside their segment by
+//       direct comparison of a 32-bit tag (the key bits right below the prefix), falling back to the full key on equal
+//       tags; equal survivors from different tiles merge their counts;
+//   (3) compacts "first of its value" flags in sorted position with a block scan and obtains its global offset from a
+//       decoupled look-back over per-CTA unique counts, so the array is read once and only unique records are written.
+// Segments too long for shared memory (highly repeated k-mers, low-complexity sequence) make their CTA "dirty"; dirty
+// ranges are sorted by the generic LSD path first and the CTA merely copies the result.
 #pragma once
 #include "common.cuh"
 #include "kmer_ops.cuh"
@@ -19,10 +24,10 @@
 namespace sb200 {
 
 template<int W> struct SegCfg {
-    static constexpr int CAP = (W == 1) ? 8192 : (W == 2) ? 4096 : 2048;   // records staged per CTA (64 KB of keys)
+    static constexpr int CAP = (W == 1) ? 8192 : (W == 2) ? 4096 : 2048;   // records per CTA (64 KB of keys)
     static constexpr int C = CAP / 2;        // a CTA owns the segments that START in its C-record window
     static constexpr int MAXSEG = CAP / 2;   // longest segment the shared-memory path accepts
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = 512;
 };
 
 struct PrefixKey {   // what defines a segment
@@ -135,36 +140,35 @@ __device__ __forceinline__ unsigned long long lb_pack(unsigned long long flag, u
 // Shared memory of seg_chunk_kernel, in bytes
 template<int W>
 constexpr size_t seg_chunk_smem() {
-    return (size_t) SegCfg<W>::CAP * W * 8      // keys of the warp-tile representatives
-           + (size_t) SegCfg<W>::CAP * 4         // their multiplicities
-           + (size_t) SegCfg<W>::CAP * 4         // representative flag by sorted position, then its exclusive scan
-           + (size_t) SegCfg<W>::CAP             // segment-head flag per representative
-           + (size_t) (SegCfg<W>::CAP / 32 + 1) * 4;   // representatives per warp tile, then its exclusive scan
+    return (size_t) SegCfg<W>::CAP * W * 8      // keys of the warp-tile survivors
+           + (size_t) SegCfg<W>::CAP * 4         // their 32-bit tags
+           + (size_t) SegCfg<W>::CAP * 2         // "first of its value" flag by sorted position, then its exclusive scan
+           + (size_t) SegCfg<W>::CAP             // bit 7: survivor starts a segment; bits 0-5: copies merged in its tile (<= 32)
+           + (size_t) (SegCfg<W>::CAP / 32 + 1) * 4;   // survivors per warp tile, then its exclusive scan
 }
 
-// Two levels.  (1) Every warp tile of 32 consecutive records is deduplicated with match.any on the record words: equal
-// records elect their lowest lane, which keeps the value and the number of copies — the bulk of the input (copies of the
-// same genomic k-mer) disappears here at a cost of W match instructions per 32 records.  (2) The survivors of the CTA
-// (kept in order, hence still grouped by segment) are ranked inside their segment by direct comparison; equal survivors
-// from different tiles merge their counts.  A block scan over "first of its value" flags in sorted position and a
-// decoupled look-back over CTAs give every unique record its final place.
+// the 32 key bits right below the 16-bit prefix (fewer for very short k-mers): monotone in the record order inside a segment
+__device__ __forceinline__ uint32_t seg_tag(uint64_t w0, int shift) {
+    return shift >= 32 ? (uint32_t) (w0 >> (shift - 32)) : (uint32_t) (w0 << (32 - shift));
+}
+
 template<int W, bool COUNTS>
 __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uint64_t *__restrict__ recs, uint64_t n,
                                                                       const uint32_t *__restrict__ hb, const ChunkRange *__restrict__ ranges,
                                                                       const uint64_t *__restrict__ side_recs, const uint32_t *__restrict__ side_cnts,
                                                                       unsigned long long *__restrict__ status, uint32_t *__restrict__ tile_counter,
                                                                       uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt,
-                                                                      unsigned long long *__restrict__ total_out, uint32_t n_chunks) {
+                                                                      unsigned long long *__restrict__ total_out, uint32_t n_chunks, int shift) {
     constexpr int CAP = SegCfg<W>::CAP, THREADS = SegCfg<W>::THREADS;
     constexpr int NT = CAP / 32;               // warp tiles per CTA
     constexpr int TPW = NT / (THREADS / 32);   // warp tiles per warp
     constexpr uint32_t PER = CAP / THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *pkey = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *pcnt = reinterpret_cast<uint32_t *>(pkey + (size_t) CAP * W);
-    uint32_t *sflag = pcnt + CAP;
-    uint8_t *phead = reinterpret_cast<uint8_t *>(sflag + CAP);
-    uint32_t *tileoff = reinterpret_cast<uint32_t *>(phead + CAP);
+    uint32_t *ptag = reinterpret_cast<uint32_t *>(pkey + (size_t) CAP * W);
+    uint16_t *sflag = reinterpret_cast<uint16_t *>(ptag + CAP);
+    uint8_t *pinfo = reinterpret_cast<uint8_t *>(sflag + CAP);
+    uint32_t *tileoff = reinterpret_cast<uint32_t *>(pinfo + CAP);
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_np;
     __shared__ unsigned long long s_base;
@@ -181,21 +185,25 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     // ---- level 1: warp-tile deduplication, records straight from global memory into registers ---------------------------
     uint64_t rec[TPW][W];
     uint32_t mult[TPW];
-    uint32_t rep_bits = 0, head_bits = 0;   // bit t: my record of tile t is a tile representative / starts a segment
+    uint32_t rep_bits = 0, head_bits = 0;   // bit t: my record of tile t is a tile survivor / starts a segment
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+        const uint32_t p = (warp * TPW + t) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < W; ++j) rec[t][j] = 0;
+        if (p < cnt) {
+            load_rec<W>(recs, (uint64_t) s + p, rec[t]);
+            const uint64_t g = (uint64_t) s + p;
+            if ((__ldg(hb + (g >> 5)) >> (g & 31)) & 1u) head_bits |= 1u << t;
+        }
+    }
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
         const uint32_t tile = warp * TPW + t;
         const uint32_t p = tile * 32 + lane;
         const bool ok = p < cnt;
-#pragma unroll
-        for (int j = 0; j < W; ++j) rec[t][j] = 0;
         uint32_t peers = 0xFFFFFFFFu;
         if (tile * 32 < cnt) {   // warp-uniform
-            if (ok) {
-                load_rec<W>(recs, (uint64_t) s + p, rec[t]);
-                const uint64_t g = (uint64_t) s + p;
-                if ((hb[g >> 5] >> (g & 31)) & 1u) head_bits |= 1u << t;
-            }
 #pragma unroll
             for (int j = 0; j < W; ++j) peers &= __match_any_sync(0xffffffffu, rec[t][j]);
             peers &= __ballot_sync(0xffffffffu, ok);
@@ -228,8 +236,8 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
             const uint32_t o = tileoff[tile] + (uint32_t) __popc(m & ((1u << lane) - 1u));
 #pragma unroll
             for (int j = 0; j < W; ++j) pkey[(size_t) o * W + j] = rec[t][j];
-            pcnt[o] = mult[t];
-            phead[o] = (uint8_t) ((head_bits >> t) & 1u);
+            ptag[o] = seg_tag(rec[t][0], shift);
+            pinfo[o] = (uint8_t) ((((head_bits >> t) & 1u) << 7) | (mult[t] - 1u));   // copies-1 fits 5 bits
         }
     }
     for (uint32_t i = threadIdx.x; i < np; i += THREADS) sflag[i] = 0;
@@ -245,27 +253,30 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
         const uint32_t p = threadIdx.x + i * THREADS;
         if (p >= np) continue;
         uint32_t sb = p;
-        while (!phead[sb]) --sb;             // entry 0 is a head by construction
-        uint32_t se = p + 1;
-        while (se < np && !phead[se]) ++se;
-        uint64_t me[W];
+        while (!(pinfo[sb] & 0x80u)) --sb;             // entry 0 is a head by construction
+        const uint32_t mytag = ptag[p];
+        uint32_t less = 0, eq_before = 0, total = (uint32_t) (pinfo[p] & 0x3Fu) + 1u;
+        for (uint32_t q = sb; q < np; ++q) {
+            if (q != sb && (pinfo[q] & 0x80u)) break;  // next segment
+            if (q == p) continue;
+            const uint32_t t = ptag[q];
+            if (t < mytag) { ++less; continue; }
+            if (t > mytag) continue;
+            // equal tags: decide on the full key (duplicates of my value from other tiles, or a true 48-bit-prefix tie)
+            uint64_t me[W], o[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) me[j] = pkey[(size_t) p * W + j];
-        uint32_t less = 0, eq_before = 0, total = 0;
-        for (uint32_t q = sb; q < se; ++q) {
-            uint64_t o[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) o[j] = pkey[(size_t) q * W + j];
-            const bool lt = rec_less<W>(o, me);
-            const bool eq = kmer_eq<W>(o, me);
-            less += lt ? 1u : 0u;
-            eq_before += (eq && q < p) ? 1u : 0u;
-            if (COUNTS) total += eq ? pcnt[q] : 0u;
+            for (int j = 0; j < W; ++j) { me[j] = pkey[(size_t) p * W + j]; o[j] = pkey[(size_t) q * W + j]; }
+            if (kmer_eq<W>(o, me)) {
+                eq_before += (q < p) ? 1u : 0u;
+                total += (uint32_t) (pinfo[q] & 0x3Fu) + 1u;
+            } else if (rec_less<W>(o, me)) {
+                ++less;
+            }
         }
         if (eq_before == 0) {
             rep_pos[i] = sb + less;
             rep_cnt[i] = total;
-            sflag[sb + less] = 1u;
+            sflag[sb + less] = 1;
         }
     }
     __syncthreads();
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
 #pragma unroll
     for (uint32_t i = 0; i < PER; ++i) {
         const uint32_t p = threadIdx.x * PER + i;
-        if (p < np) sflag[p] = pre;
+        if (p < np) sflag[p] = (uint16_t) pre;
         pre += v[i];
     }
     const uint32_t my_total = cr.dirty ? cr.side_cnt : total_u;

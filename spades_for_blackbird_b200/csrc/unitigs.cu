@@ -3,12 +3,14 @@
 // Replaces UnbranchingPathExtractor::ExtractUnbranchingPathsAndLoops
 // (C/assembly_graph/construction/debruijn_graph_constructor.hpp:182-388): the reference walks from every outgoing
 // edge of every junction one MPHF lookup at a time and appends one nucleotide per step; here
-//   1. every oriented non-junction k-mer gets its successor node with ONE lookup (succ_kernel),
-//   2. pointer jumping gives each of them the last vertex of its chain and the distance to it (jump_kernel; a
-//      (pointer, distance) pair is one 64-bit word so in-place updates are always observed consistently),
-//   3. every junction enumerates its start edges in the reference's order (file order of the canonical k-mer,
-//      forward strand then reverse strand, A,C,G,T), gets path length and end junction from step 2 and decides the
-//      orientation filter `!(s < !s)` from the two end k-mers (ties by the first edge nucleotides),
+//   1. every oriented non-junction k-mer knows its successor vertex (recorded for free while the masks were filled,
+//      ext.cu; recomputed with one lookup per vertex only after tip clipping edited the masks),
+//   2. pointer jumping gives each of them the last vertex of its chain and the distance to it (jump_kernel; pointer,
+//      distance and a "finished" flag share one 64-bit word, so in-place updates are always observed consistently),
+//   3. the junctions with outgoing edges are compacted into a work list; every start edge, enumerated in the
+//      reference's order (file order of the canonical k-mer, forward strand then reverse strand, A,C,G,T), gets its
+//      path length and end junction from step 2 and decides the orientation filter `!(s < !s)` from the two end k-mers
+//      (ties by the first edge nucleotides),
 //   4. a scan assigns output slots, heads write k+1 bases, every chain vertex writes its one base in parallel.
 // Output order is therefore the reference's own (paths in discovery order, then perfect loops).
 // Perfect loops (cycles without a junction) are what pointer jumping cannot finish; they are rare and handled by a
@@ -61,11 +63,10 @@ __device__ __forceinline__ int kmer_lex_cmp(const uint64_t *a, const uint64_t *b
     return 0;
 }
 
-// 1. successor links + initial jump state
+// 1a. successor links by lookup (only when the links recorded by fill_masks_kernel are stale)
 template<int W>
 __global__ void __launch_bounds__(256) succ_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k, const uint32_t *__restrict__ idx,
-                                                  const uint8_t *__restrict__ masks, uint32_t *__restrict__ succ,
-                                                  unsigned long long *__restrict__ state) {
+                                                  const uint8_t *__restrict__ masks, uint32_t *__restrict__ succ) {
     uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n) return;
     uint64_t i = t >> 1;
@@ -73,132 +74,146 @@ __global__ void __launch_bounds__(256) succ_kernel(MphfDev m, const uint64_t *__
     uint32_t id = idx[i];
     uint32_t v = 2 * id + strand;
     uint32_t raw = masks[id];
-    if (mask_is_junction(raw)) {
-        succ[v] = NONE;
-        state[v] = pack_state(v, 0, true);
-        return;
-    }
+    if (mask_is_junction(raw)) { succ[v] = NONE; return; }
     uint32_t mk = strand ? mask_conj(raw) : raw;
     uint64_t x[W], y[W];
     oriented_kmer<W>(kmers, i, strand, k, x);
     kmer_shl<W>(x, k, nib_next(mk & 15u), y);
     bool minimal;
     uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-    uint32_t s = 2 * idy + (minimal ? 0u : 1u);
-    succ[v] = s;
-    bool next_is_junction = mask_is_junction(masks[idy]);
-    state[v] = next_is_junction ? pack_state(v, 0, true) : pack_state(s, 1, false);
+    succ[v] = 2 * idy + (minimal ? 0u : 1u);
 }
 
-// 2. one round of pointer jumping; a vertex is finished when its pointer is the last vertex of its chain (ST_DONE)
+// 1b. initial jump state from the links: a vertex whose successor is a junction is the last of its chain
+__global__ void __launch_bounds__(256) state_init_kernel(uint64_t n_nodes, const uint8_t *__restrict__ masks, const uint32_t *__restrict__ succ,
+                                                        unsigned long long *__restrict__ state) {
+    uint64_t v = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    if (mask_is_junction(masks[v >> 1])) { state[v] = pack_state((uint32_t) v, 0, true); return; }
+    uint32_t s = succ[v];
+    state[v] = mask_is_junction(masks[s >> 1]) ? pack_state((uint32_t) v, 0, true) : pack_state(s, 1, false);
+}
+
+// 2. up to JUMPS pointer jumps per vertex and launch; a vertex is finished when its pointer is the last vertex of its
+//    chain (ST_DONE).  In-place: stale reads only make a jump shorter, never wrong.
+constexpr int JUMPS = 4;
 __global__ void __launch_bounds__(256) jump_kernel(unsigned long long *__restrict__ state, uint64_t n_nodes, uint32_t *__restrict__ changed) {
     uint64_t v = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
     unsigned long long sv = state[v];
     if (st_done(sv)) return;
-    unsigned long long sp = state[st_ptr(sv)];
-    state[v] = pack_state(st_ptr(sp), st_dist(sv) + st_dist(sp), st_done(sp));
-    if (*changed == 0) *changed = 1;
-}
-
-struct EdgeInfo {
-    uint32_t v1;       // first vertex after the junction
-    uint32_t n;        // number of appended bases: |s| = k + n
-    bool chain;        // v1 is not a junction (the path has inner vertices)
-    bool keep;         // !(s < !s)
-};
-
-// Everything the reference's ConstructSequenceWithEdge + `if (s < !s) continue` decide for start edge (x, c)
-template<int W>
-__device__ __forceinline__ EdgeInfo eval_edge(const MphfDev &m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ inv,
-                                              const uint8_t *__restrict__ masks, const uint32_t *__restrict__ succ,
-                                              const unsigned long long *__restrict__ state, const uint64_t *x, uint32_t c) {
-    EdgeInfo e;
-    uint64_t y[W], rcn[W];
-    kmer_shl<W>(x, k, c, y);
-    bool minimal;
-    uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-    e.v1 = 2 * idy + (minimal ? 0u : 1u);
-    e.chain = !mask_is_junction(masks[idy]);
-    uint32_t cprime;   // first edge nucleotide of the reverse-complement path, used only to break ties
-    if (!e.chain) {
-        e.n = 1;
-        kmer_rc<W>(y, k, rcn);
-        cprime = 3u - kmer_base(x, 0);
-    } else {
-        unsigned long long st = state[e.v1];
-        uint32_t last = st_ptr(st);
-        e.n = st_dist(st) + 2;
-        uint32_t vn = succ[last];
-        // rc(kmer(vn)): stored record if vn is the reverse strand, else its reverse complement
-        oriented_kmer<W>(kmers, inv[vn >> 1], (vn & 1) ? 0 : 1, k, rcn);
-        uint64_t lk[W];
-        oriented_kmer<W>(kmers, inv[last >> 1], (int) (last & 1), k, lk);
-        cprime = 3u - kmer_base(lk, 0);
+#pragma unroll 1
+    for (int it = 0; it < JUMPS; ++it) {
+        unsigned long long sp = state[st_ptr(sv)];
+        sv = pack_state(st_ptr(sp), st_dist(sv) + st_dist(sp), st_done(sp));
+        if (st_done(sv)) break;
     }
-    int cmp = kmer_lex_cmp<W>(x, rcn);
-    e.keep = cmp > 0 || (cmp == 0 && c >= cprime);
-    return e;
+    state[v] = sv;
+    if (!st_done(sv) && *changed == 0) *changed = 1;
 }
 
-// 3. per oriented junction: number of kept sequences and their total length
-template<int W>
-__global__ void __launch_bounds__(128) edge_count_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k,
-                                                        const uint32_t *__restrict__ idx, const uint32_t *__restrict__ inv,
-                                                        const uint8_t *__restrict__ masks, const uint32_t *__restrict__ succ,
-                                                        const unsigned long long *__restrict__ state, uint32_t *__restrict__ cnt,
-                                                        unsigned long long *__restrict__ bases) {
+// 3a. work list: oriented junctions (t = 2 * file index + strand) that have at least one outgoing edge
+__global__ void __launch_bounds__(256) junction_flag_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
+                                                           uint32_t *__restrict__ flag) {
     uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n) return;
+    uint32_t raw = masks[idx[t >> 1]];
+    uint32_t mk = (t & 1) ? mask_conj(raw) : raw;
+    flag[t] = (mask_is_junction(raw) && (mk & 15u)) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) compact_kernel(const uint32_t *__restrict__ flag_scan, uint64_t n, uint32_t total, uint32_t *__restrict__ list) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = flag_scan[i];
+    uint32_t b = (i + 1 < n) ? flag_scan[i + 1] : total;
+    if (b != a) list[a] = (uint32_t) i;
+}
+
+struct EdgeRec {       // one start edge, stored at 4 * (work-list position) + nucleotide
+    uint32_t v1;       // first vertex after the junction
+    uint32_t n;        // number of appended bases: |s| = k + n; 0 = edge absent or sequence dropped (`s < !s`)
+    uint32_t chain;    // v1 is not a junction (the path has inner vertices)
+    uint32_t pad;
+};
+
+// 3b. everything the reference's ConstructSequenceWithEdge + `if (s < !s) continue` decide for the start edges of one
+//     oriented junction; also the number of kept sequences and their total length
+template<int W>
+__global__ void __launch_bounds__(128) edge_eval_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ jlist,
+                                                       uint32_t n_j, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ inv,
+                                                       const uint8_t *__restrict__ masks, const uint32_t *__restrict__ succ,
+                                                       const unsigned long long *__restrict__ state, EdgeRec *__restrict__ edges,
+                                                       uint32_t *__restrict__ cnt, unsigned long long *__restrict__ bases) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_j) return;
+    uint32_t t = jlist[j];
     uint64_t i = t >> 1;
     int strand = (int) (t & 1);
     uint32_t raw = masks[idx[i]];
+    uint32_t mk = strand ? mask_conj(raw) : raw;
+    uint64_t x[W];
+    oriented_kmer<W>(kmers, i, strand, k, x);
     uint32_t c_kept = 0;
     unsigned long long b = 0;
-    if (mask_is_junction(raw)) {
-        uint32_t mk = strand ? mask_conj(raw) : raw;
-        if (mk & 15u) {
-            uint64_t x[W];
-            oriented_kmer<W>(kmers, i, strand, k, x);
-            for (uint32_t c = 0; c < 4; ++c) {
-                if (!(mk & (1u << c))) continue;
-                EdgeInfo e = eval_edge<W>(m, kmers, k, inv, masks, succ, state, x, c);
-                if (e.keep) { ++c_kept; b += (unsigned long long) k + e.n; }
+#pragma unroll 1
+    for (uint32_t c = 0; c < 4; ++c) {
+        EdgeRec e;
+        e.v1 = 0; e.n = 0; e.chain = 0; e.pad = 0;
+        if (mk & (1u << c)) {
+            uint64_t y[W], rcn[W];
+            kmer_shl<W>(x, k, c, y);
+            bool minimal;
+            uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
+            e.v1 = 2 * idy + (minimal ? 0u : 1u);
+            e.chain = mask_is_junction(masks[idy]) ? 0u : 1u;
+            uint32_t nn, cprime;   // cprime: first edge nucleotide of the reverse-complement path, only breaks ties
+            if (!e.chain) {
+                nn = 1;
+                kmer_rc<W>(y, k, rcn);
+                cprime = 3u - kmer_base(x, 0);
+            } else {
+                unsigned long long st = state[e.v1];
+                uint32_t last = st_ptr(st);
+                nn = st_dist(st) + 2;
+                uint32_t vn = succ[last];
+                // rc(kmer(vn)): the stored record if vn is the reverse strand, else its reverse complement
+                oriented_kmer<W>(kmers, inv[vn >> 1], (vn & 1) ? 0 : 1, k, rcn);
+                uint64_t lk[W];
+                oriented_kmer<W>(kmers, inv[last >> 1], (int) (last & 1), k, lk);
+                cprime = 3u - kmer_base(lk, 0);
             }
+            int cmp = kmer_lex_cmp<W>(x, rcn);
+            bool keep = cmp > 0 || (cmp == 0 && c >= cprime);
+            if (keep) { e.n = nn; ++c_kept; b += (unsigned long long) k + nn; }
         }
+        edges[4ull * j + c] = e;
     }
-    cnt[t] = c_kept;
-    bases[t] = b;
+    cnt[j] = c_kept;
+    bases[j] = b;
 }
 
 // 4a. heads: sequence length, first k+1 bases, and the output slot of the chain (indexed by its first vertex)
 template<int W>
-__global__ void __launch_bounds__(128) edge_emit_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k,
-                                                       const uint32_t *__restrict__ idx, const uint32_t *__restrict__ inv,
-                                                       const uint8_t *__restrict__ masks, const uint32_t *__restrict__ succ,
-                                                       const unsigned long long *__restrict__ state, const uint32_t *__restrict__ cnt_off,
+__global__ void __launch_bounds__(128) edge_emit_kernel(const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ jlist, uint32_t n_j,
+                                                       const EdgeRec *__restrict__ edges, const uint32_t *__restrict__ cnt_off,
                                                        const unsigned long long *__restrict__ base_off, uint32_t *__restrict__ seq_len,
                                                        unsigned long long *__restrict__ seq_off, uint8_t *__restrict__ chars,
                                                        uint32_t *__restrict__ slot) {
-    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n) return;
-    uint64_t i = t >> 1;
-    int strand = (int) (t & 1);
-    uint32_t raw = masks[idx[i]];
-    if (!mask_is_junction(raw)) return;
-    uint32_t mk = strand ? mask_conj(raw) : raw;
-    if (!(mk & 15u)) return;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_j) return;
+    uint32_t t = jlist[j];
+    uint32_t u = cnt_off[j];
+    unsigned long long off = base_off[j];
     uint64_t x[W];
-    oriented_kmer<W>(kmers, i, strand, k, x);
-    uint32_t u = cnt_off[t];
-    unsigned long long off = base_off[t];
+    bool have_x = false;
+#pragma unroll 1
     for (uint32_t c = 0; c < 4; ++c) {
-        if (!(mk & (1u << c))) continue;
-        EdgeInfo e = eval_edge<W>(m, kmers, k, inv, masks, succ, state, x, c);
-        if (!e.keep) continue;
+        EdgeRec e = edges[4ull * j + c];
+        if (e.n == 0) continue;
+        if (!have_x) { oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x); have_x = true; }
         seq_len[u] = (uint32_t) k + e.n;
         seq_off[u] = off;
-        for (int j = 0; j < k; ++j) chars[off + j] = (uint8_t) kmer_base(x, j);
+        for (int q = 0; q < k; ++q) chars[off + q] = (uint8_t) kmer_base(x, q);
         chars[off + k] = (uint8_t) c;
         if (e.chain) slot[e.v1] = u;
         ++u;
@@ -233,18 +248,8 @@ __global__ void loop_flag_kernel(const uint32_t *__restrict__ idx, uint64_t n, c
     if (i >= n) return;
     uint32_t id = idx[i];
     uint32_t f = 0;
-    if (!mask_is_junction(masks[id])) {
-        f = st_done(state[2 * id]) ? 0u : 1u;
-    }
+    if (!mask_is_junction(masks[id])) f = st_done(state[2 * id]) ? 0u : 1u;
     flag[i] = f;
-}
-
-__global__ void loop_compact_kernel(const uint32_t *__restrict__ flag_scan, uint64_t n, uint32_t total, uint32_t *__restrict__ list) {
-    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t a = flag_scan[i];
-    uint32_t b = (i + 1 < n) ? flag_scan[i + 1] : total;
-    if (b != a) list[a] = (uint32_t) i;
 }
 
 __device__ __forceinline__ bool chars_less_rc(const uint8_t *s, unsigned long long L) {   // s < !s
@@ -364,19 +369,30 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     int k = (int) kmers->k;
     uint64_t n_nodes = 2 * n;
     MphfDev m = mphf_dev(mphf);
-    DevBuf<uint32_t> succ(ctx, n_nodes);
+    // 1. successor links
+    DevBuf<uint32_t> succ_own;
+    const uint32_t *succ = ext->succ.p;
+    if (!ext->succ_valid) {
+        succ_own.alloc(ctx, n_nodes);
+        LAUNCH(ctx, succ_kernel<W>, div_up(n_nodes, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, succ_own.p);
+        succ = succ_own.p;
+    }
     DevBuf<unsigned long long> state(ctx, n_nodes);
-    LAUNCH(ctx, succ_kernel<W>, div_up(n_nodes, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, succ.p, state.p);
-    // 2. pointer jumping: chains finish in ceil(log2(longest chain)) rounds; only perfect loops never do
-    DevBuf<uint32_t> changed(ctx, 40);
+    LAUNCH(ctx, state_init_kernel, div_up(n_nodes, 256), 256, 0, n_nodes, ext->masks.p, succ, state.p);
+    // 2. pointer jumping: every jump of a launch adds at least the distance its target had reached in the previous launch,
+    //    so the guaranteed reach grows by (1 + JUMPS)x per launch: 5^16 > 2^32 vertices.  Whatever is still unfinished after
+    //    MAX_ROUNDS launches lies on a perfect loop.
+    constexpr int MAX_ROUNDS = 16;
+    DevBuf<uint32_t> changed(ctx, MAX_ROUNDS + 2);
     changed.zero();
     int rounds = 0;
-    for (; rounds < 34; ++rounds) {
+    bool converged = false;
+    for (; rounds < MAX_ROUNDS; ++rounds) {
         LAUNCH(ctx, jump_kernel, div_up(n_nodes, 256), 256, 0, state.p, n_nodes, changed.p + rounds);
         uint32_t ch = 0;
         CUDA_CHECK(cudaMemcpyAsync(&ch, changed.p + rounds, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        if (!ch) break;
+        if (!ch) { converged = true; break; }
     }
     // perfect loops present?
     uint32_t n_loop_nodes = 0;
@@ -384,7 +400,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     unsigned long long loop_totals[2] = {0, 0};
     DevBuf<unsigned long long> totals_dev(ctx, 4);
     DevBuf<uint8_t> visited, scratch;
-    if (with_loops && rounds >= 34) {
+    if (with_loops && !converged) {
         DevBuf<uint32_t> flag(ctx, n + 1);
         DevBuf<uint32_t> tot(ctx, 1);
         LAUNCH(ctx, loop_flag_kernel, div_up(n, 256), 256, 0, ext->idx.p, n, ext->masks.p, state.p, flag.p);
@@ -393,28 +409,43 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (n_loop_nodes) {
             loop_list.alloc(ctx, n_loop_nodes);
-            LAUNCH(ctx, loop_compact_kernel, div_up(n, 256), 256, 0, flag.p, n, n_loop_nodes, loop_list.p);
+            LAUNCH(ctx, compact_kernel, div_up(n, 256), 256, 0, flag.p, n, n_loop_nodes, loop_list.p);
             visited.alloc(ctx, n + 1); visited.zero();
             scratch.alloc(ctx, (uint64_t) n_loop_nodes + k + 8);
-            LAUNCH(ctx, loops_kernel<W>, 1, 1, 0, kmers->data.p, k, ext->idx.p, ext->masks.p, succ.p, loop_list.p, n_loop_nodes, visited.p, 0,
+            LAUNCH(ctx, loops_kernel<W>, 1, 1, 0, kmers->data.p, k, ext->idx.p, ext->masks.p, succ, loop_list.p, n_loop_nodes, visited.p, 0,
                    totals_dev.p, scratch.p, 0u, 0ull, (uint32_t *) nullptr, (unsigned long long *) nullptr, (uint8_t *) nullptr);
             CUDA_CHECK(cudaMemcpyAsync(loop_totals, totals_dev.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         }
     }
-    // 3. start edges
-    DevBuf<uint32_t> cnt(ctx, n_nodes + 1);
-    DevBuf<unsigned long long> bases(ctx, n_nodes + 1);
-    LAUNCH(ctx, edge_count_kernel<W>, div_up(n_nodes, 128), 128, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, succ.p, state.p,
-           cnt.p, bases.p);
-    DevBuf<uint32_t> cnt_total(ctx, 1);
-    exclusive_scan<uint32_t>(ctx, cnt.p, n_nodes, cnt_total.p);
-    exclusive_scan<unsigned long long>(ctx, bases.p, n_nodes, totals_dev.p + 2);
+    // 3. start edges of the junctions
+    uint32_t n_j = 0;
+    DevBuf<uint32_t> jlist;
+    {
+        DevBuf<uint32_t> flag(ctx, n_nodes + 1);
+        DevBuf<uint32_t> tot(ctx, 1);
+        LAUNCH(ctx, junction_flag_kernel, div_up(n_nodes, 256), 256, 0, n, ext->idx.p, ext->masks.p, flag.p);
+        exclusive_scan<uint32_t>(ctx, flag.p, n_nodes, tot.p);
+        CUDA_CHECK(cudaMemcpyAsync(&n_j, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        jlist.alloc(ctx, (uint64_t) n_j + 1);
+        if (n_j) LAUNCH(ctx, compact_kernel, div_up(n_nodes, 256), 256, 0, flag.p, n_nodes, n_j, jlist.p);
+    }
+    DevBuf<EdgeRec> edges(ctx, 4ull * n_j + 4);
+    DevBuf<uint32_t> cnt(ctx, (uint64_t) n_j + 1);
+    DevBuf<unsigned long long> bases(ctx, (uint64_t) n_j + 1);
     uint32_t n_paths = 0;
     unsigned long long path_bases = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_paths, cnt_total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&path_bases, totals_dev.p + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (n_j) {
+        LAUNCH(ctx, edge_eval_kernel<W>, div_up(n_j, 128), 128, 0, m, kmers->data.p, k, jlist.p, n_j, ext->idx.p, ext->inv.p, ext->masks.p, succ,
+               state.p, edges.p, cnt.p, bases.p);
+        DevBuf<uint32_t> cnt_total(ctx, 1);
+        exclusive_scan<uint32_t>(ctx, cnt.p, n_j, cnt_total.p);
+        exclusive_scan<unsigned long long>(ctx, bases.p, n_j, totals_dev.p + 2);
+        CUDA_CHECK(cudaMemcpyAsync(&n_paths, cnt_total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&path_bases, totals_dev.p + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
 
     uint64_t n_seqs = (uint64_t) n_paths + loop_totals[0];
     uint64_t n_bases = path_bases + loop_totals[1];
@@ -424,15 +455,15 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     out->word_off.alloc(ctx, n_seqs + 1);
     DevBuf<unsigned long long> seq_off(ctx, n_seqs + 1);
     DevBuf<uint8_t> chars(ctx, n_bases + 8);
-    DevBuf<uint32_t> slot(ctx, n_nodes);
-    CUDA_CHECK(cudaMemsetAsync(slot.p, 0xFF, n_nodes * 4, ctx->stream));
     if (n_paths) {
-        LAUNCH(ctx, edge_emit_kernel<W>, div_up(n_nodes, 128), 128, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, succ.p, state.p,
-               cnt.p, bases.p, out->len.p, seq_off.p, chars.p, slot.p);
+        DevBuf<uint32_t> slot(ctx, n_nodes);
+        CUDA_CHECK(cudaMemsetAsync(slot.p, 0xFF, n_nodes * 4, ctx->stream));
+        LAUNCH(ctx, edge_emit_kernel<W>, div_up(n_j, 128), 128, 0, kmers->data.p, k, jlist.p, n_j, edges.p, cnt.p, bases.p, out->len.p, seq_off.p,
+               chars.p, slot.p);
         LAUNCH(ctx, chain_emit_kernel, div_up(n_nodes, 256), 256, 0, n_nodes, k, ext->masks.p, state.p, slot.p, seq_off.p, chars.p);
     }
     if (loop_totals[0]) {
-        LAUNCH(ctx, loops_kernel<W>, 1, 1, 0, kmers->data.p, k, ext->idx.p, ext->masks.p, succ.p, loop_list.p, n_loop_nodes, visited.p, 1,
+        LAUNCH(ctx, loops_kernel<W>, 1, 1, 0, kmers->data.p, k, ext->idx.p, ext->masks.p, succ, loop_list.p, n_loop_nodes, visited.p, 1,
                totals_dev.p, scratch.p, n_paths, path_bases, out->len.p, seq_off.p, chars.p);
     }
     // 5. pack to 2 bits per base, every sequence word-aligned (the layout of Sequence / the binary reads)
@@ -447,6 +478,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     if (n_seqs)
         LAUNCH(ctx, pack_kernel, div_up(n_seqs * 32, 256), 256, 0, chars.p, seq_off.p, out->len.p, (const unsigned long long *) out->word_off.p, n_seqs,
                out->words.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // temporaries above are released stream-ordered; results are ready
     return out;
 }
 
