@@ -67,6 +67,7 @@ struct sb200_ctx {
     // SB200_TRACE=1: host-side wall time between trace points (each point drains the stream first), to stderr
     bool trace = false;
     double trace_t0 = 0;
+    bool force_jump_path = false;   // SB200_FORCE_JUMP=1: always extract unitigs by pointer jumping (tests cover both paths)
     static double now_s() {
         timespec ts;
         clock_gettime(CLOCK_MONOTONIC, &ts);

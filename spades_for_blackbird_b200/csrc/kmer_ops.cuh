@@ -260,8 +260,17 @@ DEVINL void kmer_shl(const uint64_t *x, int K, uint32_t c, uint64_t *out) {
         uint64_t nxt = (j + 1 < W) ? x[j + 1] : 0;
         out[j] = (x[j] >> 2) | (nxt << 62);
     }
-    int i = K - 1;
-    out[i >> 5] |= (uint64_t) c << (2 * (i & 31));
+    out[W - 1] |= (uint64_t) c << (2 * ((K - 1) & 31));   // base K-1 always lives in the last word (constant index: registers)
+}
+
+// base i of a W-word k-mer for a run-time i, without dynamic register-array indexing (which would spill x to local memory)
+template<int W>
+DEVINL uint32_t kmer_base_w(const uint64_t *x, int i) {
+    uint64_t w = x[0];
+#pragma unroll
+    for (int j = 1; j < W; ++j)
+        if ((i >> 5) == j) w = x[j];
+    return (uint32_t) (w >> (2 * (i & 31))) & 3u;
 }
 
 // InOutMask::conjugate: bit-reverse the byte (kmer_extension_index.hpp:87)

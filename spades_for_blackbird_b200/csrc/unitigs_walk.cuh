@@ -1,0 +1,231 @@
+// unitigs_walk.cuh — unbranching paths by direct walks, one thread per start edge (included by unitigs.cu).
+//
+// When no chain is longer than WALK_LIMIT vertices (every read set with sequencing errors: a branch every few bases),
+// list ranking is overkill.  Every outgoing edge of every oriented junction is a work item, listed in the reference's
+// discovery order (file order of the canonical k-mer, forward strand then reverse strand, A,C,G,T).  A thread follows its
+// edge with one MPHF lookup per step — bit-vectors, rank samples and masks together are ~130 MB and stay L2-resident —
+// exactly like the reference's ConstructSequenceWithEdge (debruijn_graph_constructor.hpp:236-245), but for all ~10^7
+// start edges at once.  The first walk measures (length, end k-mer -> `!(s < !s)`); after two scans a second walk over the
+// kept edges re-traces the path and emits the 2-bit packed sequence directly, 32 bases per stored word.  Only the masks,
+// the MPHF and the junction's own k-mer are needed: nothing indexed by "all vertices" is built, which is also what lets
+// several GPUs extract disjoint file ranges of junctions independently (tests/test_multi_gpu.py).  A chain longer than
+// WALK_LIMIT, or vertices no walk reached (perfect loops), send the whole extraction to the pointer-jumping path.
+#pragma once
+
+namespace sb200 {
+
+constexpr uint32_t WALK_LIMIT = 1024;
+
+template<int W>
+__device__ __forceinline__ uint32_t walk_mask(const MphfDev &m, const uint8_t *__restrict__ masks, const uint64_t *y, int k) {
+    bool minimal;
+    uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
+    uint32_t raw = __ldg(masks + idy);
+    return minimal ? raw : mask_conj(raw);
+}
+
+// out-degree of every oriented junction (0 for everything else); t = 2 * (file index - first) + strand
+__global__ void __launch_bounds__(256) junction_degree_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
+                                                             uint32_t *__restrict__ deg) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    uint32_t raw = masks[idx[t >> 1]];
+    uint32_t mk = (t & 1) ? mask_conj(raw) : raw;
+    deg[t] = mask_is_junction(raw) ? (uint32_t) __popc(mk & 15u) : 0u;
+}
+
+// work list: elist[e] = (t << 2) | nucleotide
+__global__ void __launch_bounds__(256) edge_list_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
+                                                       const uint32_t *__restrict__ deg_scan, uint32_t *__restrict__ elist) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    uint32_t raw = masks[idx[t >> 1]];
+    if (!mask_is_junction(raw)) return;
+    uint32_t mk = ((t & 1) ? mask_conj(raw) : raw) & 15u;
+    uint32_t o = deg_scan[t];
+    while (mk) {
+        uint32_t c = (uint32_t) __ffs((int) mk) - 1u;
+        mk &= mk - 1u;
+        elist[o++] = ((uint32_t) t << 2) | c;
+    }
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+                                                          uint32_t n_e, const uint8_t *__restrict__ masks, uint32_t *__restrict__ elen,
+                                                          uint32_t *__restrict__ kflag, unsigned long long *__restrict__ ewords,
+                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases */) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long chain_nodes = 0, kept_bases = 0;
+    uint32_t too_long = 0;
+    if (e < n_e) {
+        uint32_t code = elist[e];
+        uint32_t t = code >> 2, c = code & 3u;
+        uint64_t x[W], y[W], z[W];
+        oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+        kmer_shl<W>(x, k, c, y);
+        uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
+        uint32_t mk = walk_mask<W>(m, masks, y, k);
+        uint32_t nn = 1;
+        while (!mask_is_junction(mk)) {
+            if (nn > WALK_LIMIT) { too_long = 1; break; }
+            prev_first = kmer_base(y, 0);
+            kmer_shl<W>(y, k, nib_next(mk & 15u), z);
+#pragma unroll
+            for (int q = 0; q < W; ++q) y[q] = z[q];
+            mk = walk_mask<W>(m, masks, y, k);
+            ++nn;
+        }
+        uint32_t len = 0;
+        if (!too_long) {
+            chain_nodes = nn - 1;
+            uint64_t rcn[W];
+            kmer_rc<W>(y, k, rcn);
+            int cmp = kmer_lex_cmp<W>(x, rcn);
+            bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
+            if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
+        }
+        elen[e] = len;
+        kflag[e] = len ? 1u : 0u;
+        ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
+    }
+    // one atomic per warp and counter
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        chain_nodes += __shfl_down_sync(0xffffffffu, chain_nodes, d);
+        kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
+        too_long += __shfl_down_sync(0xffffffffu, too_long, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (chain_nodes) atomicAdd(&totals[0], chain_nodes);
+        if (too_long) atomicAdd(&totals[1], (unsigned long long) too_long);
+        if (kept_bases) atomicAdd(&totals[4], kept_bases);
+    }
+}
+
+__global__ void __launch_bounds__(256) kept_list_kernel(const uint32_t *__restrict__ kflag_scan, const uint32_t *__restrict__ elen, uint32_t n_e,
+                                                       uint32_t *__restrict__ klist) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_e && elen[e]) klist[kflag_scan[e]] = e;
+}
+
+// second walk, kept edges only: packed output.  Bases are accumulated 32 to a word in a register and stored once per word.
+template<int W>
+__global__ void __launch_bounds__(256) walk_emit_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+                                                       const uint32_t *__restrict__ klist, uint32_t n_kept, const uint8_t *__restrict__ masks,
+                                                       const uint32_t *__restrict__ elen, const unsigned long long *__restrict__ ewords_scan,
+                                                       uint32_t *__restrict__ seq_len, uint64_t *__restrict__ seq_word_off,
+                                                       uint64_t *__restrict__ out_words) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_kept) return;
+    uint32_t e = klist[q];
+    uint32_t code = elist[e];
+    uint32_t t = code >> 2, c = code & 3u;
+    const uint32_t nn = elen[e];
+    const unsigned long long woff = ewords_scan[e];
+    const uint32_t L = (uint32_t) k + nn;
+    seq_len[q] = L;
+    seq_word_off[q] = woff;
+    uint64_t x[W], y[W], z[W];
+    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+    // the first k bases are the junction's k-mer: whole words of x, then the partial (last) word continues in `acc`
+    uint32_t pos = 0;
+    uint64_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if ((w + 1) * 32 <= k) { out_words[woff + w] = x[w]; pos = (w + 1) * 32; }
+    }
+    if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // padding bits of x are zero
+    auto push = [&](uint32_t base) {
+        acc |= (uint64_t) base << (2 * (pos & 31));
+        ++pos;
+        if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
+    };
+    push(c);
+    kmer_shl<W>(x, k, c, y);
+    for (uint32_t s = 1; s < nn; ++s) {
+        uint32_t mk = walk_mask<W>(m, masks, y, k);
+        uint32_t b = nib_next(mk & 15u);
+        push(b);
+        kmer_shl<W>(y, k, b, z);
+#pragma unroll
+        for (int w = 0; w < W; ++w) y[w] = z[w];
+    }
+    if (pos & 31) out_words[woff + (pos >> 5)] = acc;
+}
+
+__global__ void __launch_bounds__(256) count_nonjunction_kernel(const uint8_t *__restrict__ masks, uint64_t n, unsigned long long *__restrict__ total) {
+    __shared__ uint32_t sm[256 / 32 + 1];
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
+        c += mask_is_junction(masks[i]) ? 0u : 1u;
+    uint32_t block_total;
+    block_exclusive_scan<uint32_t, 256>(c, &block_total, sm);
+    if (threadIdx.x == 0 && block_total) atomicAdd(total, (unsigned long long) block_total);   // one atomic per CTA
+}
+
+// Result of the measuring walk over the junctions of file range [first, last)
+struct WalkStats {
+    unsigned long long chain_vertices = 0, long_chains = 0, words = 0, kept_bases = 0;
+    uint32_t n_edges = 0, n_kept = 0;
+};
+
+// Returns nullptr when the direct walks do not apply (a chain longer than WALK_LIMIT, or — when checking the whole set —
+// perfect loops to collect): the caller then runs the pointer-jumping path.  [first, last) restricts the junctions to a
+// file range of k-mers; `stats_out` reports what was seen either way.
+template<int W>
+static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int check_loops,
+                                     uint64_t first, uint64_t last, WalkStats *stats_out) {
+    uint64_t n = kmers->size;
+    int k = (int) kmers->k;
+    MphfDev m = mphf_dev(mphf);
+    uint64_t n_range = last - first;
+    SB200_REQUIRE(2 * n_range < (1ull << 30), "more than 2^29 k-mers in one extraction range: shard the input");
+    WalkStats st;
+    uint64_t nt = 2 * n_range;
+    DevBuf<uint32_t> deg(ctx, nt + 1);
+    DevBuf<uint32_t> tot32(ctx, 2);
+    DevBuf<unsigned long long> totals(ctx, 6);   // [0] chain vertices seen [1] long chains [2] total words [3] non-junction k-mers [4] bases
+    totals.zero();
+    if (nt) LAUNCH(ctx, junction_degree_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p);
+    exclusive_scan<uint32_t>(ctx, deg.p, nt, tot32.p);
+    CUDA_CHECK(cudaMemcpyAsync(&st.n_edges, tot32.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    uint32_t n_e = st.n_edges;
+    DevBuf<uint32_t> elist(ctx, (uint64_t) n_e + 1), elen(ctx, (uint64_t) n_e + 1), kflag(ctx, (uint64_t) n_e + 1);
+    DevBuf<unsigned long long> ewords(ctx, (uint64_t) n_e + 1);
+    const uint64_t *kbase = kmers->data.p + first * W;
+    if (n_e) {
+        LAUNCH(ctx, edge_list_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p, elist.p);
+        LAUNCH(ctx, walk_measure_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p);
+    }
+    if (check_loops) LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, n, totals.p + 3);
+    exclusive_scan<uint32_t>(ctx, kflag.p, n_e, tot32.p + 1);
+    exclusive_scan<unsigned long long>(ctx, ewords.p, n_e, totals.p + 2);
+    unsigned long long th[6];
+    CUDA_CHECK(cudaMemcpyAsync(th, totals.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&st.n_kept, tot32.p + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    st.chain_vertices = th[0]; st.long_chains = th[1]; st.words = th[2]; st.kept_bases = th[4];
+    if (stats_out) *stats_out = st;
+    if (st.long_chains != 0) return nullptr;                          // some chain is too long for a sequential walk
+    if (check_loops && th[0] != 2 * th[3]) return nullptr;            // vertices no walk reached: perfect loops exist
+    sb200_unitigs *out = new sb200_unitigs();
+    out->ctx = ctx; out->k = (unsigned) k; out->count = st.n_kept; out->n_loops = 0; out->total_words = st.words;
+    out->total_bases = st.kept_bases;
+    out->len.alloc(ctx, (uint64_t) st.n_kept + 1);
+    out->word_off.alloc(ctx, (uint64_t) st.n_kept + 1);
+    out->words.alloc(ctx, st.words + 1);
+    if (st.n_kept) {
+        DevBuf<uint32_t> klist(ctx, st.n_kept);
+        LAUNCH(ctx, kept_list_kernel, div_up(n_e, 256), 256, 0, kflag.p, elen.p, n_e, klist.p);
+        LAUNCH(ctx, walk_emit_kernel<W>, div_up(st.n_kept, 256), 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
+               out->len.p, out->word_off.p, out->words.p);
+    }
+    uint64_t tw = st.words;
+    CUDA_CHECK(cudaMemcpyAsync(out->word_off.p + st.n_kept, &tw, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return out;
+}
+
+}  // namespace sb200

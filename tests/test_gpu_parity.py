@@ -184,3 +184,29 @@ def test_size_independent_properties_at_scale(ctx):
     # reverse complement holds both strands of its edges, hence >=)
     edges = int((ln.astype(np.int64) - k).sum())
     assert kp.total_kmers() <= edges <= int(1.001 * kp.total_kmers())
+
+
+def test_long_chains_and_forced_pointer_jumping(ctx, monkeypatch):
+    """Chains longer than the direct-walk limit (error-free reads: one 6 kbp unitig) take the pointer-jumping path;
+    SB200_FORCE_JUMP=1 sends ordinary inputs through it as well — both must equal the oracle."""
+    k, nb = 31, 10
+    genome = synth.random_genome(6000, 77)
+    codes = synth.sample_pairs(genome, 600, 120, 300, 0.0, 78)
+    reads = synth.codes_to_strings(codes)
+    want = O.gbuilder(reads, k, nb)
+    assert max(len(u) for u in want["unitigs"]) > 2000
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+    monkeypatch.setenv("SB200_FORCE_JUMP", "1")
+    ctx2 = B.Context(0)
+    try:
+        from conftest import load_golden
+        for name in ("ecoli1k_k21", "multiword_k77", "tipclip_k33", "loops_k21"):
+            g = load_golden(name)
+            streams, index, kpomers = build_index(ctx2, g["reads"], g["k"], g["buckets"])
+            if g["tip_bound"] >= 0:
+                assert B.EarlyTipClipperProcessor(index, g["tip_bound"]).ClipTips() == int(g["clipped"])
+            assert B.UnbranchingPathExtractor(index, g["k"]).ExtractUnbranchingPathsAndLoops() == g["unitigs"], name
+            index.free(); kpomers.free(); streams.free()
+    finally:
+        ctx2.close()
