@@ -17,7 +17,8 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
 
-template<int W> struct RsItems { static constexpr int value = (W <= 2) ? 16 : 8; };
+// records per thread; a tile (256 threads x ITEMS records) is staged in <= 32 KB of shared memory
+template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? 8 : 4; };
 
 // digit selector: word >= 0 -> byte `shift/8` of that word; word < 0 -> byte of the bucket id
 struct DigitSel {
@@ -97,9 +98,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__r
     hist[(uint64_t) threadIdx.x * num_tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
-// stable scatter: offsets[bin * num_tiles + tile] = exclusive scan of hist
+// stable scatter, direct version (every thread stores its records straight to their bins; kept for reference — the
+// staged version below replaced it): offsets[bin * num_tiles + tile] = exclusive scan of hist
 template<int W>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_direct_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
                                                                DigitSel sel, const uint32_t *__restrict__ offsets,
                                                                uint32_t num_tiles) {
     constexpr int ITEMS = RsItems<W>::value;
@@ -166,6 +168,89 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
 
 // Sorts recs (n x W words) into (bucket, array_less) order.  `a` holds the input; `b` is scratch of the same size.
 // Returns the buffer (a or b) that holds the result.
+// Stable scatter with shared-memory staging.  A tile's records are ranked per warp with match.any (stable: warp order,
+// then round, then lane), placed into shared memory in digit order, and only then written out: consecutive threads store
+// consecutive records of the same bin, so a bin's run inside the tile leaves as one coalesced burst instead of one
+// 16-byte store per record.  offsets[bin * num_tiles + tile] = exclusive scan of the histogram matrix.
+template<int W>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+                                                               DigitSel sel, const uint32_t *__restrict__ offsets,
+                                                               uint32_t num_tiles) {
+    constexpr int ITEMS = RsItems<W>::value;
+    constexpr int TILE = RS_THREADS * ITEMS;
+    __shared__ __align__(16) uint64_t srec[TILE * W];
+    __shared__ uint8_t sdig[TILE];
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];
+    __shared__ uint32_t delta[RS_BINS];     // global position - staged position, per bin (mod 2^32)
+    __shared__ uint32_t s_scan[RS_THREADS / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint64_t tile_base = (uint64_t) blockIdx.x * TILE;
+    const uint64_t warp_base = tile_base + (uint64_t) warp * (32 * ITEMS);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint64_t rec[ITEMS][W];
+    uint32_t info[ITEMS];   // bits 0-7 digit, bits 8-31 offset among the warp's records with the same digit
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < W; ++j) rec[i][j] = 0;
+        if (idx < n) load_rec<W>(in, idx, rec[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+        bool ok = idx < n;
+        uint32_t d = ok ? rs_digit<W>(rec[i], sel) : 0u;
+        uint32_t valid = __ballot_sync(0xffffffffu, ok);
+        uint32_t peers = __match_any_sync(0xffffffffu, d) & valid;
+        uint32_t old = ok ? cnt[warp][d] : 0;
+        __syncwarp();
+        if (ok && (peers & lt_mask) == 0) cnt[warp][d] = old + __popc(peers);
+        __syncwarp();
+        info[i] = d | ((old + __popc(peers & lt_mask)) << 8);
+    }
+    __syncthreads();
+    {   // one thread per bin: tile-local start of the bin (block scan over the 256 bin totals), per-warp bases, global delta
+        const uint32_t bin = threadIdx.x;
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) tot += cnt[w][bin];
+        uint32_t total_all;
+        uint32_t start = block_exclusive_scan<uint32_t, RS_THREADS>(tot, &total_all, s_scan);
+        delta[bin] = offsets[(uint64_t) bin * num_tiles + blockIdx.x] - start;
+        uint32_t base = start;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = cnt[w][bin];
+            cnt[w][bin] = base;
+            base += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint64_t idx = warp_base + (uint64_t) i * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = info[i] & 0xFFu;
+            const uint32_t pos = cnt[warp][d] + (info[i] >> 8);
+#pragma unroll
+            for (int j = 0; j < W; ++j) srec[(size_t) pos * W + j] = rec[i][j];
+            sdig[pos] = (uint8_t) d;
+        }
+    }
+    __syncthreads();
+    const uint32_t count = (uint32_t) ((n - tile_base) < (uint64_t) TILE ? (n - tile_base) : (uint64_t) TILE);
+    for (uint32_t q = threadIdx.x; q < count; q += RS_THREADS) {
+        uint64_t r[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] = srec[(size_t) q * W + j];
+        store_rec<W>(out, (uint64_t) (uint32_t) (q + delta[sdig[q]]), r);
+    }
+}
+
 inline void append_bucket_passes(std::vector<DigitSel> &passes, uint32_t num_buckets, bool marker) {
     if (num_buckets > 1) {
         int bbits = 0;

@@ -300,25 +300,35 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     const uint32_t my_total = cr.dirty ? cr.side_cnt : total_u;
 
     // ---- decoupled look-back for this CTA's global offset ------------------------------------------------------------------
-    if (threadIdx.x == 0) {
+    // One warp inspects 32 predecessors per step (a single thread walking them one L2 round trip at a time was 45 % of
+    // this kernel's stall samples): sum the aggregates down to the nearest CTA that already knows its inclusive prefix.
+    if (warp == 0) {
         unsigned long long excl = 0;
-        if (b == 0) {
-            atomicExch(&status[0], lb_pack(2, my_total));
-        } else {
-            atomicExch(&status[b], lb_pack(1, my_total));
-            long long p = (long long) b - 1;
+        if (b > 0) {
+            if (lane == 0) atomicExch(&status[b], lb_pack(1, my_total));
+            long long pos = (long long) b - 1;
             while (true) {
-                unsigned long long sv = atomicAdd(&status[p], 0ULL);
-                unsigned long long flag = sv >> 62;
-                if (flag == 0) continue;
-                excl += sv & ((1ULL << 62) - 1);
-                if (flag == 2) break;
-                --p;
+                const long long p = pos - lane;
+                unsigned long long sv = lb_pack(2, 0);   // before the first CTA: inclusive prefix 0
+                if (p >= 0) sv = *reinterpret_cast<volatile unsigned long long *>(status + p);
+                const unsigned long long flag = sv >> 62;
+                const uint32_t empty = __ballot_sync(0xffffffffu, flag == 0);
+                const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
+                const uint32_t need = incl ? (0xFFFFFFFFu >> (31 - (__ffs((int) incl) - 1))) : 0xFFFFFFFFu;   // lanes up to the first inclusive
+                if (empty & need) continue;   // a predecessor we depend on has not published yet: read again
+                unsigned long long v = ((need >> lane) & 1u) ? (sv & ((1ULL << 62) - 1)) : 0ULL;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (incl) break;
+                pos -= 32;
             }
-            atomicExch(&status[b], lb_pack(2, excl + my_total));
         }
-        s_base = excl;
-        if (b == n_chunks - 1) *total_out = excl + my_total;
+        if (lane == 0) {
+            atomicExch(&status[b], lb_pack(2, excl + my_total));
+            s_base = excl;
+            if (b == n_chunks - 1) *total_out = excl + my_total;
+        }
     }
     __syncthreads();
     const unsigned long long base = s_base;
