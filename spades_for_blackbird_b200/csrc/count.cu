@@ -310,18 +310,30 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
                (uint32_t *) nullptr, total_dev.p, n_chunks, pk.shift);
     }
-    unsigned long long u64 = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&u64, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // per-tile unique counts -> offsets; the total sizes the result
+    uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(status.p);
+    DevBuf<uint32_t> total32(ctx, 1);
+    exclusive_scan<uint32_t>(ctx, tile_cnt, n_chunks, total32.p);
+    uint32_t u32 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&u32, total32.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    uint64_t u = u64;
+    uint64_t u = u32;
     ctx->trace_point("  chunk kernel");
 
     sb200_kmers *s = new sb200_kmers();
     s->ctx = ctx; s->k = (unsigned) K; s->words = W; s->num_buckets = B; s->instances = n;
+    s->data.alloc(ctx, u * W);   // right-sized: the instance-sized ping-pong buffers go back to the allocator
+    if (want_counts) {
+        s->counts.alloc(ctx, u);
+        LAUNCH(ctx, (seg_compact_kernel<W, true>), n_chunks, 256, 0, other, cnt_full.p, ranges.p, tile_cnt, n_chunks, u32, s->data.p, s->counts.p);
+    } else {
+        LAUNCH(ctx, (seg_compact_kernel<W, false>), n_chunks, 256, 0, other, (const uint32_t *) nullptr, ranges.p, tile_cnt, n_chunks, u32, s->data.p,
+               (uint32_t *) nullptr);
+    }
     if (drop_marker) {
         uint32_t flag = 0;
         DevBuf<uint32_t> fl(ctx, 1);
-        LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, other, u, fl.p);
+        LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, s->data.p, u, fl.p);
         CUDA_CHECK(cudaMemcpyAsync(&flag, fl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (flag) --u;
@@ -331,14 +343,8 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         }
     }
     s->size = u;
-    s->data.alloc(ctx, u * W);   // right-sized copy; the instance-sized ping-pong buffers go back to the pool
-    CUDA_CHECK(cudaMemcpyAsync(s->data.p, other, u * W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (want_counts) {
-        s->counts.alloc(ctx, u);
-        CUDA_CHECK(cudaMemcpyAsync(s->counts.p, cnt_full.p, u * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (double_palindromes && (K % 2 == 0))
-            LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
-    }
+    if (want_counts && double_palindromes && (K % 2 == 0))
+        LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
     finish_tables<W>(ctx, s, B);
     inst.release();
     ctx->trace_point("  shrink + tables");

@@ -152,7 +152,26 @@ __device__ __forceinline__ uint32_t seg_tag(uint64_t w0, int shift) {
     return shift >= 32 ? (uint32_t) (w0 >> (shift - 32)) : (uint32_t) (w0 << (32 - shift));
 }
 
+// Moves the unique records every tile packed at the front of its own range to their final, contiguous place.
+// One CTA per tile; tile_off = exclusive scan of the per-tile unique counts.
 template<int W, bool COUNTS>
+__global__ void __launch_bounds__(256) seg_compact_kernel(const uint64_t *__restrict__ tmp, const uint32_t *__restrict__ tmp_cnt,
+                                                         const ChunkRange *__restrict__ ranges, const uint32_t *__restrict__ tile_off,
+                                                         uint32_t n_chunks, uint32_t total, uint64_t *__restrict__ out,
+                                                         uint32_t *__restrict__ out_cnt) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t o = tile_off[b];
+    const uint32_t cnt = (b + 1 < n_chunks ? tile_off[b + 1] : total) - o;
+    const uint64_t src = ranges[b].s;
+    for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+        uint64_t r[W];
+        load_rec<W>(tmp, src + i, r);
+        store_rec<W>(out, (uint64_t) o + i, r);
+        if (COUNTS) out_cnt[o + i] = tmp_cnt[src + i];
+    }
+}
+
+template<int W, bool COUNTS, bool USE_LOOKBACK = false>
 __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uint64_t *__restrict__ recs, uint64_t n,
                                                                       const uint32_t *__restrict__ hb, const ChunkRange *__restrict__ ranges,
                                                                       const uint64_t *__restrict__ side_recs, const uint32_t *__restrict__ side_cnts,
@@ -174,9 +193,16 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_scan[THREADS / 32 + 1];
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const uint32_t b = s_tile;
+    // USE_LOOKBACK: CTAs take tiles in launch order and chain their unique counts with a decoupled look-back (single pass,
+    // final positions written directly).  Otherwise (default) every CTA packs its unique records at the front of its own
+    // input range and records how many; seg_compact_kernel moves them to their final place after a scan of the counts —
+    // that copy replaces the right-sizing copy the host did anyway and costs less than the look-back wait (30 % of the
+    // stall samples of the single-pass version: fifteen warps idle while one chases predecessors through L2).
+    if (USE_LOOKBACK) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+    }
+    const uint32_t b = USE_LOOKBACK ? s_tile : blockIdx.x;
     if (b >= n_chunks) return;
     const ChunkRange cr = ranges[b];
     const uint32_t s = cr.s, cnt = cr.dirty ? 0u : cr.e - cr.s;
@@ -302,7 +328,12 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     // ---- decoupled look-back for this CTA's global offset ------------------------------------------------------------------
     // One warp inspects 32 predecessors per step (a single thread walking them one L2 round trip at a time was 45 % of
     // this kernel's stall samples): sum the aggregates down to the nearest CTA that already knows its inclusive prefix.
-    if (warp == 0) {
+    if (!USE_LOOKBACK) {
+        if (threadIdx.x == 0) {
+            reinterpret_cast<uint32_t *>(status)[b] = my_total;   // per-tile unique count (status doubles as the count array)
+            s_base = cr.s;                                        // front of my own input range
+        }
+    } else if (warp == 0) {
         unsigned long long excl = 0;
         if (b > 0) {
             if (lane == 0) atomicExch(&status[b], lb_pack(1, my_total));
