@@ -117,6 +117,36 @@ int  sb200_unitigs_download(const sb200_unitigs *u, uint64_t *words_out, uint64_
                             uint32_t *len_out);
 void sb200_unitigs_free(sb200_unitigs *u);
 
+/* ---- hash-sharded path (several GPUs, one process each): the same stages with the shuffle points exposed.
+ *      GPU g of G owns the buckets [g*B/G, (g+1)*B/G) of KMerSegmentPolicy — a contiguous range of the reference's file
+ *      order — so the shards concatenated in rank order are the single-GPU (= reference) result.  The reference has no
+ *      counterpart (it shuffles through kmers_raw<i> files, kmer_splitter.hpp:140-161); the caller moves the byte ranges
+ *      between GPUs (NCCL all-to-all / all-reduce; spades_for_blackbird_b200/host/distributed.py).
+ *        records_extract | records_derive  -> records_partition (grouped by owner, counts per owner)
+ *        [exchange] -> records_alloc + copy -> count_records            : this GPU's shard of KMerDiskStorage
+ *        mphf_build_sharded + [sum bits/ranks over GPUs]                  : the whole KMerIndex on every GPU
+ *        ext_build(local (k+1)-mers, local k-mers, whole index) + [sum masks over GPUs]
+ *        unitigs_extract_local                                            : sequences whose start junction is in the shard */
+typedef struct sb200_records sb200_records;   /* unsorted k-mer instances on their way through the shuffle */
+int  sb200_records_extract(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, sb200_records **out);
+int  sb200_records_derive(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_records **out);
+int  sb200_records_partition(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, unsigned n_owners, uint64_t *counts_out /* n_owners */);
+int  sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int double_palindromes, int marker, sb200_records **out);
+uint64_t sb200_records_size(const sb200_records *r);
+unsigned sb200_records_words(const sb200_records *r);
+unsigned sb200_records_k(const sb200_records *r);
+int  sb200_records_flags(const sb200_records *r);        /* bit 0: double_palindromes, bit 1: marker */
+uint64_t *sb200_records_device(sb200_records *r);        /* device pointer to n * words uint64 */
+void sb200_records_free(sb200_records *r);
+int  sb200_count_records(sb200_ctx *ctx, sb200_records *r /* consumed */, unsigned num_buckets, int want_counts, sb200_kmers **out);
+int  sb200_mphf_build_sharded(sb200_ctx *ctx, const sb200_kmers *local_kmers, const uint64_t *global_bucket_sizes /* B */, sb200_mphf **out);
+int  sb200_mphf_arrays(const sb200_mphf *m, uint64_t **bits, uint64_t *n_words, uint64_t **ranks, uint64_t *n_ranks);   /* device */
+int  sb200_ext_masks_device(const sb200_ext *e, uint8_t **masks, uint64_t *size_padded);                                /* device */
+int  sb200_unitigs_extract_local(sb200_ctx *ctx, const sb200_kmers *local_kmers, const sb200_mphf *mphf, const sb200_ext *ext,
+                                 uint64_t *stats /* 6: chain vertices, long chains, edges, kept, bases, non-junction k-mers */,
+                                 sb200_unitigs **out /* NULL if a chain exceeded the walk limit */);
+int  sb200_unitigs_device(const sb200_unitigs *u, uint64_t **words, uint64_t **word_off, uint32_t **len);               /* device */
+
 /* ---- whole path, host buffers in / host buffers out: what spades-gbuilder does between read conversion and output
  *      (projects/gbuilder/main.cpp:165-181) and spades-core's Construction stage (stages/construction.cpp:469-483).
  *      Result buffers are pinned host memory owned by the graph handle. ---------------------------------------------- */

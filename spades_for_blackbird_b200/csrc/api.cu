@@ -11,7 +11,7 @@
 namespace sb200 {
 sb200_kmers *count_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B);
 sb200_kmers *derive_kmers(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B);
-sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks);
+sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
 void mphf_lookup_device(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *recs_dev, uint64_t n, uint64_t *out_dev);
 uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out);
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf);
@@ -247,7 +247,7 @@ void sb200_kmers_free(sb200_kmers *s) {
 // ---- MPHF -----------------------------------------------------------------------------------------------------------------
 int sb200_mphf_build(sb200_ctx *ctx, const sb200_kmers *kmers, sb200_mphf **out) {
     *out = nullptr;
-    return guarded(ctx, [&] { *out = sb200::mphf_build(ctx, kmers); });
+    return guarded(ctx, [&] { *out = sb200::mphf_build(ctx, kmers, nullptr); });
 }
 uint64_t sb200_mphf_size(const sb200_mphf *m) { return m->total; }
 uint64_t sb200_mphf_mem_size(const sb200_mphf *m) {
@@ -292,7 +292,7 @@ int sb200_ext_masks_download(const sb200_ext *e, uint8_t *masks_out) {
 }
 int sb200_ext_idx_download(const sb200_ext *e, uint32_t *idx_out) {
     return guarded(e->ctx, [&] {
-        CUDA_CHECK(cudaMemcpyAsync(idx_out, e->idx.p, e->size * 4, cudaMemcpyDeviceToHost, e->ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(idx_out, e->idx.p, e->n_local * 4, cudaMemcpyDeviceToHost, e->ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(e->ctx->stream));
     });
 }

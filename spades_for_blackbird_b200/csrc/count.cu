@@ -459,4 +459,123 @@ sb200_kmers *derive_kmers(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B) {
     return derive_w<4, 4>(ctx, kp, B);
 }
 
+// ---- sharded counting: the same two steps with the hash shuffle exposed ---------------------------------------------------
+// Several GPUs share one k-mer space by giving GPU g the buckets [g*B/G, (g+1)*B/G) of the reference's own bucket
+// function: (1) every GPU turns its reads (or its (k+1)-mers) into records and groups them by owner — one stable counting
+// pass whose digit is the owner id; (2) the host exchanges the groups (NCCL all-to-all over NVLink, host/distributed.py);
+// (3) every GPU sorts/deduplicates/counts what it received.  All copies of a k-mer meet at its owner, so multiplicities,
+// per-bucket order and bucket boundaries are those of the single-GPU run, shard by shard.
+template<int W>
+static sb200_records *extract_records_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc) {
+    int mode = canonical_only ? (add_rc ? MODE_CANON_RC : MODE_CANON_FWD) : (add_rc ? MODE_ALL_RC : MODE_ALL_FWD);
+    uint32_t mult = (mode == MODE_ALL_RC) ? 2 : 1;
+    DevBuf<uint64_t> off(ctx, rd->n_reads + 1);
+    DevBuf<uint64_t> total_dev(ctx, 1);
+    LAUNCH(ctx, window_count_kernel, div_up(rd->n_reads ? rd->n_reads : 1, 256), 256, 0, rd->len.p, rd->n_reads, (uint32_t) K, mult, off.p);
+    exclusive_scan<uint64_t>(ctx, off.p, rd->n_reads, total_dev.p);
+    uint64_t n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    sb200_records *r = new sb200_records();
+    r->ctx = ctx; r->k = (unsigned) K; r->words = W; r->n = n;
+    r->double_palindromes = mode == MODE_CANON_RC; r->marker = mode == MODE_CANON_FWD;
+    r->data.alloc(ctx, n * W);
+    if (n) {
+        unsigned grid = (unsigned) std::min<uint64_t>((rd->n_reads + 7) / 8, (uint64_t) ctx->num_sms * 32);
+        LAUNCH(ctx, extract_reads_kernel<W>, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, off.p, r->data.p);
+    }
+    return r;
+}
+
+sb200_records *extract_records(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc) {
+    SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
+    switch ((K + 31) / 32) {
+        case 1: return extract_records_w<1>(ctx, rd, (int) K, canonical_only, add_rc);
+        case 2: return extract_records_w<2>(ctx, rd, (int) K, canonical_only, add_rc);
+        case 3: return extract_records_w<3>(ctx, rd, (int) K, canonical_only, add_rc);
+        default: return extract_records_w<4>(ctx, rd, (int) K, canonical_only, add_rc);
+    }
+}
+
+template<int WS, int W>
+static sb200_records *derive_records_w(sb200_ctx *ctx, const sb200_kmers *kp) {
+    sb200_records *r = new sb200_records();
+    r->ctx = ctx; r->k = kp->k - 1; r->words = W; r->n = kp->size * 2;
+    r->data.alloc(ctx, r->n * W);
+    auto derive_kernel_ = derive_kernel<WS, W>;
+    if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, r->data.p);
+    return r;
+}
+
+sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp) {
+    SB200_REQUIRE(kp->k >= 2, "source k-mers too short");
+    int WS = (int) kp->words, W = (int) ((kp->k - 1 + 31) / 32);
+    if (WS == 1) return derive_records_w<1, 1>(ctx, kp);
+    if (WS == 2 && W == 1) return derive_records_w<2, 1>(ctx, kp);
+    if (WS == 2) return derive_records_w<2, 2>(ctx, kp);
+    if (WS == 3 && W == 2) return derive_records_w<3, 2>(ctx, kp);
+    if (WS == 3) return derive_records_w<3, 3>(ctx, kp);
+    if (WS == 4 && W == 3) return derive_records_w<4, 3>(ctx, kp);
+    return derive_records_w<4, 4>(ctx, kp);
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t *__restrict__ recs, uint64_t n, DigitSel sel, unsigned long long *__restrict__ counts) {
+    __shared__ uint32_t sh[RS_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        uint64_t r[W];
+        load_rec<W>(recs, i, r);
+        atomicAdd(&sh[rs_digit<W>(r, sel)], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long) sh[threadIdx.x]);
+}
+
+template<int W>
+static void partition_records_w(sb200_ctx *ctx, sb200_records *r, uint32_t B, uint32_t n_parts, uint64_t *counts_out) {
+    DigitSel sel{-2, (int) n_parts, B, r->marker ? 1 : 0};
+    DevBuf<unsigned long long> counts(ctx, RS_BINS);
+    counts.zero();
+    if (r->n) {
+        LAUNCH(ctx, owner_count_kernel<W>, (unsigned) std::min<uint64_t>(div_up(r->n, 256), (uint64_t) ctx->num_sms * 16), 256, 0, r->data.p, r->n, sel,
+               counts.p);
+        DevBuf<uint64_t> scratch(ctx, r->n * W);
+        std::vector<DigitSel> passes{sel};
+        uint64_t *res = radix_sort_passes<W>(ctx, r->data.p, scratch.p, r->n, passes);
+        if (res == scratch.p) std::swap(r->data, scratch);   // keep the buffer that holds the grouped records
+    }
+    std::vector<unsigned long long> h(RS_BINS);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), counts.p, RS_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t p = 0; p < n_parts; ++p) counts_out[p] = h[p];
+}
+
+void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out) {
+    SB200_REQUIRE(n_parts >= 1 && n_parts <= 256, "number of owners out of range [1,256]");
+    SB200_REQUIRE(B >= 1 && B <= 65536 && B % n_parts == 0, "num_buckets must be a multiple of the number of owners");
+    switch (r->words) {
+        case 1: partition_records_w<1>(ctx, r, B, n_parts, counts_out); break;
+        case 2: partition_records_w<2>(ctx, r, B, n_parts, counts_out); break;
+        case 3: partition_records_w<3>(ctx, r, B, n_parts, counts_out); break;
+        default: partition_records_w<4>(ctx, r, B, n_parts, counts_out); break;
+    }
+}
+
+sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts) {
+    SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
+    SB200_REQUIRE(r->n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    sb200_kmers *s;
+    switch (r->words) {
+        case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
+        case 2: s = finish_set<2>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
+        case 3: s = finish_set<3>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
+        default: s = finish_set<4>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
+    }
+    if (!want_counts) s->instances = 0;
+    r->n = 0;
+    return s;
+}
+
 }  // namespace sb200

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const ui
     load_rec<W>(kmers, i, r);
     uint32_t id = (uint32_t) mphf_lookup<W>(m, r);
     idx[i] = id;
-    inv[id] = (uint32_t) i;
+    if (inv) inv[id] = (uint32_t) i;
 }
 
 // Besides the two mask bits, every (k+1)-mer x = y -> z also records the link itself: succ[y] = z and, for the other
@@ -65,13 +65,17 @@ __global__ void __launch_bounds__(256) fill_masks_kernel(MphfDev m, const uint64
 template<int WS, int W>
 static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf) {
     sb200_ext *e = new sb200_ext();
-    e->ctx = ctx; e->k = kmers->k; e->size = kmers->size;
-    uint64_t padded = (kmers->size + 3) & ~3ULL;
+    // The mask array covers the whole index (mphf->total entries); `kmers` may be one GPU's shard of the k-mer table, in which
+    // case idx[] covers only the shard, the masks hold only the bits of this GPU's (k+1)-mers (summed over the GPUs by the
+    // caller: distinct (k+1)-mers set distinct bits) and the inverse permutation is not built.
+    const bool sharded = kmers->size != mphf->total;
+    e->ctx = ctx; e->k = kmers->k; e->size = mphf->total; e->n_local = kmers->size;
+    uint64_t padded = (e->size + 3) & ~3ULL;
     e->masks.alloc(ctx, padded + 4);
     e->masks.zero();
     e->idx.alloc(ctx, kmers->size);
-    e->inv.alloc(ctx, kmers->size);
-    SB200_REQUIRE(2 * kmers->size < 0xFFFFFFF0ull, "more than 2^31 k-mers on one GPU: shard the input");
+    if (!sharded) e->inv.alloc(ctx, kmers->size);
+    SB200_REQUIRE(2 * e->size < 0xFFFFFFF0ull, "more than 2^31 k-mers in one index");
     e->succ_valid = false;   // the direct-walk extraction needs no links; the pointer-jumping path computes them on demand
     MphfDev m = mphf_dev(mphf);
     LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p);
@@ -83,7 +87,7 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
 
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf) {
     SB200_REQUIRE(kpomers->k == kmers->k + 1, "kpomers.k() must equal index.k() + 1");
-    SB200_REQUIRE(mphf->total == kmers->size && mphf->words == kmers->words, "MPHF was not built over this k-mer set");
+    SB200_REQUIRE(mphf->total >= kmers->size && mphf->words == kmers->words, "MPHF was not built over this k-mer set");
     int WS = (int) kpomers->words, W = (int) kmers->words;
     if (WS == 1) return build_ext_w<1, 1>(ctx, kpomers, kmers, mphf);
     if (WS == 2 && W == 1) return build_ext_w<2, 1>(ctx, kpomers, kmers, mphf);

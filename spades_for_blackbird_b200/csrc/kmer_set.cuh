@@ -23,6 +23,15 @@ struct sb200_kmers {
     std::vector<uint64_t> bucket_starts_host;
 };
 
+struct sb200_records {   // unsorted k-mer instances / candidates on their way through the hash shuffle
+    sb200_ctx *ctx = nullptr;
+    unsigned k = 0, words = 0;
+    uint64_t n = 0;
+    bool double_palindromes = false;   // canonical fwd+RC counting mode: a self-reverse-complement record counts twice
+    bool marker = false;               // canonical forward-only mode: all-ones records are "filtered out" markers
+    DevBuf<uint64_t> data;
+};
+
 struct sb200_mphf {
     sb200_ctx *ctx = nullptr;
     unsigned num_buckets = 0, words = 0;
@@ -44,7 +53,8 @@ struct sb200_mphf {
 struct sb200_ext {   // DeBruijnExtensionIndex payload: masks in MPHF-index order (+ successor links for the walks)
     sb200_ctx *ctx = nullptr;
     unsigned k = 0;
-    uint64_t size = 0;
+    uint64_t size = 0;          // entries of the mask array = keys of the whole index
+    uint64_t n_local = 0;       // k-mers of the table this GPU holds (== size unless the table is sharded)
     DevBuf<uint8_t> masks;      // size bytes (padded to a multiple of 4), PerfectHashMap::data_
     DevBuf<uint32_t> idx;       // MPHF index of every k-mer in file order
     DevBuf<uint32_t> inv;       // file position of every MPHF index

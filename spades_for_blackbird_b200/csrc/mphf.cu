@@ -129,12 +129,18 @@ __global__ void mphf_bucket_ends_kernel(const uint32_t *__restrict__ pc_scan, co
 }
 
 template<int W>
-static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks) {
+static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) {
+    // global_sizes != nullptr: `ks` is one GPU's shard (whole buckets); level geometry, rank offsets and segment starts are laid
+    // out for ALL buckets, only the shard's keys are inserted.  Bit-vectors and rank samples of different shards are then
+    // disjoint, so summing the arrays over the GPUs (all-reduce) yields exactly the single-GPU index.
     sb200_mphf *m = new sb200_mphf();
     m->ctx = ctx;
     uint32_t B = ks->num_buckets;
-    m->num_buckets = B; m->words = W; m->total = ks->size;
-    SB200_REQUIRE(ks->size < (1ull << 32), "more than 2^32-1 k-mers on one GPU: shard the input");
+    uint64_t total_keys = 0;
+    for (uint32_t b = 0; b < B; ++b)
+        total_keys += global_sizes ? global_sizes[b] : ks->bucket_starts_host[b + 1] - ks->bucket_starts_host[b];
+    m->num_buckets = B; m->words = W; m->total = total_keys;
+    SB200_REQUIRE(total_keys < (1ull << 32), "more than 2^32-1 k-mers in one index");
     size_t NL = (size_t) B * MPHF_LEVELS;
     m->domain_host.assign(NL, 0); m->word_off_host.assign(NL, 0); m->rank_off_host.assign(NL, 0);
     std::vector<uint64_t> nchar(NL, 0);
@@ -143,7 +149,7 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks) {
     m->bucket_sizes_host.assign(B, 0);
     uint64_t words = 0, ranks = 0;
     for (uint32_t b = 0; b < B; ++b) {
-        uint64_t n = ks->bucket_starts_host[b + 1] - ks->bucket_starts_host[b];
+        uint64_t n = global_sizes ? global_sizes[b] : ks->bucket_starts_host[b + 1] - ks->bucket_starts_host[b];
         m->segment_starts_host[b + 1] = n;
         m->bucket_sizes_host[b] = n;
         if (n > 0) {
@@ -223,12 +229,12 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks) {
     return m;
 }
 
-sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks) {
+sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) {
     switch (ks->words) {
-        case 1: return mphf_build_w<1>(ctx, ks);
-        case 2: return mphf_build_w<2>(ctx, ks);
-        case 3: return mphf_build_w<3>(ctx, ks);
-        default: return mphf_build_w<4>(ctx, ks);
+        case 1: return mphf_build_w<1>(ctx, ks, global_sizes);
+        case 2: return mphf_build_w<2>(ctx, ks, global_sizes);
+        case 3: return mphf_build_w<3>(ctx, ks, global_sizes);
+        default: return mphf_build_w<4>(ctx, ks, global_sizes);
     }
 }
 

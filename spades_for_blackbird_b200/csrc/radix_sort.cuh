@@ -38,6 +38,7 @@ __device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &
         for (int j = 0; j < W; ++j) m &= (r[j] == ~0ULL);
         if (m) b = d.num_buckets - 1;
     }
+    if (d.word == -2) return (uint32_t) (((uint64_t) b * (uint32_t) d.shift) / d.num_buckets);   // owner of the bucket; shift = #owners
     return (b >> d.shift) & 0xFFu;
 }
 

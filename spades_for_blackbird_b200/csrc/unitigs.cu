@@ -685,8 +685,33 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     return out;
 }
 
+// One GPU's share of a sharded extraction: the junctions among the k-mers of its own table shard, walked against the
+// all-reduced masks and MPHF.  stats: [0] chain vertices seen, [1] chains longer than the walk limit, [2] start edges,
+// [3] kept sequences, [4] kept bases, [5] non-junction k-mers of the WHOLE index (for the perfect-loop check
+// sum_g stats_g[0] == 2 * stats[5]).  Returns nullptr (with stats filled) when a chain was too long.
+sb200_unitigs *extract_unitigs_local(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, uint64_t *stats) {
+    SB200_REQUIRE(ext->n_local == kmers->size && ext->k == kmers->k && ext->size == mphf->total, "extension index does not belong to this shard");
+    WalkStats st;
+    sb200_unitigs *u = nullptr;
+    switch (kmers->words) {
+        case 1: u = unitigs_walk_w<1>(ctx, kmers, mphf, ext, 0, 0, kmers->size, &st); break;
+        case 2: u = unitigs_walk_w<2>(ctx, kmers, mphf, ext, 0, 0, kmers->size, &st); break;
+        case 3: u = unitigs_walk_w<3>(ctx, kmers, mphf, ext, 0, 0, kmers->size, &st); break;
+        default: u = unitigs_walk_w<4>(ctx, kmers, mphf, ext, 0, 0, kmers->size, &st); break;
+    }
+    DevBuf<unsigned long long> nj(ctx, 1);
+    nj.zero();
+    LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, ext->size, nj.p);
+    unsigned long long h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, nj.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    stats[0] = st.chain_vertices; stats[1] = st.long_chains; stats[2] = st.n_edges; stats[3] = st.n_kept; stats[4] = st.kept_bases; stats[5] = h;
+    return u;
+}
+
 sb200_unitigs *extract_unitigs(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int with_loops) {
-    SB200_REQUIRE(ext->size == kmers->size && ext->k == kmers->k, "extension index does not belong to this k-mer set");
+    SB200_REQUIRE(ext->size == kmers->size && ext->n_local == kmers->size && ext->k == kmers->k,
+                  "extension index does not belong to this k-mer set (sharded tables go through sb200_unitigs_extract_local)");
     switch (kmers->words) {
         case 1: return unitigs_w<1>(ctx, kmers, mphf, ext, with_loops);
         case 2: return unitigs_w<2>(ctx, kmers, mphf, ext, with_loops);

@@ -91,6 +91,22 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_unitigs_total_words": (C.c_uint64, [vp]),
     "sb200_unitigs_download": (C.c_int, [vp, u64p, u64p, u32p]),
     "sb200_unitigs_free": (None, [vp]),
+    "sb200_records_extract": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]),
+    "sb200_records_derive": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "sb200_records_partition": (C.c_int, [vp, vp, C.c_uint, C.c_uint, u64p]),
+    "sb200_records_alloc": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]),
+    "sb200_records_size": (C.c_uint64, [vp]),
+    "sb200_records_words": (C.c_uint, [vp]),
+    "sb200_records_k": (C.c_uint, [vp]),
+    "sb200_records_flags": (C.c_int, [vp]),
+    "sb200_records_device": (vp, [vp]),
+    "sb200_records_free": (None, [vp]),
+    "sb200_count_records": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.POINTER(vp)]),
+    "sb200_mphf_build_sharded": (C.c_int, [vp, vp, u64p, C.POINTER(vp)]),
+    "sb200_mphf_arrays": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(vp), u64p]),
+    "sb200_ext_masks_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
+    "sb200_unitigs_extract_local": (C.c_int, [vp, vp, vp, vp, u64p, C.POINTER(vp)]),
+    "sb200_unitigs_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "sb200_construct": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, C.POINTER(ConstructParams), C.POINTER(vp)]),
     "sb200_graph_get": (C.c_int, [vp, C.POINTER(GraphView)]),
     "sb200_graph_free": (None, [vp]),
