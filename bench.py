@@ -175,10 +175,116 @@ def reference_arm(a):
     return 0
 
 
+def main_sharded(a, world, rank, local_rank):
+    """N > 1: one rank per GPU, k-mer space sharded by hash bucket (host/distributed.py).  Weak scaling: the genome grows
+    with N (4.6 Mbp x N) at fixed coverage, so every rank brings the same 460 Mbp of reads as the N = 1 workload."""
+    import torch
+    import torch.distributed as dist
+    from spades_for_blackbird_b200.host import binding as B
+    from spades_for_blackbird_b200.host import distributed as D
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    if a.buckets % world:
+        raise SystemExit("--buckets must be a multiple of the number of GPUs")
+    # this rank's slice of the read set: pairs sampled from the shared genome with rank-specific seeds
+    g = synth.random_genome(a.genome_len * world, 42)
+    n_pairs = int(a.genome_len * a.coverage / (2 * a.read_len))
+    chunks = []
+    for s in range(0, n_pairs, 200_000):
+        c = synth.sample_pairs(g, min(200_000, n_pairs - s), a.read_len, 350 if a.read_len <= 150 else 500, 0.005,
+                               1042 + s + 7_000_003 * rank)
+        chunks.append(synth.pack_codes(c)[0])
+    words = np.concatenate(chunks)
+    n = 2 * n_pairs
+    wpr = (a.read_len + 31) // 32
+    word_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(wpr)
+    lens = np.full(n, a.read_len, dtype=np.uint32)
+    pw = torch.from_numpy(words.view(np.int64)).pin_memory()
+    hw = pw.numpy().view(np.uint64)
+    total_bases = int(lens.astype(np.int64).sum()) * world
+
+    ctx = B.Context(local_rank)
+    comm = D.TorchComm()
+    backend = D.GpuShardBackend(ctx, dev)
+    streams = B.ReadStreams(ctx, hw, word_off, lens)
+    info = {}
+
+    def step(e2e):
+        rs = B.ReadStreams(ctx, hw, word_off, lens) if e2e else streams      # e2e: H2D of the reads inside the timed region
+        res = D.construct_sharded(backend, comm, rs, a.k, a.buckets, gather_to=0)
+        info.update(kpomers=res.kpomers.total_kmers(), instances=res.kpomers.instances, kmers=res.kmers.total_kmers(),
+                    unitigs=int(res.stats[:, 3].sum()), unitig_bases=int(res.stats[:, 4].sum()))
+        d2h = 0
+        if e2e:   # every rank brings its shard of the tables home; rank 0 also the masks and the gathered unitigs
+            kp, kc, km = res.kpomers.final_kmers(), res.kpomers.counts(), res.kmers.final_kmers()
+            d2h = kp.nbytes + kc.nbytes + km.nbytes
+            if rank == 0:
+                m = backend.ext_masks(res.ext).cpu()
+                gw = [t.cpu() for t in res.gathered[0]]
+                d2h += m.numel() + sum(t.numel() * 8 for t in gw)
+        res.kpomers.free(); res.kmers.free(); res.index.free()
+        backend.free_ext(res.ext); backend.free_unitigs(res.unitigs)
+        if e2e:
+            rs.free()
+        return d2h
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e):
+        for _ in range(a.warmup):
+            step(e2e)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d2h = 0
+        for _ in range(a.steps):
+            d2h = step(e2e)
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        ms = max(ms, (time.perf_counter() - t0) * 1e3 - 1.0) if ms == 0.0 else ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / a.steps, d2h
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.kernel_launches(reset=True)
+    ms_per_step, _ = timed(False)
+    launches = ctx.kernel_launches()
+    clocks = sampler.stop()
+    ms_e2e, d2h = (None, 0) if a.no_e2e else timed(True)
+    if rank == 0:
+        cfg = workload_config(a, world)
+        cfg["workload"] += "; N>1: genome %.1f Mbp x %d, every rank brings 460 Mbp of reads, k-mer space sharded by hash bucket" % (
+            a.genome_len / 1e6, world)
+        line = {"metric": METRIC, "value": total_bases / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": None if ms_e2e is None else {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+                                                    "h2d_bytes_per_step": int(words.nbytes + word_off.nbytes + lens.nbytes),
+                                                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                                                    "returns": "per rank: its shard of (k+1)-mers + counts and k-mers; rank 0: masks + all unitigs"},
+                "roofline": None, "cpu_baseline": None,
+                "counts": {k_: int(v_) for k_, v_ in info.items()},
+                "exchange": "2 x NCCL all-to-all (k-mer instances, k-mer candidates), all-reduce of MPHF bit-vectors and masks, gather of unitigs"}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         return reference_arm(a)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_sharded(a, int(os.environ["WORLD_SIZE"]), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")))
 
     import torch
     import torch.distributed as dist

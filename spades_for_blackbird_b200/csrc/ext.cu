@@ -82,6 +82,7 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
     LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,
            e->succ.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // blocking like every entry point: callers all-reduce the masks next
     return e;
 }
 

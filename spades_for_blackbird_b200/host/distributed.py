@@ -290,8 +290,9 @@ def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=Fa
     long_chains = int(allstats[:, 1].sum())
     loops = int(allstats[:, 0].sum()) != 2 * int(allstats[0, 5])
     if long_chains or loops:
-        raise B.Sb200Error("the sharded extraction met %s: run this input through the single-GPU path (pointer jumping)" % (
-            "chains longer than the direct-walk limit" if long_chains else "perfect loops"))
+        raise B.Sb200Error("the sharded extraction met %s: run this input through the single-GPU path (pointer jumping) "
+                           "[per-rank stats (chain vertices, long chains, edges, kept, bases, non-junction k-mers): %s]" % (
+                               "chains longer than the direct-walk limit" if long_chains else "perfect loops", allstats.tolist()))
     res.unitigs = u
     if gather_to is not None:
         w, o, ln = backend.unitigs_views(u)
