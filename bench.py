@@ -31,6 +31,13 @@ sys.path.insert(0, ROOT)
 from spades_for_blackbird_b200.host import synth  # noqa: E402
 
 METRIC = "reads_to_condensed_dbg_throughput"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) from the committed ncu --set full capture of this same command
+# (profiles/); keys are the names of sb200_profile_report().
+NCU_TRAFFIC = {}
+try:
+    NCU_TRAFFIC = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+except Exception:
+    pass
 UNIT = "Gbp/s"
 
 
@@ -365,33 +372,55 @@ def main():
     value = world * total_bases / (ms_per_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
+    # achieved = ALGORITHMIC bytes of one step's launches of that kernel / their measured device time.  Algorithmic bytes follow
+    # SURVEY.md section 8(d)'s single-pass model: every launch reads its input once and writes its output once (DESIGN.md lists
+    # the per-kernel formulas).  W1/W0 = bytes of a (k+1)-mer / k-mer record.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    peak_src = "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     n_kp, n_inst, n_km, n_unitigs, unitig_bases = stats
-    top = report[0] if report else ("none", 1, 0.0)
     kernel_ms = {name: (n, t) for name, n, t in report}
+    W1, W0 = 8 * ((a.k + 1 + 31) // 32), 8 * ((a.k + 31) // 32)
+    n_words_out = (unitig_bases + 31 * n_unitigs) / 32.0 * 8     # packed unitig bytes (upper bound on padding)
+    alg = {   # algorithmic bytes per STEP of every launch of the kernel
+        "extract_reads_kernel<W>": total_bases / 4 + n_inst * W1,
+        "seg_chunk_kernel_": n_inst * W1 + n_kp * (W1 + 4) + 2 * n_kp * W0 + n_km * W0,     # S2 + S4: instances in, unique (+count) out
+        "seg_heads_kernel<W>": n_inst * (W1 + 0.125) + 2 * n_kp * (W0 + 0.125),
+        "derive_kernel_": n_kp * W1 + 2 * n_kp * W0,
+        "fill_masks_kernel_": n_kp * W1 + n_km,
+        "index_of_kmers_kernel<W>": n_km * (W0 + 8),
+        "walk_measure_kernel<W>": n_km * (W0 + 1),
+        "walk_emit_kernel<W>": n_km * 1 + n_words_out,
+        "mphf_level0_kernel<W>": n_km * W0 + n_km * 5.8 / 8,
+    }
+    for name in ("rs_scatter_kernel<W>", "rs_hist_kernel<W>"):
+        if name in kernel_ms:
+            per_sort = kernel_ms[name][0] / a.steps / 2.0        # launches per sort
+            mult = 2 if "scatter" in name else 1                   # a counting pass reads and writes every record once
+            alg[name] = per_sort * mult * (n_inst * W1 + 2 * n_kp * W0)
     roof = None
-    if "rs_scatter_kernel<W>" in kernel_ms:
-        n_l, t_l = kernel_ms["rs_scatter_kernel<W>"]
-        # Each launch of a pass moves every record once: read W*8 bytes + write W*8 bytes.  Passes run over the
-        # (k+1)-mer instances (I1 records of W1 words) and over the k-mer candidates (2*U1 records of W0 words).
-        W1, W0 = (a.k + 1 + 31) // 32, (a.k + 31) // 32
-        bbits = max(1, int(np.ceil(np.log2(a.buckets)))) if a.buckets > 1 else 0
-        passes1 = (2 * (a.k + 1) + 7) // 8 if W1 == 1 else sum(((64 if j < W1 - 1 else 2 * (a.k + 1) - 64 * (W1 - 1)) + 7) // 8 for j in range(W1))
-        passes0 = sum(((64 if j < W0 - 1 else 2 * a.k - 64 * (W0 - 1)) + 7) // 8 for j in range(W0))
-        passes1 += (bbits + 7) // 8
-        passes0 += (bbits + 7) // 8
-        bytes_total = a.steps * (passes1 * n_inst * W1 * 16 + passes0 * 2 * n_kp * W0 * 16)
-        achieved = bytes_total / (t_l * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "rs_scatter_kernel (stable LSD radix scatter pass)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "launches": n_l, "mean_launch_ms": t_l / n_l, "share_of_step": t_l / ms,
-                "algorithmic_bytes_per_launch": bytes_total / n_l}
+    top = next(((name, n, t) for name, n, t in report if name in alg), None)
+    if top:
+        name, n_l, t_l = top
+        bytes_step = float(alg[name])
+        achieved = bytes_step * a.steps / (t_l * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC.get(name), "peak_source": peak_src, "launches_per_step": n_l / a.steps,
+                "mean_launch_ms": t_l / n_l, "share_of_step": t_l / ms,
+                "algorithmic_bytes_per_launch": bytes_step * a.steps / n_l,
+                "note": "top kernel by measured device time; traffic = dram read+write bytes per launch from profiles/ (ncu --set full), null if not captured"}
+    # whole path against the single-pass model of SURVEY.md 8(d): sum of the stage formulas S1..S7
+    path_bytes = (total_bases / 4 + n_inst * W1) + (n_inst * W1 + n_kp * (W1 + 4)) + (n_kp * W1 + 2 * n_kp * (W0 + 1)) + \
+                 (2 * n_kp * (W0 + 1) + n_km * (W0 + 1)) + (n_km * W0 + n_km * 5.8 / 8) + (n_km * (W0 + 1) + n_km) + \
+                 (n_km * (W0 + 1) + (n_kp + a.k * n_unitigs) / 4)
+    path_roof = {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+    kernels_roof = [{"kernel": name, "ms_per_step": t / a.steps, "achieved_gbs": alg[name] * a.steps / (t * 1e-3) / 1e9,
+                     "frac": alg[name] * a.steps / (t * 1e-3) / 1e9 / peak} for name, n, t in report if name in alg]
     breakdown = [{"kernel": name, "launches": n // a.steps if a.steps else n, "ms_per_step": t / a.steps} for name, n, t in report[:12]]
     if a.breakdown and rank == 0:
         for name, n, t in report:
@@ -440,7 +469,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic", "config": workload_config(a, world), "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "roofline_path": path_roof, "roofline_kernels": kernels_roof,
                 "kmers_counted_per_s": world * n_inst / (stage_s["count_kpomers"] / a.steps),
                 "stage_ms": {k_: 1e3 * v_ / a.steps for k_, v_ in stage_s.items()},
                 "counts": {"kpomer_instances": int(n_inst), "kpomers": int(n_kp), "kmers": int(n_km), "unitigs": int(n_unitigs),

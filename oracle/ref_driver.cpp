@@ -14,6 +14,7 @@
 //     UnbranchingPathExtractor(ext,k).ExtractUnbranchingPathsAndLoops(nchunks)
 //         C/assembly_graph/construction/debruijn_graph_constructor.hpp:377-384
 //     [CoverageHashMapBuilder().BuildIndex(cov, kpomers, streams)]  C/utils/ph_map/coverage_hash_map_builder.hpp:39-54
+//   tobinary   C/io/reads/binary_converter.cpp:50-113 (BinaryWriter::ToBinary) -> lib.seq / lib.off
 //   kmercount  A/projects/kmercount/main.cpp:186-228: every k-window of read and RC(read), no canonical
 //     filter, CountAll(16, T, merge=true).  The tool's own splitter class lives inside main.cpp, so the
 //     driver uses the reference's DeBruijnReadKMerSplitter with the always-true filter
@@ -45,6 +46,7 @@
 #include "io/reads/rc_reader_wrapper.hpp"
 #include "io/reads/longest_valid_wrapper.hpp"
 #include "io/reads/converting_reader_wrapper.hpp"
+#include "io/reads/binary_converter.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
 
@@ -144,7 +146,7 @@ int main(int argc, char **argv) {
         else { std::cerr << "unknown arg " << s << "\n"; return 2; }
     }
     if (a.mode.empty() || a.reads.empty() || a.out.empty()) {
-        std::cerr << "usage: ref_driver --mode gbuilder|kmercount --reads R.txt --out DIR -k K -t T "
+        std::cerr << "usage: ref_driver --mode gbuilder|kmercount|tobinary --reads R.txt --out DIR -k K -t T "
                      "[--buckets B] [--nchunks N] [--tip-bound L] [--coverage] [--quiet] [--no-dump]\n";
         return 2;
     }
@@ -169,7 +171,12 @@ int main(int argc, char **argv) {
     timing << "load " << now() - t0 << "\n" << "reads " << reads.size() << "\nbases " << bases << "\n";
     auto workdir = fs::tmp::make_temp_dir(a.out, "ref");
 
-    if (a.mode == "kmercount") {
+    if (a.mode == "tobinary") {
+        // io::BinaryWriter::ToBinary (C/io/reads/binary_converter.cpp:50-113) on the LongestValid-trimmed reads:
+        // <out>/lib.seq + <out>/lib.off, the files io::BinaryFileStream reads back (binary_streams.hpp:48-97)
+        io::ReadStream<io::SingleRead> rs = io::VectorReadStream<io::SingleRead>(reads);
+        io::BinaryWriter(a.out + "/lib").ToBinary(rs);
+    } else if (a.mode == "kmercount") {
         unsigned B = a.buckets ? a.buckets : 16;   // kmercount/main.cpp:215
         using Splitter = utils::DeBruijnReadKMerSplitter<io::SingleReadSeq,
                                                          utils::StoringTypeFilter<utils::SimpleStoring>>;

@@ -149,9 +149,39 @@ def cases():
     return c
 
 
+def binary_reads_fixture():
+    """binreads/: the reference's own .seq/.off files (io::BinaryWriter::ToBinary, binary_converter.cpp:50-113) for 257 reads
+    of mixed lengths with Ns — pins the on-disk read format the C++ adapters parse and emit (tests/test_cpp_adapters.py)."""
+    rng = np.random.default_rng(77)
+    reads = []
+    for i in range(257):
+        n = int(rng.integers(0, 200))
+        s = "".join("ACGT"[c] for c in rng.integers(0, 4, n))
+        if i % 5 == 0 and n > 10:
+            p = int(rng.integers(0, n))
+            s = s[:p] + "N" * int(rng.integers(1, 4)) + s[p:]
+        reads.append(s if s else "N")
+    d = os.path.join(HERE, "binreads")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "reads.txt"), "w") as f:
+        f.write("\n".join(reads) + "\n")
+    tmp = tempfile.mkdtemp(prefix="sb200_golden_")
+    try:
+        subprocess.check_call([DRIVER, "--mode", "tobinary", "--reads", os.path.join(d, "reads.txt"), "--out", tmp, "-k", "5", "-t", "1",
+                               "--quiet"], stdout=subprocess.DEVNULL)
+        for ext in ("seq", "off"):
+            shutil.copy(os.path.join(tmp, "lib." + ext), os.path.join(d, "lib." + ext))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    print("binreads: %d reads, lib.seq %d bytes" % (len(reads), os.path.getsize(os.path.join(d, "lib.seq"))))
+
+
 def main():
     if not os.path.exists(DRIVER):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    binary_reads_fixture()
+    if "--binreads-only" in sys.argv:
+        return
     for name, (reads, k, B, tip) in cases().items():
         res = run_ref(reads, k, B, tip_bound=tip)
         res.update(run_ref(reads, k, 16, mode="kmercount"))
