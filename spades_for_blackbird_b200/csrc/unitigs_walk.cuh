@@ -109,6 +109,131 @@ __global__ void __launch_bounds__(256) kept_list_kernel(const uint32_t *__restri
     if (e < n_e && elen[e]) klist[kflag_scan[e]] = e;
 }
 
+// ---- link table: the walks as pointer chasing ----------------------------------------------------------------------------
+// With the whole k-mer table on this GPU every chain vertex (in = out = 1) gets one 32-bit word, indexed by its oriented
+// FILE position t = 2 * file index + strand:
+//     bits 0-27  oriented file position of its successor      bits 28-29  nucleotide appended by the step
+//     bits 30-31 first base of the vertex itself (the reverse path's tie-breaker)        junctions hold LINK_JUNCTION.
+// Building it costs one MPHF lookup per chain vertex in a fully parallel, coalesced kernel; the walks then cost one 4-byte
+// read per step instead of a canonicalisation, two XXH3 hashes, the level probes and a rank per step (ncu, profiles/r1a:
+// the lookup walks executed 13.5 G warp instructions and pulled 25 GB through DRAM for 210 M steps).
+constexpr uint32_t LINK_JUNCTION = 0xFFFFFFFFu;
+constexpr uint32_t LINK_POS_MASK = 0x0FFFFFFFu;
+
+template<int W>
+__global__ void __launch_bounds__(256) links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k, const uint32_t *__restrict__ idx,
+                                                   const uint32_t *__restrict__ inv, const uint8_t *__restrict__ masks, uint32_t *__restrict__ link) {
+    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const uint32_t raw = __ldg(masks + __ldg(idx + (t >> 1)));
+    uint32_t out = LINK_JUNCTION;
+    if (!mask_is_junction(raw)) {
+        const int strand = (int) (t & 1);
+        const uint32_t c = nib_next((strand ? mask_conj(raw) : raw) & 15u);
+        uint64_t x[W], y[W];
+        oriented_kmer<W>(kmers, t >> 1, strand, k, x);
+        kmer_shl<W>(x, k, c, y);
+        bool minimal;
+        const uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
+        out = (2u * __ldg(inv + idy) + (minimal ? 0u : 1u)) | (c << 28) | (kmer_base(x, 0) << 30);
+    }
+    link[t] = out;
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+                                                                uint32_t n_e, const uint32_t *__restrict__ inv, const uint32_t *__restrict__ link,
+                                                                uint32_t *__restrict__ elen, uint32_t *__restrict__ efirst, uint32_t *__restrict__ kflag,
+                                                                unsigned long long *__restrict__ ewords, unsigned long long *__restrict__ totals) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long chain_nodes = 0, kept_bases = 0;
+    uint32_t too_long = 0;
+    if (e < n_e) {
+        uint32_t code = elist[e];
+        uint32_t t = code >> 2, c = code & 3u;
+        uint64_t x[W], y[W];
+        oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+        kmer_shl<W>(x, k, c, y);
+        bool minimal;
+        const uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
+        uint32_t v = 2u * __ldg(inv + idy) + (minimal ? 0u : 1u);
+        efirst[e] = v;
+        uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
+        uint32_t nn = 1;
+        uint32_t L = __ldg(link + v);
+        while (L != LINK_JUNCTION) {
+            if (nn > WALK_LIMIT) { too_long = 1; break; }
+            prev_first = L >> 30;
+            v = L & LINK_POS_MASK;
+            L = __ldg(link + v);
+            ++nn;
+        }
+        uint32_t len = 0;
+        if (!too_long) {
+            chain_nodes = nn - 1;
+            uint64_t rcn[W];
+            oriented_kmer<W>(kmers, v >> 1, (v & 1) ? 0 : 1, k, rcn);   // rc of the end vertex
+            int cmp = kmer_lex_cmp<W>(x, rcn);
+            bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
+            if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
+        }
+        elen[e] = len;
+        kflag[e] = len ? 1u : 0u;
+        ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        chain_nodes += __shfl_down_sync(0xffffffffu, chain_nodes, d);
+        kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
+        too_long += __shfl_down_sync(0xffffffffu, too_long, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (chain_nodes) atomicAdd(&totals[0], chain_nodes);
+        if (too_long) atomicAdd(&totals[1], (unsigned long long) too_long);
+        if (kept_bases) atomicAdd(&totals[4], kept_bases);
+    }
+}
+
+template<int W>
+__global__ void __launch_bounds__(256) walk_emit_links_kernel(const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+                                                             const uint32_t *__restrict__ klist, uint32_t n_kept, const uint32_t *__restrict__ link,
+                                                             const uint32_t *__restrict__ elen, const uint32_t *__restrict__ efirst,
+                                                             const unsigned long long *__restrict__ ewords_scan, uint32_t *__restrict__ seq_len,
+                                                             uint64_t *__restrict__ seq_word_off, uint64_t *__restrict__ out_words) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_kept) return;
+    uint32_t e = klist[q];
+    uint32_t code = elist[e];
+    uint32_t t = code >> 2, c = code & 3u;
+    const uint32_t nn = elen[e];
+    const unsigned long long woff = ewords_scan[e];
+    const uint32_t L = (uint32_t) k + nn;
+    seq_len[q] = L;
+    seq_word_off[q] = woff;
+    uint64_t x[W];
+    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+    uint32_t pos = 0;
+    uint64_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if ((w + 1) * 32 <= k) { out_words[woff + w] = x[w]; pos = (w + 1) * 32; }
+    }
+    if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // padding bits of x are zero
+    auto push = [&](uint32_t base) {
+        acc |= (uint64_t) base << (2 * (pos & 31));
+        ++pos;
+        if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
+    };
+    push(c);
+    uint32_t v = efirst[e];
+    for (uint32_t s = 1; s < nn; ++s) {
+        const uint32_t lw = __ldg(link + v);
+        push((lw >> 28) & 3u);
+        v = lw & LINK_POS_MASK;
+    }
+    if (pos & 31) out_words[woff + (pos >> 5)] = acc;
+}
+
 // second walk, kept edges only: packed output.  Bases are accumulated 32 to a word in a register and stored once per word.
 template<int W>
 __global__ void __launch_bounds__(256) walk_emit_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
@@ -195,9 +320,21 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     DevBuf<uint32_t> elist(ctx, (uint64_t) n_e + 1), elen(ctx, (uint64_t) n_e + 1), kflag(ctx, (uint64_t) n_e + 1);
     DevBuf<unsigned long long> ewords(ctx, (uint64_t) n_e + 1);
     const uint64_t *kbase = kmers->data.p + first * W;
+    // pointer-chasing walks need the whole k-mer table and the inverse permutation on this GPU; a shard (or a table too
+    // large for 28-bit positions) walks by MPHF lookups instead
+    const bool use_links = !ctx->no_links && first == 0 && last == n && ext->n_local == ext->size && ext->inv.p != nullptr && 2 * n <= LINK_POS_MASK;
+    DevBuf<uint32_t> link, efirst;
     if (n_e) {
         LAUNCH(ctx, edge_list_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p, elist.p);
-        LAUNCH(ctx, walk_measure_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p);
+        if (use_links) {
+            link.alloc(ctx, 2 * n);
+            efirst.alloc(ctx, (uint64_t) n_e + 1);
+            LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, link.p);
+            LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
+                   kflag.p, ewords.p, totals.p);
+        } else {
+            LAUNCH(ctx, walk_measure_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p);
+        }
     }
     if (check_loops) LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, n, totals.p + 3);
     exclusive_scan<uint32_t>(ctx, kflag.p, n_e, tot32.p + 1);
@@ -219,8 +356,12 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     if (st.n_kept) {
         DevBuf<uint32_t> klist(ctx, st.n_kept);
         LAUNCH(ctx, kept_list_kernel, div_up(n_e, 256), 256, 0, kflag.p, elen.p, n_e, klist.p);
-        LAUNCH(ctx, walk_emit_kernel<W>, div_up(st.n_kept, 256), 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
-               out->len.p, out->word_off.p, out->words.p);
+        if (use_links)
+            LAUNCH(ctx, walk_emit_links_kernel<W>, div_up(st.n_kept, 256), 256, 0, kbase, k, elist.p, klist.p, st.n_kept, link.p, elen.p, efirst.p,
+                   ewords.p, out->len.p, out->word_off.p, out->words.p);
+        else
+            LAUNCH(ctx, walk_emit_kernel<W>, div_up(st.n_kept, 256), 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
+                   out->len.p, out->word_off.p, out->words.p);
     }
     uint64_t tw = st.words;
     CUDA_CHECK(cudaMemcpyAsync(out->word_off.p + st.n_kept, &tw, 8, cudaMemcpyHostToDevice, ctx->stream));

@@ -210,3 +210,21 @@ def test_long_chains_and_forced_pointer_jumping(ctx, monkeypatch):
             index.free(); kpomers.free(); streams.free()
     finally:
         ctx2.close()
+
+
+def test_direct_walks_by_lookup(monkeypatch):
+    """SB200_NO_LINKS=1: the direct walks resolve every step by MPHF lookup (what a table shard does) instead of following
+    the link table — same unitigs, same order."""
+    monkeypatch.setenv("SB200_NO_LINKS", "1")
+    ctx2 = B.Context(0)
+    try:
+        from conftest import load_golden
+        for name in ("ecoli1k_k55", "multiword_k127", "tipclip_k21", "ctest_SplitThread2"):
+            g = load_golden(name)
+            streams, index, kpomers = build_index(ctx2, g["reads"], g["k"], g["buckets"])
+            if g["tip_bound"] >= 0:
+                assert B.EarlyTipClipperProcessor(index, g["tip_bound"]).ClipTips() == int(g["clipped"])
+            assert B.UnbranchingPathExtractor(index, g["k"]).ExtractUnbranchingPathsAndLoops() == g["unitigs"], name
+            index.free(); kpomers.free(); streams.free()
+    finally:
+        ctx2.close()
