@@ -142,7 +142,8 @@ template<int W>
 constexpr size_t seg_chunk_smem() {
     return (size_t) SegCfg<W>::CAP * W * 8      // keys of the warp-tile survivors
            + (size_t) SegCfg<W>::CAP * 4         // their 32-bit tags
-           + (size_t) SegCfg<W>::CAP * 2         // "first of its value" flag by sorted position, then its exclusive scan
+           + (size_t) SegCfg<W>::CAP * 2         // owner[s]: 1 + survivor index whose value is first at sorted position s (0 = none)
+           + (size_t) SegCfg<W>::CAP * 2         // rcnt[p]: total multiplicity of survivor p's value (<= MAXSEG)
            + (size_t) SegCfg<W>::CAP             // bit 7: survivor starts a segment; bits 0-5: copies merged in its tile (<= 32)
            + (size_t) (SegCfg<W>::CAP / 32 + 1) * 4;   // survivors per warp tile, then its exclusive scan
 }
@@ -185,8 +186,9 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *pkey = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *ptag = reinterpret_cast<uint32_t *>(pkey + (size_t) CAP * W);
-    uint16_t *sflag = reinterpret_cast<uint16_t *>(ptag + CAP);
-    uint8_t *pinfo = reinterpret_cast<uint8_t *>(sflag + CAP);
+    uint16_t *owner = reinterpret_cast<uint16_t *>(ptag + CAP);
+    uint16_t *rcnt = owner + CAP;
+    uint8_t *pinfo = reinterpret_cast<uint8_t *>(rcnt + CAP);
     uint32_t *tileoff = reinterpret_cast<uint32_t *>(pinfo + CAP);
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_np;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     uint32_t rep_bits = 0, head_bits = 0;   // bit t: my record of tile t is a tile survivor / starts a segment
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
-        const uint32_t p = (warp * TPW + t) * 32 + lane;
+        const uint32_t p = ((uint32_t) t * (THREADS / 32) + warp) * 32 + lane;   // tiles round-robin over the warps: a typical range fills only half of CAP
 #pragma unroll
         for (int j = 0; j < W; ++j) rec[t][j] = 0;
         if (p < cnt) {
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     }
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
-        const uint32_t tile = warp * TPW + t;
+        const uint32_t tile = (uint32_t) t * (THREADS / 32) + warp;
         const uint32_t p = tile * 32 + lane;
         const bool ok = p < cnt;
         uint32_t peers = 0xFFFFFFFFu;
@@ -241,21 +243,19 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
         if (lane == 0) tileoff[tile] = (uint32_t) __popc(m);
     }
     __syncthreads();
-    if (warp == 0) {   // exclusive scan of NT (<= 256) tile counts by one warp
-        uint32_t carry = 0;
-        for (int base = 0; base < NT; base += 32) {
-            uint32_t v = tileoff[base + lane];
-            uint32_t inc = warp_inclusive_scan(v);
-            tileoff[base + lane] = carry + inc - v;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) s_np = carry;
+    {   // exclusive scan of the NT (<= 256) tile counts by the whole block
+        static_assert(NT <= THREADS, "one thread per warp tile");
+        const uint32_t c = threadIdx.x < NT ? tileoff[threadIdx.x] : 0u;
+        uint32_t total_np;
+        const uint32_t ex = block_exclusive_scan<uint32_t, THREADS>(c, &total_np, s_scan);
+        if (threadIdx.x < NT) tileoff[threadIdx.x] = ex;
+        if (threadIdx.x == 0) s_np = total_np;
     }
     __syncthreads();
     const uint32_t np = s_np;
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
-        const uint32_t tile = warp * TPW + t;
+        const uint32_t tile = (uint32_t) t * (THREADS / 32) + warp;
         const bool is_rep = (rep_bits >> t) & 1u;
         const uint32_t m = __ballot_sync(0xffffffffu, is_rep);
         if (is_rep) {
@@ -266,63 +266,91 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
             pinfo[o] = (uint8_t) ((((head_bits >> t) & 1u) << 7) | (mult[t] - 1u));   // copies-1 fits 5 bits
         }
     }
-    for (uint32_t i = threadIdx.x; i < np; i += THREADS) sflag[i] = 0;
+    for (uint32_t i = threadIdx.x; i < np; i += THREADS) owner[i] = 0;
     __syncthreads();
 
     // ---- level 2: rank the survivors inside their segment ------------------------------------------------------------------
-    uint32_t rep_pos[PER];   // sorted position if I am the first survivor of my value, else ~0
-    uint32_t rep_cnt[PER];   // total multiplicity of the value
-#pragma unroll
-    for (uint32_t i = 0; i < PER; ++i) {
-        rep_pos[i] = 0xFFFFFFFFu;
-        rep_cnt[i] = 0;
-        const uint32_t p = threadIdx.x + i * THREADS;
-        if (p >= np) continue;
-        uint32_t sb = p;
-        while (!(pinfo[sb] & 0x80u)) --sb;             // entry 0 is a head by construction
-        const uint32_t mytag = ptag[p];
-        uint32_t less = 0, eq_before = 0, total = (uint32_t) (pinfo[p] & 0x3Fu) + 1u;
-        for (uint32_t q = sb; q < np; ++q) {
-            if (q != sb && (pinfo[q] & 0x80u)) break;  // next segment
-            if (q == p) continue;
-            const uint32_t t = ptag[q];
-            if (t < mytag) { ++less; continue; }
-            if (t > mytag) continue;
-            // equal tags: decide on the full key (duplicates of my value from other tiles, or a true 48-bit-prefix tie)
-            uint64_t me[W], o[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) { me[j] = pkey[(size_t) p * W + j]; o[j] = pkey[(size_t) q * W + j]; }
-            if (kmer_eq<W>(o, me)) {
-                eq_before += (q < p) ? 1u : 0u;
-                total += (uint32_t) (pinfo[q] & 0x3Fu) + 1u;
-            } else if (rec_less<W>(o, me)) {
-                ++less;
+    // One warp per run of whole segments, one lane per survivor: every lane walks the segment once and all lanes read the
+    // same tag per step (a shared-memory broadcast), so the trip count is uniform across the warp.  (The first version gave
+    // each THREAD a survivor and let it scan its own segment: lanes of a warp sat in segments of different lengths and 29 %
+    // of the kernel's stall samples were the barrier after the loop, profiles/r1b_seg_chunk_source.md.)
+    {
+        constexpr uint32_t NW = THREADS / 32;
+        auto next_head = [&](uint32_t from) -> uint32_t {   // warp-uniform: first survivor >= from that starts a segment, else np
+            for (uint32_t bb = from; bb < np; bb += 32) {
+                const uint32_t q = bb + lane;
+                const uint32_t hm = __ballot_sync(0xffffffffu, q < np && (pinfo[q] & 0x80u));
+                if (hm) return bb + (uint32_t) __ffs((int) hm) - 1u;
             }
-        }
-        if (eq_before == 0) {
-            rep_pos[i] = sb + less;
-            rep_cnt[i] = total;
-            sflag[sb + less] = 1;
+            return np;
+        };
+        // survivors [np*w/NW, np*(w+1)/NW) snapped forward to segment heads: the ranges tile [0, np) exactly
+        uint32_t sb = next_head((uint32_t) ((uint64_t) np * warp / NW));
+        const uint32_t send = (warp == (int) NW - 1) ? np : next_head((uint32_t) ((uint64_t) np * (warp + 1) / NW));
+        while (sb < send) {
+            const uint32_t se = next_head(sb + 1);
+            for (uint32_t cb = sb; cb < se; cb += 32) {
+                const uint32_t p = cb + lane;
+                const bool act = p < se;
+                const uint32_t mytag = act ? ptag[p] : 0u;
+                uint64_t me[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) me[j] = act ? pkey[(size_t) p * W + j] : 0ULL;
+                uint32_t less = 0, eq_before = 0, total = act ? (uint32_t) (pinfo[p] & 0x3Fu) + 1u : 0u;
+                // Branch-free over blocks of 32 candidates: count the tags below mine and collect the positions whose tag
+                // equals mine (all lanes read the same tag: a broadcast; the loads of a block are independent).  Only those
+                // positions — copies of my value that survived in other tiles, or a true 48-bit-prefix tie — need the full key.
+                for (uint32_t qb = sb; qb < se; qb += 32) {
+                    const uint32_t nq = se - qb < 32u ? se - qb : 32u;
+                    uint32_t eqm = 0;
+                    uint32_t j = 0;
+                    for (; j + 4 <= nq; j += 4) {
+                        const uint32_t t0 = ptag[qb + j], t1 = ptag[qb + j + 1], t2 = ptag[qb + j + 2], t3 = ptag[qb + j + 3];
+                        less += (uint32_t) (t0 < mytag) + (uint32_t) (t1 < mytag) + (uint32_t) (t2 < mytag) + (uint32_t) (t3 < mytag);
+                        eqm |= ((uint32_t) (t0 == mytag) | ((uint32_t) (t1 == mytag) << 1) | ((uint32_t) (t2 == mytag) << 2) |
+                                ((uint32_t) (t3 == mytag) << 3)) << j;
+                    }
+                    for (; j < nq; ++j) {
+                        const uint32_t t = ptag[qb + j];
+                        less += (uint32_t) (t < mytag);
+                        eqm |= (uint32_t) (t == mytag) << j;
+                    }
+                    if (!act) eqm = 0;
+                    else if (p - qb < 32u) eqm &= ~(1u << (p - qb));   // myself
+                    while (eqm) {
+                        const uint32_t q = qb + (uint32_t) __ffs((int) eqm) - 1u;
+                        eqm &= eqm - 1u;
+                        uint64_t o[W];
+#pragma unroll
+                        for (int jj = 0; jj < W; ++jj) o[jj] = pkey[(size_t) q * W + jj];
+                        if (kmer_eq<W>(o, me)) {
+                            eq_before += (q < p) ? 1u : 0u;
+                            total += (uint32_t) (pinfo[q] & 0x3Fu) + 1u;
+                        } else if (rec_less<W>(o, me)) {
+                            ++less;
+                        }
+                    }
+                }
+                if (act && eq_before == 0) {
+                    owner[sb + less] = (uint16_t) (p + 1u);
+                    rcnt[p] = (uint16_t) total;
+                }
+            }
+            sb = se;
         }
     }
     __syncthreads();
-    // exclusive scan of the flags in sorted order, in place
-    uint32_t v[PER];
+    // compact the occupied sorted positions (blocked: thread t owns positions [t*PER, (t+1)*PER))
+    uint32_t own[PER];
     uint32_t local_sum = 0;
 #pragma unroll
     for (uint32_t i = 0; i < PER; ++i) {
-        const uint32_t p = threadIdx.x * PER + i;
-        v[i] = (p < np) ? sflag[p] : 0u;
-        local_sum += v[i];
+        const uint32_t sp = threadIdx.x * PER + i;
+        own[i] = (sp < np) ? owner[sp] : 0u;
+        local_sum += own[i] ? 1u : 0u;
     }
     uint32_t total_u;
     uint32_t pre = block_exclusive_scan<uint32_t, THREADS>(local_sum, &total_u, s_scan);
-#pragma unroll
-    for (uint32_t i = 0; i < PER; ++i) {
-        const uint32_t p = threadIdx.x * PER + i;
-        if (p < np) sflag[p] = (uint16_t) pre;
-        pre += v[i];
-    }
     const uint32_t my_total = cr.dirty ? cr.side_cnt : total_u;
 
     // ---- decoupled look-back for this CTA's global offset ------------------------------------------------------------------
@@ -375,14 +403,15 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) seg_chunk_kernel(const uin
     }
 #pragma unroll
     for (uint32_t i = 0; i < PER; ++i) {
-        if (rep_pos[i] == 0xFFFFFFFFu) continue;
-        const uint32_t p = threadIdx.x + i * THREADS;
+        if (!own[i]) continue;
+        const uint32_t p = own[i] - 1u;
         uint64_t r[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) r[j] = pkey[(size_t) p * W + j];
-        const unsigned long long dst = base + sflag[rep_pos[i]];
+        const unsigned long long dst = base + pre;
         store_rec<W>(out, dst, r);
-        if (COUNTS) out_cnt[dst] = rep_cnt[i];
+        if (COUNTS) out_cnt[dst] = rcnt[p];
+        ++pre;
     }
 }
 
