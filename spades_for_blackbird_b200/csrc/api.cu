@@ -67,6 +67,8 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaHostAlloc((void **) &ctx->mailbox_host, sb200_ctx::MAILBOX_BYTES, cudaHostAllocMapped));
+        CUDA_CHECK(cudaHostGetDevicePointer((void **) &ctx->mailbox_dev, ctx->mailbox_host, 0));
         cudaMemPool_t pool;
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t threshold = UINT64_MAX;
@@ -87,6 +89,7 @@ void sb200_destroy(sb200_ctx *ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     ctx->dev_trim();
     ctx->pinned_free_all();
+    if (ctx->mailbox_host) { cudaFreeHost(ctx->mailbox_host); ctx->mailbox_host = nullptr; ctx->mailbox_dev = nullptr; }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     ctx->event_pool.clear();
     // Handles created from this context may outlive it (garbage-collected wrappers): their device blocks are still
@@ -333,85 +336,6 @@ void sb200_unitigs_free(sb200_unitigs *u) {
 }
 
 // ---- whole path: see construct.cu ------------------------------------------------------------------------------------------
-#if 0
-int sb200_construct_v0(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
-                    const sb200_construct_params *p, sb200_graph **out) {
-    *out = nullptr;
-    sb200_reads *reads = nullptr;
-    sb200_kmers *kp = nullptr, *km = nullptr;
-    sb200_mphf *mp = nullptr;
-    sb200_ext *ext = nullptr;
-    sb200_unitigs *un = nullptr;
-    sb200_graph *g = nullptr;
-    int rc = guarded(ctx, [&] {
-        SB200_REQUIRE(p && (p->k & 1) && p->k >= 1 && p->k < 128, "k must be odd and in [1,128)");
-        cudaStream_t s = ctx->stream;
-        g = new sb200_graph();
-        g->ctx = ctx;
-        memset(&g->view, 0, sizeof g->view);
-        sb200_graph_view &v = g->view;
-        int e;
-        if ((e = sb200_reads_upload(ctx, words, word_off, len, n_reads, &reads))) throw sb200_error(e, ctx->last_error);
-        v.h2d_bytes = reads->n_words * 8 + (n_reads + 1) * 8 + n_reads * 4;
-        if ((e = sb200_count(ctx, reads, p->k + 1, 1, 1, p->num_buckets, &kp))) throw sb200_error(e, ctx->last_error);
-        sb200_reads_free(reads); reads = nullptr;
-        v.n_kpomers = kp->size; v.kpomer_instances = kp->instances;
-        if (p->fetch_kmers) {
-            uint64_t *h = g->pin<uint64_t>(kp->size * kp->words);
-            uint32_t *c = g->pin<uint32_t>(kp->size);
-            CUDA_CHECK(cudaMemcpyAsync(h, kp->data.p, kp->size * kp->words * 8, cudaMemcpyDeviceToHost, s));
-            CUDA_CHECK(cudaMemcpyAsync(c, kp->counts.p, kp->size * 4, cudaMemcpyDeviceToHost, s));
-            v.kpomers = h; v.kpomer_counts = c;
-            g->kp_starts = kp->bucket_starts_host; v.kpomer_bucket_starts = g->kp_starts.data();
-            v.d2h_bytes += kp->size * kp->words * 8 + kp->size * 4;
-        }
-        if ((e = sb200_derive_kmers(ctx, kp, p->num_buckets, &km))) throw sb200_error(e, ctx->last_error);
-        v.n_kmers = km->size;
-        if (p->fetch_kmers) {
-            uint64_t *h = g->pin<uint64_t>(km->size * km->words);
-            CUDA_CHECK(cudaMemcpyAsync(h, km->data.p, km->size * km->words * 8, cudaMemcpyDeviceToHost, s));
-            v.kmers = h;
-            g->km_starts = km->bucket_starts_host; v.kmer_bucket_starts = g->km_starts.data();
-            v.d2h_bytes += km->size * km->words * 8;
-        }
-        if ((e = sb200_mphf_build(ctx, km, &mp))) throw sb200_error(e, ctx->last_error);
-        if ((e = sb200_ext_build(ctx, kp, km, mp, &ext))) throw sb200_error(e, ctx->last_error);
-        sb200_kmers_free(kp); kp = nullptr;
-        if (p->tip_clip) {
-            uint64_t removed = 0;
-            if ((e = sb200_tipclip(ctx, km, mp, ext, p->tip_length_bound, &removed))) throw sb200_error(e, ctx->last_error);
-            v.clipped = removed;
-        }
-        uint8_t *masks = g->pin<uint8_t>(km->size);
-        CUDA_CHECK(cudaMemcpyAsync(masks, ext->masks.p, km->size, cudaMemcpyDeviceToHost, s));
-        v.masks = masks; v.d2h_bytes += km->size;
-        if ((e = sb200_unitigs_extract(ctx, km, mp, ext, p->with_loops, &un))) throw sb200_error(e, ctx->last_error);
-        uint64_t isz = sb200::mphf_serialize(mp, nullptr);
-        g->index_bytes.resize(isz);
-        sb200::mphf_serialize(mp, g->index_bytes.data());
-        v.index_bytes = g->index_bytes.data(); v.index_size = isz; v.d2h_bytes += mp->total_words * 8 + mp->total_ranks * 8;
-        v.n_unitigs = un->count; v.n_loops = un->n_loops; v.unitig_bases = un->total_bases; v.n_unitig_words = un->total_words;
-        uint64_t *uw = g->pin<uint64_t>(un->total_words);
-        uint64_t *uo = g->pin<uint64_t>(un->count + 1);
-        uint32_t *ul = g->pin<uint32_t>(un->count);
-        CUDA_CHECK(cudaMemcpyAsync(uw, un->words.p, un->total_words * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(uo, un->word_off.p, (un->count + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(ul, un->len.p, un->count * 4, cudaMemcpyDeviceToHost, s));
-        v.unitig_words = uw; v.unitig_word_off = uo; v.unitig_len = ul;
-        v.d2h_bytes += un->total_words * 8 + (un->count + 1) * 8 + un->count * 4;
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        *out = g;
-    });
-    if (reads) sb200_reads_free(reads);
-    if (kp) sb200_kmers_free(kp);
-    if (km) sb200_kmers_free(km);
-    if (mp) sb200_mphf_free(mp);
-    if (ext) sb200_ext_free(ext);
-    if (un) sb200_unitigs_free(un);
-    if (rc && g) { delete g; }
-    return rc;
-}
-#endif
 
 int sb200_graph_get(const sb200_graph *g, sb200_graph_view *view) {
     *view = g->view;

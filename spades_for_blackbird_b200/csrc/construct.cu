@@ -6,6 +6,7 @@
 // next stage computes: the (k+1)-mer table travels during k-mer counting, the k-mer table during MPHF/mask building,
 // masks and index during unitig extraction.  Device buffers whose copy may still be in flight are kept alive until
 // both streams have drained; host buffers come from the context's pinned pool.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sb200.h"
@@ -15,6 +16,7 @@
 
 namespace sb200 {
 uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, const uint64_t *ranks_host, uint8_t *out);
+void mphf_serialize_device(sb200_ctx *ctx, const sb200_mphf *m, uint8_t *out_dev);
 }
 
 extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
@@ -38,6 +40,11 @@ extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint
             CUDA_CHECK(cudaEventRecord(ev, s));
             CUDA_CHECK(cudaStreamWaitEvent(c, ev, 0));
         };
+        const bool timeline = getenv("SB200_TIMELINE") != nullptr;   // host wall clock at the stage boundaries (stages are blocking)
+        const double t_start = sb200_ctx::now_s();
+        auto mark = [&](const char *label) {
+            if (timeline) fprintf(stderr, "[sb200_construct] %-28s %9.3f ms\n", label, (sb200_ctx::now_s() - t_start) * 1e3);
+        };
         g = new sb200_graph();
         g->ctx = ctx;
         memset(&g->view, 0, sizeof g->view);
@@ -45,8 +52,10 @@ extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint
         int e;
         if ((e = sb200_reads_upload(ctx, words, word_off, len, n_reads, &reads))) fail(e);
         v.h2d_bytes = reads->n_words * 8 + (n_reads + 1) * 8 + n_reads * 4;
+        mark("reads uploaded");
         if ((e = sb200_count(ctx, reads, p->k + 1, 1, 1, p->num_buckets, &kp))) fail(e);
         v.n_kpomers = kp->size; v.kpomer_instances = kp->instances;
+        mark("(k+1)-mers counted");
         if (p->fetch_kmers) {
             uint64_t *h = g->pin<uint64_t>(kp->size * kp->words);
             uint32_t *cn = g->pin<uint32_t>(kp->size);
@@ -59,6 +68,7 @@ extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint
         }
         if ((e = sb200_derive_kmers(ctx, kp, p->num_buckets, &km))) fail(e);
         v.n_kmers = km->size;
+        mark("k-mers derived");
         if (p->fetch_kmers) {
             uint64_t *h = g->pin<uint64_t>(km->size * km->words);
             copy_after_compute();
@@ -68,23 +78,29 @@ extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint
             v.d2h_bytes += km->size * km->words * 8;
         }
         if ((e = sb200_mphf_build(ctx, km, &mp))) fail(e);
-        uint64_t *bits_h = g->pin<uint64_t>(mp->total_words + 1);
-        uint64_t *ranks_h = g->pin<uint64_t>(mp->total_ranks + 1);
+        mark("MPHF built");
+        // KMerIndex::serialize: the byte stream is assembled on the device and travels as one copy; the host only fills in the
+        // small fields between the bit-vectors once it has landed
+        const uint64_t isz = sb200::mphf_serialize_host(mp, nullptr, nullptr, nullptr);
+        DevBuf<uint8_t> index_dev(ctx, isz + 8);
+        sb200::mphf_serialize_device(ctx, mp, index_dev.p);
+        uint8_t *index_h = g->pin<uint8_t>(isz + 8);
         copy_after_compute();
-        CUDA_CHECK(cudaMemcpyAsync(bits_h, mp->bits.p, mp->total_words * 8, cudaMemcpyDeviceToHost, c));
-        CUDA_CHECK(cudaMemcpyAsync(ranks_h, mp->ranks.p, mp->total_ranks * 8, cudaMemcpyDeviceToHost, c));
-        v.d2h_bytes += mp->total_words * 8 + mp->total_ranks * 8;
+        CUDA_CHECK(cudaMemcpyAsync(index_h, index_dev.p, isz, cudaMemcpyDeviceToHost, c));
+        v.d2h_bytes += isz;
         if ((e = sb200_ext_build(ctx, kp, km, mp, &ext))) fail(e);
         if (p->tip_clip) {
             uint64_t removed = 0;
             if ((e = sb200_tipclip(ctx, km, mp, ext, p->tip_length_bound, &removed))) fail(e);
             v.clipped = removed;
         }
+        mark("masks filled");
         uint8_t *masks = g->pin<uint8_t>(km->size);
         copy_after_compute();
         CUDA_CHECK(cudaMemcpyAsync(masks, ext->masks.p, km->size, cudaMemcpyDeviceToHost, c));
         v.masks = masks; v.d2h_bytes += km->size;
         if ((e = sb200_unitigs_extract(ctx, km, mp, ext, p->with_loops, &un))) fail(e);
+        mark("unitigs extracted");
         v.n_unitigs = un->count; v.n_loops = un->n_loops; v.unitig_bases = un->total_bases; v.n_unitig_words = un->total_words;
         uint64_t *uw = g->pin<uint64_t>(un->total_words);
         uint64_t *uo = g->pin<uint64_t>(un->count + 1);
@@ -95,13 +111,13 @@ extern "C" int sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint
         CUDA_CHECK(cudaMemcpyAsync(ul, un->len.p, un->count * 4, cudaMemcpyDeviceToHost, c));
         v.unitig_words = uw; v.unitig_word_off = uo; v.unitig_len = ul;
         v.d2h_bytes += un->total_words * 8 + (un->count + 1) * 8 + un->count * 4;
-        // KMerIndex::serialize needs only the geometry (host) until the bit-vectors have landed
-        uint64_t isz = sb200::mphf_serialize_host(mp, nullptr, nullptr, nullptr);
-        g->index_bytes.resize(isz);
+        mark("copies issued");
         CUDA_CHECK(cudaStreamSynchronize(c));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        sb200::mphf_serialize_host(mp, bits_h, ranks_h, g->index_bytes.data());
-        v.index_bytes = g->index_bytes.data(); v.index_size = isz;
+        mark("copies drained");
+        sb200::mphf_serialize_host(mp, nullptr, nullptr, index_h);   // small fields only
+        v.index_bytes = index_h; v.index_size = isz;
+        mark("index header fields");
         *out = g;
     } catch (const sb200_error &err) {
         ctx->last_error = err.what();

@@ -209,7 +209,7 @@ static uint32_t lsd_unique_range(sb200_ctx *ctx, uint64_t *recs, uint64_t m, int
     LAUNCH(ctx, unique_count_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p);
     exclusive_scan<uint32_t>(ctx, tile_cnt.p, tiles, total_dev.p);
     uint32_t u = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&u, total_dev.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&u, total_dev.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     DevBuf<uint32_t> head_pos(ctx, (uint64_t) u + 1);
     LAUNCH(ctx, unique_write_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p, side_recs, head_pos.p);
@@ -227,7 +227,7 @@ static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B) {
     s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
     LAUNCH(ctx, bucket_starts_kernel<W>, div_up(s->size, 256), 256, 0, s->data.p, s->size, B, s->bucket_starts.p);
     s->bucket_starts_host.resize((size_t) B + 1);
-    CUDA_CHECK(cudaMemcpyAsync(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -262,7 +262,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     ctrl.zero();
     LAUNCH(ctx, seg_ranges_kernel<W>, div_up(n_chunks, 128), 128, 0, hb.p, n, n_chunks, ranges.p, dirty_list.p, ctrl.p);
     uint32_t n_dirty = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_dirty, ctrl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&n_dirty, ctrl.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->trace_point("  heads + ranges");
 
@@ -270,12 +270,12 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     DevBuf<uint32_t> side_cnts;
     if (n_dirty) {   // oversize segments: sort their chunks' ranges with the generic LSD path first
         std::vector<uint32_t> dl(n_dirty);
-        CUDA_CHECK(cudaMemcpyAsync(dl.data(), dirty_list.p, (size_t) n_dirty * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(dl.data(), dirty_list.p, (size_t) n_dirty * 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         std::vector<ChunkRange> cr(n_dirty);
         uint64_t side_total = 0;
         for (uint32_t i = 0; i < n_dirty; ++i) {
-            CUDA_CHECK(cudaMemcpyAsync(&cr[i], ranges.p + dl[i], sizeof(ChunkRange), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->fetch(&cr[i], ranges.p + dl[i], sizeof(ChunkRange));
         }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         for (uint32_t i = 0; i < n_dirty; ++i) side_total += cr[i].e - cr[i].s;
@@ -315,7 +315,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     DevBuf<uint32_t> total32(ctx, 1);
     exclusive_scan<uint32_t>(ctx, tile_cnt, n_chunks, total32.p);
     uint32_t u32 = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&u32, total32.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&u32, total32.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     uint64_t u = u32;
     ctx->trace_point("  chunk kernel");
@@ -334,7 +334,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         uint32_t flag = 0;
         DevBuf<uint32_t> fl(ctx, 1);
         LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, s->data.p, u, fl.p);
-        CUDA_CHECK(cudaMemcpyAsync(&flag, fl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&flag, fl.p, 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (flag) --u;
         if (u == 0) {
@@ -366,7 +366,7 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
     LAUNCH(ctx, unique_count_kernel<W>, tiles, UQ_THREADS, 0, sorted, n, tile_cnt.p);
     exclusive_scan<uint32_t>(ctx, tile_cnt.p, tiles, total_dev.p);
     uint32_t u32 = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&u32, total_dev.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&u32, total_dev.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     uint64_t u = u32;
 
@@ -380,7 +380,7 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
     if (drop_marker) {
         LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, s->data.p, u, total_dev.p + 1);
         uint32_t flag = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&flag, total_dev.p + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&flag, total_dev.p + 1, 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (flag) {
             --u;
@@ -398,7 +398,7 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
     s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
     LAUNCH(ctx, bucket_starts_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, B, s->bucket_starts.p);
     s->bucket_starts_host.resize((size_t) B + 1);
-    CUDA_CHECK(cudaMemcpyAsync(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     inst.release();
     return s;
@@ -413,7 +413,7 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
     LAUNCH(ctx, window_count_kernel, div_up(rd->n_reads, 256), 256, 0, rd->len.p, rd->n_reads, (uint32_t) K, mult, off.p);
     exclusive_scan<uint64_t>(ctx, off.p, rd->n_reads, total_dev.p);
     uint64_t n = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&n, total_dev.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     DevBuf<uint64_t> inst(ctx, n * W);
@@ -474,7 +474,7 @@ static sb200_records *extract_records_w(sb200_ctx *ctx, const sb200_reads *rd, i
     LAUNCH(ctx, window_count_kernel, div_up(rd->n_reads ? rd->n_reads : 1, 256), 256, 0, rd->len.p, rd->n_reads, (uint32_t) K, mult, off.p);
     exclusive_scan<uint64_t>(ctx, off.p, rd->n_reads, total_dev.p);
     uint64_t n = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n, total_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&n, total_dev.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     sb200_records *r = new sb200_records();
     r->ctx = ctx; r->k = (unsigned) K; r->words = W; r->n = n;
@@ -547,7 +547,7 @@ static void partition_records_w(sb200_ctx *ctx, sb200_records *r, uint32_t B, ui
         if (res == scratch.p) std::swap(r->data, scratch);   // keep the buffer that holds the grouped records
     }
     std::vector<unsigned long long> h(RS_BINS);
-    CUDA_CHECK(cudaMemcpyAsync(h.data(), counts.p, RS_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(h.data(), counts.p, RS_BINS * 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t p = 0; p < n_parts; ++p) counts_out[p] = h[p];
 }

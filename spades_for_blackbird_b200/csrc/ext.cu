@@ -234,7 +234,7 @@ static uint64_t tipclip_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_
     LAUNCH(ctx, tipclip_apply_kernel, div_up(n, 256), 256, 0, ext->masks.p, kill.p, n);
     LAUNCH(ctx, tipclip_links_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, tipped.p);
     unsigned long long r = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&r, removed.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&r, removed.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (r) ext->succ_valid = false;   // a junction that lost a tip may now have a single successor the racing writes did not keep
     return r;

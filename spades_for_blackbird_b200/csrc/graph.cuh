@@ -7,7 +7,6 @@ struct sb200_graph {
     sb200_ctx *ctx = nullptr;
     sb200_graph_view view;
     std::vector<void *> pinned;
-    std::vector<uint8_t> index_bytes;
     std::vector<uint64_t> kp_starts, km_starts;
     template<class T>
     T *pin(size_t n) {

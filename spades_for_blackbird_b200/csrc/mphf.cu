@@ -207,7 +207,7 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
         std::swap(src, dst);
     }
     uint32_t final_keys = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&final_keys, counters.p + (MPHF_LEVELS - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&final_keys, counters.p + (MPHF_LEVELS - 1), 4);
 
     DevBuf<uint32_t> pc(ctx, words + 1);
     LAUNCH(ctx, mphf_clear_popc_kernel, div_up(words + 1, 256), 256, 0, (unsigned long long *) m->bits.p,
@@ -218,7 +218,7 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     std::vector<uint32_t> ends(B + 1, 0);
     DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
     LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pc.p, m->word_off.p, B, words, ends_dev.p);
-    CUDA_CHECK(cudaMemcpyAsync(ends.data(), ends_dev.p, ((size_t) B + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(ends.data(), ends_dev.p, ((size_t) B + 1) * 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];
     m->final_level_keys = final_keys;
@@ -282,13 +282,21 @@ uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out) {
     return mphf_serialize_host(m, bits.data(), ranks.data(), out);
 }
 
-// bits_host / ranks_host: host copies of the device arrays (only read when out != nullptr)
+// bits_host / ranks_host: host copies of the device arrays.  out == nullptr: size query.  out != nullptr with bits_host ==
+// nullptr: only the small fields are written and the bit-vector / rank bytes are skipped over (they were put in place by
+// mphf_serialize_device + one D2H copy).
 uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, const uint64_t *ranks_host, uint8_t *out) {
-    struct { const uint64_t *b; const uint64_t *data() const { return b; } } bits{bits_host}, ranks{ranks_host};
     uint64_t total = 0;
     uint8_t *p = out;
     auto put = [&](const void *src, size_t n) {
         if (p) { memcpy(p, src, n); p += n; }
+        total += n;
+    };
+    auto put_bulk = [&](const uint64_t *base, uint64_t first_word, size_t n) {
+        if (p) {
+            if (base) memcpy(p, base + first_word, n);
+            p += n;
+        }
         total += n;
     };
     uint64_t nseg = m->num_buckets;
@@ -308,15 +316,54 @@ uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, con
             uint64_t nr = (nchar + 7) / 8;
             put(&size, 8);
             put(&nchar, 8);
-            if (nchar) put(bits.data() + m->word_off_host[t], nchar * 8);
+            if (nchar) put_bulk(bits_host, m->word_off_host[t], nchar * 8);
             put(&nr, 8);
-            if (nr) put(ranks.data() + m->rank_off_host[t], nr * 8);
+            if (nr) put_bulk(ranks_host, m->rank_off_host[t], nr * 8);
         }
         uint64_t nf = 0;
         put(&nf, 8);
     }
     put(m->segment_starts_host.data(), ((size_t) m->num_buckets + 1) * 8);
     return total;
+}
+
+// The same byte stream assembled on the device: every bit-vector and rank array is copied to its place in `out_dev`
+// (`size` bytes, from mphf_serialize_host(m, 0, 0, 0)); the few small fields in between are left for the host to fill after
+// the single D2H copy (mphf_serialize_host(m, nullptr, nullptr, host_copy)).  Saves the host a 50 MB scatter-gather.
+struct SerSeg {
+    uint64_t dst_byte, src_word, nwords;
+    uint32_t is_rank, pad;
+};
+__global__ void __launch_bounds__(256) mphf_serialize_kernel(const SerSeg *__restrict__ segs, const uint64_t *__restrict__ bits,
+                                                            const uint64_t *__restrict__ ranks, uint8_t *__restrict__ out) {
+    const SerSeg sg = segs[blockIdx.x];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>((sg.is_rank ? ranks : bits) + sg.src_word);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + sg.dst_byte);   // the stream keeps 4-byte alignment (BooPHF.h:514-532 field sizes)
+    for (uint64_t i = threadIdx.x; i < 2 * sg.nwords; i += blockDim.x) dst[i] = src[i];
+}
+
+void mphf_serialize_device(sb200_ctx *ctx, const sb200_mphf *m, uint8_t *out_dev) {
+    std::vector<SerSeg> segs;
+    uint64_t off = 8;
+    for (uint32_t b = 0; b < m->num_buckets; ++b) {
+        off += 8 + 4 + 8 + 8;
+        for (int l = 0; l < MPHF_LEVELS; ++l) {
+            size_t t = (size_t) b * MPHF_LEVELS + l;
+            uint64_t size = m->domain_host[t];
+            uint64_t nchar = size ? 1 + size / 64 : 0, nr = (nchar + 7) / 8;
+            off += 16;
+            if (nchar) segs.push_back(SerSeg{off, m->word_off_host[t], nchar, 0u, 0u});
+            off += nchar * 8 + 8;
+            if (nr) segs.push_back(SerSeg{off, m->rank_off_host[t], nr, 1u, 0u});
+            off += nr * 8;
+        }
+        off += 8;
+    }
+    if (segs.empty()) return;
+    DevBuf<SerSeg> d(ctx, segs.size());
+    CUDA_CHECK(cudaMemcpyAsync(d.p, segs.data(), segs.size() * sizeof(SerSeg), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, mphf_serialize_kernel, (unsigned) segs.size(), 256, 0, d.p, m->bits.p, m->ranks.p, out_dev);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `segs` (pageable) must outlive the H2D copy
 }
 
 }  // namespace sb200

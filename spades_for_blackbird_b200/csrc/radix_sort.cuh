@@ -18,7 +18,13 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
 
 // records per thread; a tile (256 threads x ITEMS records) is staged in <= 32 KB of shared memory
-template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? 8 : 4; };
+#ifndef RS_ITEMS_W2
+#define RS_ITEMS_W2 8
+#endif
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 1
+#endif
+template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? RS_ITEMS_W2 : 4; };
 
 // digit selector: word >= 0 -> byte `shift/8` of that word; word < 0 -> byte of the bucket id
 struct DigitSel {
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_direct_kernel(const uin
 // consecutive records of the same bin, so a bin's run inside the tile leaves as one coalesced burst instead of one
 // 16-byte store per record.  offsets[bin * num_tiles + tile] = exclusive scan of the histogram matrix.
 template<int W>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
                                                                DigitSel sel, const uint32_t *__restrict__ offsets,
                                                                uint32_t num_tiles) {
     constexpr int ITEMS = RsItems<W>::value;

@@ -365,201 +365,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
 }  // namespace sb200
 #include "unitigs_walk.cuh"
 namespace sb200 {
-#if 0   // first version of the direct walks (one thread per oriented junction); superseded by unitigs_walk.cuh
-// ---- direct walks ------------------------------------------------------------------------------------------------------
-// When no chain is longer than WALK_LIMIT vertices (every read set with sequencing errors: a branch every few bases),
-// list ranking is overkill: one thread per oriented junction follows each of its start edges with one MPHF lookup per
-// step — bit-vectors, rank samples and masks together are ~130 MB and stay L2-resident — exactly like the reference's
-// ConstructSequenceWithEdge, but for all ~10^7 start edges at once.  A first walk measures (length, end k-mer -> keep or
-// drop); after a scan a second walk re-traces the kept paths and emits the 2-bit packed sequence directly.  Needs only
-// the masks, the MPHF and the junction's own k-mer: nothing indexed by "all vertices" is built, which is also what lets
-// several GPUs extract disjoint file ranges of junctions independently.  A chain longer than WALK_LIMIT sends the
-// whole extraction to the pointer-jumping path below.
-constexpr uint32_t WALK_LIMIT = 1024;
-
-struct WalkRec {       // one start edge, stored at 4 * (work-list position) + nucleotide
-    uint32_t n;        // appended bases (|s| = k + n); 0 = edge absent or sequence dropped
-};
-
-template<int W>
-__device__ __forceinline__ uint32_t walk_mask(const MphfDev &m, const uint8_t *__restrict__ masks, const uint64_t *y, int k) {
-    bool minimal;
-    uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-    uint32_t raw = masks[idy];
-    return minimal ? raw : mask_conj(raw);
-}
-
-template<int W>
-__global__ void __launch_bounds__(128) walk_measure_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ jlist,
-                                                          uint32_t n_j, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
-                                                          WalkRec *__restrict__ edges, uint32_t *__restrict__ cnt,
-                                                          unsigned long long *__restrict__ words,
-                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases */) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_j) return;
-    uint32_t t = jlist[j];
-    uint64_t i = t >> 1;
-    int strand = (int) (t & 1);
-    uint32_t raw = masks[idx[i]];
-    uint32_t mk0 = strand ? mask_conj(raw) : raw;
-    uint64_t x[W];
-    oriented_kmer<W>(kmers, i, strand, k, x);
-    uint32_t c_kept = 0;
-    unsigned long long nwords = 0, chain_nodes = 0, kept_bases = 0;
-    bool too_long = false;
-#pragma unroll 1
-    for (uint32_t c = 0; c < 4; ++c) {
-        WalkRec e;
-        e.n = 0;
-        if (mk0 & (1u << c)) {
-            uint64_t y[W], z[W];
-            kmer_shl<W>(x, k, c, y);
-            uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
-            uint32_t mk = walk_mask<W>(m, masks, y, k);
-            uint32_t nn = 1;
-            while (!mask_is_junction(mk)) {
-                if (nn > WALK_LIMIT) { too_long = true; break; }
-                prev_first = kmer_base(y, 0);
-                kmer_shl<W>(y, k, nib_next(mk & 15u), z);
-#pragma unroll
-                for (int q = 0; q < W; ++q) y[q] = z[q];
-                mk = walk_mask<W>(m, masks, y, k);
-                ++nn;
-            }
-            if (!too_long) {
-                chain_nodes += nn - 1;
-                uint64_t rcn[W];
-                kmer_rc<W>(y, k, rcn);
-                int cmp = kmer_lex_cmp<W>(x, rcn);
-                uint32_t cprime = 3u - prev_first;
-                bool keep = cmp > 0 || (cmp == 0 && c >= cprime);
-                if (keep) { e.n = nn; ++c_kept; nwords += ((unsigned long long) k + nn + 31) >> 5; kept_bases += (unsigned long long) k + nn; }
-            }
-        }
-        edges[4ull * j + c] = e;
-    }
-    cnt[j] = c_kept;
-    words[j] = nwords;
-    if (chain_nodes) atomicAdd(&totals[0], chain_nodes);
-    if (too_long) atomicAdd(&totals[1], 1ULL);
-    if (kept_bases) atomicAdd(&totals[4], kept_bases);
-}
-
-// second walk: packed output.  Bases are accumulated 32 to a word in a register and stored once per word.
-template<int W>
-__global__ void __launch_bounds__(128) walk_emit_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ jlist,
-                                                       uint32_t n_j, const uint8_t *__restrict__ masks, const WalkRec *__restrict__ edges,
-                                                       const uint32_t *__restrict__ cnt_off, const unsigned long long *__restrict__ word_base,
-                                                       uint32_t *__restrict__ seq_len, uint64_t *__restrict__ seq_word_off,
-                                                       uint64_t *__restrict__ out_words) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_j) return;
-    uint32_t t = jlist[j];
-    uint32_t u = cnt_off[j];
-    unsigned long long woff = word_base[j];
-    uint64_t x[W];
-    bool have_x = false;
-#pragma unroll 1
-    for (uint32_t c = 0; c < 4; ++c) {
-        uint32_t nn = edges[4ull * j + c].n;
-        if (nn == 0) continue;
-        if (!have_x) { oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x); have_x = true; }
-        const uint32_t L = (uint32_t) k + nn;
-        seq_len[u] = L;
-        seq_word_off[u] = woff;
-        // the first k bases are the junction's k-mer: whole words of x, then the partial word continues in `acc`
-        uint32_t pos = 0;
-        uint64_t acc = 0;
-#pragma unroll
-        for (int q = 0; q < W; ++q) {
-            if ((q + 1) * 32 <= k) { out_words[woff + q] = x[q]; pos = (q + 1) * 32; }
-        }
-        if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // the partial word is always the last; its padding bits are zero
-        auto push = [&](uint32_t base) {
-            acc |= (uint64_t) base << (2 * (pos & 31));
-            ++pos;
-            if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
-        };
-        push(c);
-        uint64_t y[W], z[W];
-        kmer_shl<W>(x, k, c, y);
-        for (uint32_t s = 1; s < nn; ++s) {
-            uint32_t mk = walk_mask<W>(m, masks, y, k);
-            uint32_t b = nib_next(mk & 15u);
-            push(b);
-            kmer_shl<W>(y, k, b, z);
-#pragma unroll
-            for (int q = 0; q < W; ++q) y[q] = z[q];
-        }
-        if (pos & 31) out_words[woff + (pos >> 5)] = acc;
-        ++u;
-        woff += ((unsigned long long) L + 31) >> 5;
-    }
-}
-
-__global__ void count_nonjunction_kernel(const uint8_t *__restrict__ masks, uint64_t n, unsigned long long *__restrict__ total) {
-    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    bool nj = (i < n) && !mask_is_junction(masks[i]);
-    uint32_t b = __ballot_sync(0xffffffffu, nj);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(total, (unsigned long long) __popc(b));
-}
-
-// Returns nullptr when the direct walks do not apply (a chain longer than WALK_LIMIT, or perfect loops to collect):
-// the caller then runs the pointer-jumping path.  [first, last) restricts the junctions to a file range of k-mers.
-template<int W>
-static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int with_loops,
-                                     uint64_t first, uint64_t last, bool whole) {
-    uint64_t n = kmers->size;
-    int k = (int) kmers->k;
-    MphfDev m = mphf_dev(mphf);
-    uint64_t n_range = last - first;
-    uint32_t n_j = 0;
-    DevBuf<uint32_t> jlist;
-    {
-        DevBuf<uint32_t> flag(ctx, 2 * n_range + 1);
-        DevBuf<uint32_t> tot(ctx, 1);
-        LAUNCH(ctx, junction_flag_kernel, div_up(2 * n_range ? 2 * n_range : 1, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, flag.p);
-        exclusive_scan<uint32_t>(ctx, flag.p, 2 * n_range, tot.p);
-        CUDA_CHECK(cudaMemcpyAsync(&n_j, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        jlist.alloc(ctx, (uint64_t) n_j + 1);
-        if (n_j) LAUNCH(ctx, compact_kernel, div_up(2 * n_range, 256), 256, 0, flag.p, 2 * n_range, n_j, jlist.p);
-    }
-    DevBuf<WalkRec> edges(ctx, 4ull * n_j + 4);
-    DevBuf<uint32_t> cnt(ctx, (uint64_t) n_j + 1);
-    DevBuf<unsigned long long> words(ctx, (uint64_t) n_j + 1);
-    DevBuf<unsigned long long> totals(ctx, 6);   // [0] chain vertices seen [1] long chains [2] total words [3] non-junction k-mers [4] bases
-    totals.zero();
-    const uint64_t *kbase = kmers->data.p + first * W;
-    if (n_j)
-        LAUNCH(ctx, walk_measure_kernel<W>, div_up(n_j, 128), 128, 0, m, kbase, k, jlist.p, n_j, ext->idx.p + first, ext->masks.p, edges.p, cnt.p,
-               words.p, totals.p);
-    if (whole && with_loops) LAUNCH(ctx, count_nonjunction_kernel, div_up(n, 256), 256, 0, ext->masks.p, n, totals.p + 3);
-    DevBuf<uint32_t> cnt_total(ctx, 1);
-    exclusive_scan<uint32_t>(ctx, cnt.p, n_j, cnt_total.p);
-    exclusive_scan<unsigned long long>(ctx, words.p, n_j, totals.p + 2);
-    unsigned long long th[6];
-    uint32_t n_paths = 0;
-    CUDA_CHECK(cudaMemcpyAsync(th, totals.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&n_paths, cnt_total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (th[1] != 0) return nullptr;                                        // some chain is too long for a sequential walk
-    if (whole && with_loops && th[0] != 2 * th[3]) return nullptr;        // vertices no walk reached: perfect loops exist
-    sb200_unitigs *out = new sb200_unitigs();
-    out->ctx = ctx; out->k = (unsigned) k; out->count = n_paths; out->n_loops = 0; out->total_words = th[2];
-    out->len.alloc(ctx, (uint64_t) n_paths + 1);
-    out->word_off.alloc(ctx, (uint64_t) n_paths + 1);
-    out->words.alloc(ctx, th[2] + 1);
-    if (n_j && n_paths)
-        LAUNCH(ctx, walk_emit_kernel<W>, div_up(n_j, 128), 128, 0, m, kbase, k, jlist.p, n_j, ext->masks.p, edges.p, cnt.p, words.p, out->len.p,
-               out->word_off.p, out->words.p);
-    uint64_t tw = th[2];
-    CUDA_CHECK(cudaMemcpyAsync(out->word_off.p + n_paths, &tw, 8, cudaMemcpyHostToDevice, ctx->stream));
-    out->total_bases = th[4];
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    return out;
-}
-#endif
 
 template<int W>
 static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int with_loops) {
@@ -593,7 +398,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     for (; rounds < MAX_ROUNDS; ++rounds) {
         LAUNCH(ctx, jump_kernel, div_up(n_nodes, 256), 256, 0, state.p, n_nodes, changed.p + rounds);
         uint32_t ch = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&ch, changed.p + rounds, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&ch, changed.p + rounds, 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (!ch) { converged = true; break; }
     }
@@ -608,7 +413,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
         DevBuf<uint32_t> tot(ctx, 1);
         LAUNCH(ctx, loop_flag_kernel, div_up(n, 256), 256, 0, ext->idx.p, n, ext->masks.p, state.p, flag.p);
         exclusive_scan<uint32_t>(ctx, flag.p, n, tot.p);
-        CUDA_CHECK(cudaMemcpyAsync(&n_loop_nodes, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&n_loop_nodes, tot.p, 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (n_loop_nodes) {
             loop_list.alloc(ctx, n_loop_nodes);
@@ -617,7 +422,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
             scratch.alloc(ctx, (uint64_t) n_loop_nodes + k + 8);
             LAUNCH(ctx, loops_kernel<W>, 1, 1, 0, kmers->data.p, k, ext->idx.p, ext->masks.p, succ, loop_list.p, n_loop_nodes, visited.p, 0,
                    totals_dev.p, scratch.p, 0u, 0ull, (uint32_t *) nullptr, (unsigned long long *) nullptr, (uint8_t *) nullptr);
-            CUDA_CHECK(cudaMemcpyAsync(loop_totals, totals_dev.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->fetch(loop_totals, totals_dev.p, 16);
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -629,7 +434,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
         DevBuf<uint32_t> tot(ctx, 1);
         LAUNCH(ctx, junction_flag_kernel, div_up(n_nodes, 256), 256, 0, n, ext->idx.p, ext->masks.p, flag.p);
         exclusive_scan<uint32_t>(ctx, flag.p, n_nodes, tot.p);
-        CUDA_CHECK(cudaMemcpyAsync(&n_j, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&n_j, tot.p, 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         jlist.alloc(ctx, (uint64_t) n_j + 1);
         if (n_j) LAUNCH(ctx, compact_kernel, div_up(n_nodes, 256), 256, 0, flag.p, n_nodes, n_j, jlist.p);
@@ -645,8 +450,8 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
         DevBuf<uint32_t> cnt_total(ctx, 1);
         exclusive_scan<uint32_t>(ctx, cnt.p, n_j, cnt_total.p);
         exclusive_scan<unsigned long long>(ctx, bases.p, n_j, totals_dev.p + 2);
-        CUDA_CHECK(cudaMemcpyAsync(&n_paths, cnt_total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(&path_bases, totals_dev.p + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->fetch(&n_paths, cnt_total.p, 4);
+        ctx->fetch(&path_bases, totals_dev.p + 2, 8);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
 
@@ -674,7 +479,7 @@ static sb200_unitigs *unitigs_w(sb200_ctx *ctx, const sb200_kmers *kmers, const 
     LAUNCH(ctx, seq_words_kernel, div_up(n_seqs ? n_seqs : 1, 256), 256, 0, out->len.p, n_seqs, (unsigned long long *) out->word_off.p);
     exclusive_scan<unsigned long long>(ctx, (unsigned long long *) out->word_off.p, n_seqs, (unsigned long long *) (out->word_off.p + n_seqs));
     uint64_t total_words = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&total_words, out->word_off.p + n_seqs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&total_words, out->word_off.p + n_seqs, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     out->total_words = total_words;
     out->words.alloc(ctx, total_words + 1);
@@ -703,7 +508,7 @@ sb200_unitigs *extract_unitigs_local(sb200_ctx *ctx, const sb200_kmers *kmers, c
     nj.zero();
     LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, ext->size, nj.p);
     unsigned long long h = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h, nj.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&h, nj.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     stats[0] = st.chain_vertices; stats[1] = st.long_chains; stats[2] = st.n_edges; stats[3] = st.n_kept; stats[4] = st.kept_bases; stats[5] = h;
     return u;

@@ -314,7 +314,7 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     totals.zero();
     if (nt) LAUNCH(ctx, junction_degree_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p);
     exclusive_scan<uint32_t>(ctx, deg.p, nt, tot32.p);
-    CUDA_CHECK(cudaMemcpyAsync(&st.n_edges, tot32.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(&st.n_edges, tot32.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     uint32_t n_e = st.n_edges;
     DevBuf<uint32_t> elist(ctx, (uint64_t) n_e + 1), elen(ctx, (uint64_t) n_e + 1), kflag(ctx, (uint64_t) n_e + 1);
@@ -340,8 +340,8 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     exclusive_scan<uint32_t>(ctx, kflag.p, n_e, tot32.p + 1);
     exclusive_scan<unsigned long long>(ctx, ewords.p, n_e, totals.p + 2);
     unsigned long long th[6];
-    CUDA_CHECK(cudaMemcpyAsync(th, totals.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&st.n_kept, tot32.p + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fetch(th, totals.p, 48);
+    ctx->fetch(&st.n_kept, tot32.p + 1, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     st.chain_vertices = th[0]; st.long_chains = th[1]; st.words = th[2]; st.kept_bases = th[4];
     if (stats_out) *stats_out = st;
