@@ -217,6 +217,14 @@ def main_sharded(a, world, rank, local_rank):
     backend = D.GpuShardBackend(ctx, dev)
     streams = B.ReadStreams(ctx, hw, word_off, lens)
     info = {}
+    pinned_bufs = {}
+
+    def pinned(name, nbytes):   # grow-only pinned host buffers, reused by every step
+        t = pinned_bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.05) + 64, dtype=torch.uint8).pin_memory()
+            pinned_bufs[name] = t
+        return t
 
     def step(e2e):
         rs = B.ReadStreams(ctx, hw, word_off, lens) if e2e else streams      # e2e: H2D of the reads inside the timed region
@@ -224,13 +232,23 @@ def main_sharded(a, world, rank, local_rank):
         info.update(kpomers=res.kpomers.total_kmers(), instances=res.kpomers.instances, kmers=res.kmers.total_kmers(),
                     unitigs=int(res.stats[:, 3].sum()), unitig_bases=int(res.stats[:, 4].sum()))
         d2h = 0
-        if e2e:   # every rank brings its shard of the tables home; rank 0 also the masks and the gathered unitigs
-            kp, kc, km = res.kpomers.final_kmers(), res.kpomers.counts(), res.kmers.final_kmers()
-            d2h = kp.nbytes + kc.nbytes + km.nbytes
+        if e2e:   # every rank brings its shard of the tables home (pinned buffers); rank 0 also the masks and the gathered unitigs
+            kp, km = res.kpomers, res.kmers
+            hp = pinned("kp", kp.total_kmers() * kp.words * 8)
+            hc = pinned("kc", kp.total_kmers() * 4)
+            hk = pinned("km", km.total_kmers() * km.words * 8)
+            ctx.check(ctx.lib.sb200_kmers_download(kp.h, 0, kp.total_kmers(), B.C.cast(hp.data_ptr(), B.u64p)))
+            ctx.check(ctx.lib.sb200_kmers_counts_download(kp.h, 0, kp.total_kmers(), B.C.cast(hc.data_ptr(), B.u32p)))
+            ctx.check(ctx.lib.sb200_kmers_download(km.h, 0, km.total_kmers(), B.C.cast(hk.data_ptr(), B.u64p)))
+            d2h = kp.total_kmers() * (kp.words * 8 + 4) + km.total_kmers() * km.words * 8
             if rank == 0:
-                m = backend.ext_masks(res.ext).cpu()
-                gw = [t.cpu() for t in res.gathered[0]]
-                d2h += m.numel() + sum(t.numel() * 8 for t in gw)
+                m = backend.ext_masks(res.ext)
+                parts = [m] + [t for lst in res.gathered for t in lst]
+                for i, t in enumerate(parts):
+                    nb = t.numel() * t.element_size()
+                    pinned("g%d" % i, nb)[:nb].copy_(t.contiguous().view(torch.uint8).reshape(-1), non_blocking=True)
+                    d2h += nb
+                torch.cuda.synchronize()
         res.kpomers.free(); res.kmers.free(); res.index.free()
         backend.free_ext(res.ext); backend.free_unitigs(res.unitigs)
         if e2e:

@@ -236,106 +236,84 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
                                    bool double_palindromes, bool drop_marker);
 
 // Sort + unique + counts + bucket table.  `inst` (n x W) is consumed.
-//   1. three stable counting passes group the instances by (bucket, 16-bit value prefix)            radix_sort.cuh
-//   2. one shared-memory pass ranks, deduplicates and counts inside every group and writes the unique records to
-//      their final place (decoupled look-back for the offsets)                                        segsort.cuh
+//   1. one or two stable counting passes group the instances by the composite key bucket << p | top p value bits, with p
+//      chosen so that a group is ~7 K records (radix_sort.cuh)
+//   2. one CTA per group finishes the order in shared memory (counting sort on the next 8 bits, warp-tile deduplication,
+//      ranking inside segments), counts, and packs the unique records; a scan + compaction closes the gaps (segsort.cuh)
 template<int W>
 static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
                                bool double_palindromes, bool drop_marker) {
     SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     if (2 * K < 24) return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
     using Cfg = SegCfg<W>;
+    const int top = (W == 1) ? 2 * K : 64;
+    int bbits = 0;
+    while ((1ull << bbits) < B) ++bbits;
+    const int pmax = std::min(24 - std::min(bbits, 24), top - 8);
+    int p = 0;
+    while (p < pmax && (double) n / (double) ((uint64_t) B << p) > (double) Cfg::TARGET) ++p;
+    const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
+    const int dshift = top - p - 8;
+    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top};
+
     DevBuf<uint64_t> scratch(ctx, n * W);
     ctx->trace_point("  instances ready");
-    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, prefix_passes(W, K, B, drop_marker));
-    ctx->trace_point("  prefix passes");
+    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker));
+    ctx->trace_point("  group passes");
     uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
 
-    PrefixKey pk{prefix_shift(W, K), B, drop_marker ? 1 : 0};
-    DevBuf<uint32_t> hb(ctx, (n + 31) / 32 + 2);
-    LAUNCH(ctx, seg_heads_kernel<W>, div_up(n, 256), 256, 0, grouped, n, pk, hb.p);
-    uint32_t n_chunks = div_up(n, Cfg::C);
-    DevBuf<ChunkRange> ranges(ctx, n_chunks);
-    DevBuf<uint32_t> dirty_list(ctx, n_chunks);
-    DevBuf<uint32_t> ctrl(ctx, 4);   // [0] n_dirty  [1] tile counter
-    DevBuf<unsigned long long> total_dev(ctx, 1);
+    DevBuf<uint32_t> starts(ctx, (uint64_t) n_groups + 1);
+    DevBuf<ChunkRange> ranges(ctx, n_groups);
+    DevBuf<uint32_t> ctrl(ctx, 4);   // [0] fail flag
     ctrl.zero();
-    LAUNCH(ctx, seg_ranges_kernel<W>, div_up(n_chunks, 128), 128, 0, hb.p, n, n_chunks, ranges.p, dirty_list.p, ctrl.p);
-    uint32_t n_dirty = 0;
-    ctx->fetch(&n_dirty, ctrl.p, 4);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->trace_point("  heads + ranges");
+    LAUNCH(ctx, group_bounds_kernel<W>, div_up((uint64_t) n_groups + 1, 128), 128, 0, grouped, n, gk, n_groups, starts.p);
+    LAUNCH(ctx, group_ranges_kernel, div_up(n_groups, 256), 256, 0, starts.p, n_groups, ranges.p);
+    ctx->trace_point("  group bounds");
 
-    DevBuf<uint64_t> side_recs;
-    DevBuf<uint32_t> side_cnts;
-    if (n_dirty) {   // oversize segments: sort their chunks' ranges with the generic LSD path first
-        std::vector<uint32_t> dl(n_dirty);
-        ctx->fetch(dl.data(), dirty_list.p, (size_t) n_dirty * 4);
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        std::vector<ChunkRange> cr(n_dirty);
-        uint64_t side_total = 0;
-        for (uint32_t i = 0; i < n_dirty; ++i) {
-            ctx->fetch(&cr[i], ranges.p + dl[i], sizeof(ChunkRange));
-        }
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < n_dirty; ++i) side_total += cr[i].e - cr[i].s;
-        side_recs.alloc(ctx, side_total * W);
-        side_cnts.alloc(ctx, side_total);
-        uint64_t off = 0;
-        for (uint32_t i = 0; i < n_dirty; ++i) {
-            uint64_t m = cr[i].e - cr[i].s;
-            uint32_t u = lsd_unique_range<W>(ctx, grouped + (uint64_t) cr[i].s * W, m, K, B, drop_marker, want_counts,
-                                             side_recs.p + off * W, side_cnts.p + off);
-            cr[i].side_off = (uint32_t) off;
-            cr[i].side_cnt = u;
-            off += m;
-            CUDA_CHECK(cudaMemcpyAsync(ranges.p + dl[i], &cr[i], sizeof(ChunkRange), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    }
-
-    DevBuf<unsigned long long> status(ctx, n_chunks);
-    status.zero();
+    DevBuf<uint32_t> group_unique(ctx, (uint64_t) n_groups + 1);
     DevBuf<uint32_t> cnt_full;
     if (want_counts) cnt_full.alloc(ctx, n);
     size_t smem = seg_chunk_smem<W>();
     if (want_counts) {
-        auto seg_chunk_kernel_ = seg_chunk_kernel<W, true>;
+        auto seg_chunk_kernel_ = group_chunk_kernel<W, true>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
-               cnt_full.p, total_dev.p, n_chunks, pk.shift);
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift);
     } else {
-        auto seg_chunk_kernel_ = seg_chunk_kernel<W, false>;
+        auto seg_chunk_kernel_ = group_chunk_kernel<W, false>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_chunks, Cfg::THREADS, smem, grouped, n, hb.p, ranges.p, side_recs.p, side_cnts.p, status.p, ctrl.p + 1, other,
-               (uint32_t *) nullptr, total_dev.p, n_chunks, pk.shift);
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift);
     }
-    // per-tile unique counts -> offsets; the total sizes the result
-    uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(status.p);
+    // per-group unique counts -> offsets; the total sizes the result
     DevBuf<uint32_t> total32(ctx, 1);
-    exclusive_scan<uint32_t>(ctx, tile_cnt, n_chunks, total32.p);
-    uint32_t u32 = 0;
+    exclusive_scan<uint32_t>(ctx, group_unique.p, n_groups, total32.p);
+    uint32_t u32 = 0, failed = 0;
     ctx->fetch(&u32, total32.p, 4);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    uint64_t u = u32;
+    ctx->fetch(&failed, ctrl.p, 4);
     ctx->trace_point("  chunk kernel");
+    if (failed) {   // a digit bin beyond the shared-memory capacity (massively repeated k-mer): redo with the generic path
+        uint64_t *src = grouped;
+        if (src != inst.p) CUDA_CHECK(cudaMemcpyAsync(inst.p, src, n * W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        scratch.release();
+        cnt_full.release();
+        return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+    }
+    uint64_t u = u32;
 
     sb200_kmers *s = new sb200_kmers();
     s->ctx = ctx; s->k = (unsigned) K; s->words = W; s->num_buckets = B; s->instances = n;
     s->data.alloc(ctx, u * W);   // right-sized: the instance-sized ping-pong buffers go back to the allocator
     if (want_counts) {
         s->counts.alloc(ctx, u);
-        LAUNCH(ctx, (seg_compact_kernel<W, true>), n_chunks, 256, 0, other, cnt_full.p, ranges.p, tile_cnt, n_chunks, u32, s->data.p, s->counts.p);
+        LAUNCH(ctx, (seg_compact_kernel<W, true>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p, s->counts.p);
     } else {
-        LAUNCH(ctx, (seg_compact_kernel<W, false>), n_chunks, 256, 0, other, (const uint32_t *) nullptr, ranges.p, tile_cnt, n_chunks, u32, s->data.p,
-               (uint32_t *) nullptr);
+        LAUNCH(ctx, (seg_compact_kernel<W, false>), n_groups, 256, 0, other, (const uint32_t *) nullptr, ranges.p, group_unique.p, n_groups, u32,
+               s->data.p, (uint32_t *) nullptr);
     }
     if (drop_marker) {
         uint32_t flag = 0;
         DevBuf<uint32_t> fl(ctx, 1);
         LAUNCH(ctx, last_is_marker_kernel<W>, 1, 1, 0, s->data.p, u, fl.p);
         ctx->fetch(&flag, fl.p, 4);
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         if (flag) --u;
         if (u == 0) {
             delete s;

@@ -26,17 +26,19 @@ constexpr int RS_BINS = 256;
 #endif
 template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? RS_ITEMS_W2 : 4; };
 
-// digit selector: word >= 0 -> byte `shift/8` of that word; word < 0 -> byte of the bucket id
+// digit selector: word >= 0 -> byte `shift/8` of that word; word == -1 -> byte of the bucket id; word == -2 -> owner of the
+// bucket; word == -3 -> byte `shift/8` of the composite group key  bucket << p | top p bits of word 0  (segsort.cuh)
 struct DigitSel {
     int word;
     int shift;
     uint32_t num_buckets;
     int marker;   // 1: an all-ones record is the "filtered out" marker and belongs to the last bucket (sorts last)
+    int p;        // composite only: prefix bits of the value
+    int top;      // composite only: significant bits of word 0 (64, or 2K for one-word records)
 };
 
 template<int W>
-__device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &d) {
-    if (d.word >= 0) return (uint32_t) (r[d.word] >> d.shift) & 0xFFu;
+__device__ __forceinline__ uint32_t rs_bucket(const uint64_t *r, const DigitSel &d) {
     uint32_t b = kmer_bucket<W>(r, d.num_buckets);
     if (d.marker) {
         bool m = true;
@@ -44,6 +46,20 @@ __device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &
         for (int j = 0; j < W; ++j) m &= (r[j] == ~0ULL);
         if (m) b = d.num_buckets - 1;
     }
+    return b;
+}
+
+template<int W>
+__device__ __forceinline__ uint32_t rs_composite(const uint64_t *r, const DigitSel &d) {
+    const uint32_t pre = d.p ? (uint32_t) ((r[0] >> (d.top - d.p)) & ((1ULL << d.p) - 1ULL)) : 0u;
+    return (rs_bucket<W>(r, d) << d.p) | pre;
+}
+
+template<int W>
+__device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &d) {
+    if (d.word >= 0) return (uint32_t) (r[d.word] >> d.shift) & 0xFFu;
+    if (d.word == -3) return (rs_composite<W>(r, d) >> d.shift) & 0xFFu;
+    uint32_t b = rs_bucket<W>(r, d);
     if (d.word == -2) return (uint32_t) (((uint64_t) b * (uint32_t) d.shift) / d.num_buckets);   // owner of the bucket; shift = #owners
     return (b >> d.shift) & 0xFFu;
 }
@@ -277,16 +293,10 @@ inline std::vector<DigitSel> full_passes(int W, int K, uint32_t num_buckets, boo
     return passes;
 }
 
-// bit offset of the 16-bit value prefix (the two most significant bytes' worth of bits of word 0)
-inline int prefix_shift(int W, int K) { return (W == 1 ? 2 * K : 64) - 16; }
-
-// only the 16 most significant bits of word 0, then the bucket id: groups records into (bucket, prefix) segments
-inline std::vector<DigitSel> prefix_passes(int W, int K, uint32_t num_buckets, bool marker) {
+// the composite group key (segsort.cuh), least significant byte first: `bits` = bucket bits + p
+inline std::vector<DigitSel> composite_passes(int bits, int p, int top, uint32_t num_buckets, bool marker) {
     std::vector<DigitSel> passes;
-    int sh = prefix_shift(W, K);
-    passes.push_back(DigitSel{0, sh, 0, 0});
-    passes.push_back(DigitSel{0, sh + 8, 0, 0});
-    append_bucket_passes(passes, num_buckets, marker);
+    for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{-3, s, num_buckets, marker ? 1 : 0, p, top});
     return passes;
 }
 

@@ -228,3 +228,49 @@ def test_direct_walks_by_lookup(monkeypatch):
             index.free(); kpomers.free(); streams.free()
     finally:
         ctx2.close()
+
+
+@pytest.mark.parametrize("k,nb,cov", [(21, 1, 300), (33, 2, 250), (55, 1, 200)])
+def test_clumpy_groups_take_several_rounds(ctx, k, nb, cov):
+    """High coverage makes group sizes of the shared-memory sort clumpy (every genomic k-mer brings `cov` copies at once): groups
+    larger than the shared-memory capacity are processed in several digit-range rounds.  Same sets, counts, unitigs."""
+    genome = synth.random_genome(2500, 300 + k)
+    n_pairs = int(2500 * cov / (2 * 100))
+    codes = synth.sample_pairs(genome, n_pairs, 100, 250, 0.004, 301 + k)
+    reads = synth.codes_to_strings(codes)
+    want = O.gbuilder(reads, k, nb)
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
+    assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
+    assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+
+
+def test_massively_repeated_kmer_falls_back_to_lsd(ctx):
+    """One read repeated 12 000 times: a single digit bin exceeds the shared-memory capacity, the group kernel raises its fail
+    flag and the set is redone by the generic LSD path — multiplicities included."""
+    genome = synth.random_genome(400, 11)
+    base = synth.codes_to_strings(synth.sample_pairs(genome, 40, 100, 250, 0.0, 12))
+    reads = base + [base[0]] * 12000
+    k, nb = 31, 10
+    want = O.gbuilder(reads, k, nb)
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
+    assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
+    assert int(kpomers.counts().max()) >= 12000
+    assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+
+
+def test_low_complexity_reads_overflow_a_segment(ctx):
+    """Reads that are 90 % A: thousands of distinct k-mers share their leading bits, one shared-memory segment holds more
+    distinct values than a warp keeps in registers, the fail flag sends the set to the generic LSD path."""
+    rng = np.random.default_rng(5)
+    reads = ["".join("ACGT"[c] for c in np.where(rng.random(70) < 0.9, 0, rng.integers(0, 4, 70))) for _ in range(4000)]
+    k, nb = 21, 10
+    want = O.gbuilder(reads, k, nb)
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
+    assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
+    assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
