@@ -217,6 +217,7 @@ def main_sharded(a, world, rank, local_rank):
     backend = D.GpuShardBackend(ctx, dev)
     streams = B.ReadStreams(ctx, hw, word_off, lens)
     info = {}
+    stage_acc = {}
     pinned_bufs = {}
 
     def pinned(name, nbytes):   # grow-only pinned host buffers, reused by every step
@@ -229,6 +230,9 @@ def main_sharded(a, world, rank, local_rank):
     def step(e2e):
         rs = B.ReadStreams(ctx, hw, word_off, lens) if e2e else streams      # e2e: H2D of the reads inside the timed region
         res = D.construct_sharded(backend, comm, rs, a.k, a.buckets, gather_to=0)
+        if not e2e:
+            for k_, v_ in res.stage_ms.items():
+                stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
         info.update(kpomers=res.kpomers.total_kmers(), instances=res.kpomers.instances, kmers=res.kmers.total_kmers(),
                     unitigs=int(res.stats[:, 3].sum()), unitig_bases=int(res.stats[:, 4].sum()))
         d2h = 0
@@ -282,6 +286,7 @@ def main_sharded(a, world, rank, local_rank):
     sampler.start()
     ctx.kernel_launches(reset=True)
     ms_per_step, _ = timed(False)
+    stage_ms = {k_: v_ / (a.steps + a.warmup) for k_, v_ in stage_acc.items()}
     launches = ctx.kernel_launches()
     clocks = sampler.stop()
     ms_e2e, d2h = (None, 0) if a.no_e2e else timed(True)
@@ -296,7 +301,7 @@ def main_sharded(a, world, rank, local_rank):
                                                     "h2d_bytes_per_step": int(words.nbytes + word_off.nbytes + lens.nbytes),
                                                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                                                     "returns": "per rank: its shard of (k+1)-mers + counts and k-mers; rank 0: masks + all unitigs"},
-                "roofline": None, "cpu_baseline": None,
+                "roofline": None, "cpu_baseline": None, "stage_ms_rank0": stage_ms,
                 "counts": {k_: int(v_) for k_, v_ in info.items()},
                 "exchange": "2 x NCCL all-to-all (k-mer instances, k-mer candidates), all-reduce of MPHF bit-vectors and masks, gather of unitigs"}
         print(json.dumps(line))

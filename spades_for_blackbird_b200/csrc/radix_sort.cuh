@@ -58,7 +58,11 @@ __device__ __forceinline__ uint32_t rs_composite(const uint64_t *r, const DigitS
 template<int W>
 __device__ __forceinline__ uint32_t rs_digit(const uint64_t *r, const DigitSel &d) {
     if (d.word >= 0) return (uint32_t) (r[d.word] >> d.shift) & 0xFFu;
-    if (d.word == -3) return (rs_composite<W>(r, d) >> d.shift) & 0xFFu;
+    if (d.word == -3) {
+        // a digit that lies entirely inside the value prefix needs no bucket hash (the low pass of every two-pass grouping)
+        if (d.shift + 8 <= d.p) return (uint32_t) (r[0] >> (d.top - d.p + d.shift)) & 0xFFu;
+        return (rs_composite<W>(r, d) >> d.shift) & 0xFFu;
+    }
     uint32_t b = rs_bucket<W>(r, d);
     if (d.word == -2) return (uint32_t) (((uint64_t) b * (uint32_t) d.shift) / d.num_buckets);   // owner of the bucket; shift = #owners
     return (b >> d.shift) & 0xFFu;

@@ -29,8 +29,12 @@
 namespace sb200 {
 
 template<int W> struct SegCfg {
-    static constexpr int CAP = (W <= 2) ? 6144 : 3072;          // records one round of a CTA holds in shared memory (2 CTAs per SM)
-    static constexpr int THREADS = 512;
+#ifndef SEG_CAP_W2
+#define SEG_CAP_W2 6144
+#define SEG_THREADS_W2 512
+#endif
+    static constexpr int CAP = (W <= 2) ? SEG_CAP_W2 : 3072;    // records one round of a CTA holds in shared memory (2 CTAs per SM)
+    static constexpr int THREADS = (W <= 2) ? SEG_THREADS_W2 : 512;
     static constexpr int TARGET = (W <= 2) ? 7168 : 3584;       // average group size aimed for when choosing p
     static constexpr int MAX_DISTINCT = 64;                     // distinct values one segment may hold (two per lane)
 };
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
     uint32_t *cursor = bstart + 257;           // 256 entries
     uint32_t *ucnt = cursor + 256;             // 256 entries
     uint16_t *rdig = reinterpret_cast<uint16_t *>(ucnt + 256);   // 258 entries
-    __shared__ uint32_t s_rounds, s_bad;
+    __shared__ uint32_t s_rounds, s_bad, s_next;
     __shared__ uint32_t s_scan[THREADS / 32 + 1];
 
     const uint32_t b = blockIdx.x;
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
         if (cnt == 0) continue;
         // ---- level 0b: counting sort of this round's records into shared memory --------------------------------------------
         if (threadIdx.x < 256) { cursor[threadIdx.x] = 0; ucnt[threadIdx.x] = 0; }
+        if (threadIdx.x == 0) s_next = d_lo;
         __syncthreads();
         for (uint32_t q0 = 0; q0 < gcnt; q0 += THREADS * 4) {   // four independent loads in flight per thread
             uint64_t in[4][W];
@@ -218,7 +223,12 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
         __syncthreads();
 
         // ---- level 1: one warp per segment: distinct values with multiplicities, in order, written back in place ------------
-        for (uint32_t d = d_lo + warp; d < d_hi; d += NWARPS) {
+        // (segments are handed out dynamically: their cost varies with the number of distinct values)
+        while (true) {
+            uint32_t d = 0;
+            if (lane == 0) d = atomicAdd(&s_next, 1u);
+            d = __shfl_sync(0xffffffffu, d, 0);
+            if (d >= d_hi) break;
             const uint32_t bs = bstart[d] - r_base, m = bstart[d + 1] - bstart[d];
             if (m == 0) continue;
             uint64_t keyA[W], keyB[W];   // distinct values of the segment: up to two per lane; VA / VB = lanes whose slot is taken

@@ -262,10 +262,18 @@ def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=Fa
     if num_buckets % G:
         raise B.Sb200Error("num_buckets (%d) must be a multiple of the number of GPUs (%d)" % (num_buckets, G))
     res = ShardedResult()
+    import time as _time
+    marks = []
+
+    def mark(label):   # stages are blocking on the library's stream; collectives are followed by backend.sync()
+        marks.append((label, _time.perf_counter()))
+    mark("start")
     res.kpomers = count_shard(backend, comm, lambda: backend.extract_partition(reads, k + 1, num_buckets, G), k + 1, num_buckets,
                               True, True)
+    mark("count_kpomers (partition + all-to-all + sort)")
     res.kmers = count_shard(backend, comm, lambda: backend.derive_partition(res.kpomers, num_buckets, G), k, num_buckets,
                             False, False)
+    mark("count_kmers (derive + partition + all-to-all + sort)")
     # 5. global bucket sizes: every bucket is non-empty on exactly one rank
     local_sizes = np.diff(res.kmers.bucket_starts).astype(np.int64)
     sizes = np.sum(np.stack(comm.all_gather_obj(local_sizes)), axis=0).astype(np.uint64)
@@ -277,14 +285,17 @@ def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=Fa
         comm.all_reduce_sum_(bits)
         comm.all_reduce_sum_(ranks)
         backend.sync()
+    mark("mphf (build + all-reduce)")
     # 7. masks
     res.ext = backend.ext_build(res.kpomers, res.kmers, res.index)
     masks = backend.ext_masks(res.ext)
     if G > 1:
         comm.all_reduce_sum_(masks)
         backend.sync()
+    mark("masks (fill + all-reduce)")
     # 8. unitigs of the junctions in my shard
     stats, u = backend.unitigs_local(res.kmers, res.index, res.ext)
+    mark("unitigs (local walks)")
     allstats = np.stack(comm.all_gather_obj(stats.astype(np.int64)))
     res.stats = allstats
     long_chains = int(allstats[:, 1].sum())
@@ -299,6 +310,9 @@ def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=Fa
         gw, go, gl = comm.gather_v(w, gather_to), comm.gather_v(o, gather_to), comm.gather_v(ln, gather_to)
         if comm.rank == gather_to:
             res.gathered = (gw, go, gl)
+        backend.sync()
+        mark("gather")
+    res.stage_ms = {marks[i][0]: 1e3 * (marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))}
     return res
 
 
