@@ -64,6 +64,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->trace = getenv("SB200_TRACE") != nullptr;
         ctx->force_jump_path = getenv("SB200_FORCE_JUMP") != nullptr;
         ctx->no_links = getenv("SB200_NO_LINKS") != nullptr;
+        ctx->no_mask_payload = getenv("SB200_NO_MASK_PAYLOAD") != nullptr;
         ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

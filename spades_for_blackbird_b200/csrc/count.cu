@@ -66,18 +66,32 @@ __global__ void __launch_bounds__(256) extract_reads_kernel(const uint64_t *__re
 
 // kmer_splitters.hpp:159-176: every stored (k+1)-mer x contributes canon(x[0..k)) and canon(x[1..k]) (its RC
 // contributes the same two canonical k-mers, so add_rc only duplicates and is folded away).
+// pshift >= 0: every candidate also carries, in the padding bits [pshift, pshift + 3) of its last word, the InOutMask bit this
+// (k+1)-mer contributes to it — AddOutgoing(next nucleotide) for the prefix k-mer, AddIncoming(previous nucleotide) for the
+// suffix k-mer, mirrored when the k-mer is stored as its reverse complement (kmer_extension_index_builder.hpp:44-59,
+// kmer_extension_index.hpp:92-106) — so that the masks fall out of the k-mer sort without a single MPHF lookup.
 template<int WS, int W>
-__global__ void __launch_bounds__(256) derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, uint64_t *__restrict__ out) {
+__global__ void __launch_bounds__(256) derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, int pshift, uint64_t *__restrict__ out) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t x[WS], a[W], c[W];
     load_rec<WS>(kp, i, x);
+    const uint32_t pnucl = kmer_base(x, 0), nnucl = kmer_base_w<WS>(x, k);
     kmer_subwindow<WS, W>(x, 0, k, a);
-    kmer_canonical<W>(a, k, c);
+    bool minimal = kmer_canonical<W>(a, k, c);
+    if (pshift >= 0) c[W - 1] |= (uint64_t) (minimal ? nnucl : 7u - nnucl) << pshift;
     store_rec<W>(out, 2 * i, c);
     kmer_subwindow<WS, W>(x, 1, k, a);
-    kmer_canonical<W>(a, k, c);
+    minimal = kmer_canonical<W>(a, k, c);
+    if (pshift >= 0) c[W - 1] |= (uint64_t) (minimal ? pnucl + 4u : 3u - pnucl) << pshift;
     store_rec<W>(out, 2 * i + 1, c);
+}
+
+// payload bits off (the LSD fallback sorts whole words)
+template<int W>
+__global__ void strip_payload_kernel(uint64_t *__restrict__ recs, uint64_t n, uint64_t lw_keep) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) recs[i * W + (W - 1)] &= lw_keep;
 }
 
 // ---- unique --------------------------------------------------------------------------------------------------------
@@ -240,11 +254,18 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
 //      chosen so that a group is ~7 K records (radix_sort.cuh)
 //   2. one CTA per group finishes the order in shared memory (counting sort on the next 8 bits, warp-tile deduplication,
 //      ranking inside segments), counts, and packs the unique records; a scan + compaction closes the gaps (segsort.cuh)
+// pshift >= 0 (derived sets only, never together with counts): records carry a mask-bit payload (derive_kernel); the set then
+// comes with masks_file.
 template<int W>
 static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
-                               bool double_palindromes, bool drop_marker) {
+                               bool double_palindromes, bool drop_marker, int pshift = -1) {
     SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
-    if (2 * K < 24) return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+    const uint64_t lw_keep = last_word_mask(K);
+    const bool masks_mode = pshift >= 0 && !want_counts;
+    if (2 * K < 24) {
+        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, inst.p, n, lw_keep);
+        return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+    }
     using Cfg = SegCfg<W>;
     const int top = (W == 1) ? 2 * K : 64;
     int bbits = 0;
@@ -254,11 +275,11 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     while (p < pmax && (double) n / (double) ((uint64_t) B << p) > (double) Cfg::TARGET) ++p;
     const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
     const int dshift = top - p - 8;
-    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top};
+    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top, lw_keep};
 
     DevBuf<uint64_t> scratch(ctx, n * W);
     ctx->trace_point("  instances ready");
-    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker));
+    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker, lw_keep));
     ctx->trace_point("  group passes");
     uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
 
@@ -271,17 +292,22 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     ctx->trace_point("  group bounds");
 
     DevBuf<uint32_t> group_unique(ctx, (uint64_t) n_groups + 1);
-    DevBuf<uint32_t> cnt_full;
-    if (want_counts) cnt_full.alloc(ctx, n);
+    DevBuf<uint32_t> cnt_full;   // multiplicity (or OR-ed mask bits) of the unique record at the same position of `other`
+    if (want_counts || masks_mode) cnt_full.alloc(ctx, n);
     size_t smem = seg_chunk_smem<W>();
     if (want_counts) {
-        auto seg_chunk_kernel_ = group_chunk_kernel<W, true>;
+        auto seg_chunk_kernel_ = group_chunk_kernel<W, 1>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift);
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, 0);
+    } else if (masks_mode) {
+        auto seg_chunk_kernel_ = group_chunk_kernel<W, 2>;
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, pshift);
     } else {
-        auto seg_chunk_kernel_ = group_chunk_kernel<W, false>;
+        auto seg_chunk_kernel_ = group_chunk_kernel<W, 0>;
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift);
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift,
+               lw_keep, 0);
     }
     // per-group unique counts -> offsets; the total sizes the result
     DevBuf<uint32_t> total32(ctx, 1);
@@ -295,6 +321,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         if (src != inst.p) CUDA_CHECK(cudaMemcpyAsync(inst.p, src, n * W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         scratch.release();
         cnt_full.release();
+        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, inst.p, n, lw_keep);   // masks then come from lookups (ext.cu)
         return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
     }
     uint64_t u = u32;
@@ -304,9 +331,13 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     s->data.alloc(ctx, u * W);   // right-sized: the instance-sized ping-pong buffers go back to the allocator
     if (want_counts) {
         s->counts.alloc(ctx, u);
-        LAUNCH(ctx, (seg_compact_kernel<W, true>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p, s->counts.p);
+        LAUNCH(ctx, (seg_compact_kernel<W, 1>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p, s->counts.p);
+    } else if (masks_mode) {
+        s->masks_file.alloc(ctx, u + 4);
+        LAUNCH(ctx, (seg_compact_kernel<W, 2>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p,
+               reinterpret_cast<uint32_t *>(s->masks_file.p));
     } else {
-        LAUNCH(ctx, (seg_compact_kernel<W, false>), n_groups, 256, 0, other, (const uint32_t *) nullptr, ranges.p, group_unique.p, n_groups, u32,
+        LAUNCH(ctx, (seg_compact_kernel<W, 0>), n_groups, 256, 0, other, (const uint32_t *) nullptr, ranges.p, group_unique.p, n_groups, u32,
                s->data.p, (uint32_t *) nullptr);
     }
     if (drop_marker) {
@@ -418,8 +449,11 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
     uint64_t n = kp->size * 2;
     DevBuf<uint64_t> inst(ctx, n * W);
     auto derive_kernel_ = derive_kernel<WS, W>;
-    LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, inst.p);
-    sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false);
+    // three padding bits above the k-mer in its last word carry the mask bit when they exist (every odd k except k = 31 mod 32)
+    const int used = 2 * (k - 32 * (W - 1));
+    const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
+    LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, pshift, inst.p);
+    sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false, pshift);
     s->instances = 0;
     return s;
 }
@@ -481,7 +515,7 @@ static sb200_records *derive_records_w(sb200_ctx *ctx, const sb200_kmers *kp) {
     r->ctx = ctx; r->k = kp->k - 1; r->words = W; r->n = kp->size * 2;
     r->data.alloc(ctx, r->n * W);
     auto derive_kernel_ = derive_kernel<WS, W>;
-    if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, r->data.p);
+    if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, -1, r->data.p);
     return r;
 }
 

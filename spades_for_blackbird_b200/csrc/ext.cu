@@ -24,9 +24,12 @@ __device__ __forceinline__ void mask_and_not(uint8_t *masks, uint64_t idx, uint3
     atomicAnd(reinterpret_cast<unsigned int *>(masks + (idx & ~3ULL)), ~(bits << (8 * (idx & 3))));
 }
 
+// file_masks != nullptr: the masks were OR-ed in file order while the k-mers were sorted (count.cu); they only move to their
+// place in MPHF-index order here.
 template<int W>
 __global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *__restrict__ idx,
-                                                            uint32_t *__restrict__ inv) {
+                                                            uint32_t *__restrict__ inv, const uint8_t *__restrict__ file_masks,
+                                                            uint8_t *__restrict__ masks) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t r[W];
@@ -34,6 +37,7 @@ __global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const ui
     uint32_t id = (uint32_t) mphf_lookup<W>(m, r);
     idx[i] = id;
     if (inv) inv[id] = (uint32_t) i;
+    if (file_masks) masks[id] = file_masks[i];
 }
 
 // Besides the two mask bits, every (k+1)-mer x = y -> z also records the link itself: succ[y] = z and, for the other
@@ -78,10 +82,14 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     SB200_REQUIRE(2 * e->size < 0xFFFFFFF0ull, "more than 2^31 k-mers in one index");
     e->succ_valid = false;   // the direct-walk extraction needs no links; the pointer-jumping path computes them on demand
     MphfDev m = mphf_dev(mphf);
-    LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p);
-    auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
-    LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,
-           e->succ.p);
+    const bool have_masks = !sharded && kmers->masks_file.p != nullptr;
+    LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
+           have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
+    if (!have_masks) {
+        auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
+        LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,
+               e->succ.p);
+    }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // blocking like every entry point: callers all-reduce the masks next
     return e;
 }

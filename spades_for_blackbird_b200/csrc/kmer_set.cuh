@@ -19,6 +19,7 @@ struct sb200_kmers {
     uint64_t instances = 0;              // window instances that were counted (0 for derived sets)
     DevBuf<uint64_t> data;               // size x words, file order: bucket, then array_less
     DevBuf<uint32_t> counts;             // multiplicity per record (empty for derived sets)
+    DevBuf<uint8_t> masks_file;          // derived sets: InOutMask byte per record in FILE order, OR-ed while the set was sorted (may be empty)
     DevBuf<uint64_t> bucket_starts;      // num_buckets + 1 (device)
     std::vector<uint64_t> bucket_starts_host;
 };

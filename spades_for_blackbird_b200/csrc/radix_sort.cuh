@@ -35,11 +35,16 @@ struct DigitSel {
     int marker;   // 1: an all-ones record is the "filtered out" marker and belongs to the last bucket (sorts last)
     int p;        // composite only: prefix bits of the value
     int top;      // composite only: significant bits of word 0 (64, or 2K for one-word records)
+    uint64_t lw_keep = ~0ULL;   // bits of the LAST word that belong to the k-mer (the padding above may carry a payload, count.cu)
 };
 
 template<int W>
 __device__ __forceinline__ uint32_t rs_bucket(const uint64_t *r, const DigitSel &d) {
-    uint32_t b = kmer_bucket<W>(r, d.num_buckets);
+    uint64_t c[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) c[j] = r[j];
+    c[W - 1] &= d.lw_keep;
+    uint32_t b = kmer_bucket<W>(c, d.num_buckets);
     if (d.marker) {
         bool m = true;
 #pragma unroll
@@ -298,9 +303,9 @@ inline std::vector<DigitSel> full_passes(int W, int K, uint32_t num_buckets, boo
 }
 
 // the composite group key (segsort.cuh), least significant byte first: `bits` = bucket bits + p
-inline std::vector<DigitSel> composite_passes(int bits, int p, int top, uint32_t num_buckets, bool marker) {
+inline std::vector<DigitSel> composite_passes(int bits, int p, int top, uint32_t num_buckets, bool marker, uint64_t lw_keep) {
     std::vector<DigitSel> passes;
-    for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{-3, s, num_buckets, marker ? 1 : 0, p, top});
+    for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{-3, s, num_buckets, marker ? 1 : 0, p, top, lw_keep});
     return passes;
 }
 

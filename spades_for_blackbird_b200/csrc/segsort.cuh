@@ -100,7 +100,8 @@ __device__ __forceinline__ uint32_t seg_tag(uint64_t w0, int shift) {
 
 // Moves the unique records every group packed at the front of its own range to their final, contiguous place.
 // One CTA per group; tile_off = exclusive scan of the per-group unique counts.
-template<int W, bool COUNTS>
+// MODE: 0 records only, 1 + multiplicities (uint32), 2 + OR-ed mask payload (out_cnt points to bytes)
+template<int W, int MODE>
 __global__ void __launch_bounds__(256) seg_compact_kernel(const uint64_t *__restrict__ tmp, const uint32_t *__restrict__ tmp_cnt,
                                                          const ChunkRange *__restrict__ ranges, const uint32_t *__restrict__ tile_off,
                                                          uint32_t n_chunks, uint32_t total, uint64_t *__restrict__ out,
@@ -113,17 +114,21 @@ __global__ void __launch_bounds__(256) seg_compact_kernel(const uint64_t *__rest
         uint64_t r[W];
         load_rec<W>(tmp, src + i, r);
         store_rec<W>(out, (uint64_t) o + i, r);
-        if (COUNTS) out_cnt[o + i] = tmp_cnt[src + i];
+        if (MODE == 1) out_cnt[o + i] = tmp_cnt[src + i];
+        if (MODE == 2) reinterpret_cast<uint8_t *>(out_cnt)[o + i] = (uint8_t) tmp_cnt[src + i];
     }
 }
 
 // dshift: the shared-memory digit is bits [dshift, dshift + 8) of word 0; the tag is the 32 bits below dshift.
 constexpr uint32_t GROUP_MAX_ROUNDS_FACTOR = 32;   // groups beyond 32 x CAP records are left to the LSD fallback
 
-template<int W, bool COUNTS>
+// MODE 2: every record carries a 3-bit payload at bit `pshift` of its last word (the InOutMask bit it contributes, count.cu
+// derive_kernel); equal records OR their bits, `lw_keep` strips the payload before any comparison.
+template<int W, int MODE>
 __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const uint64_t *__restrict__ recs, const ChunkRange *__restrict__ ranges,
                                                                         uint32_t *__restrict__ group_unique, uint32_t *__restrict__ fail_flag,
-                                                                        uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, int dshift) {
+                                                                        uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, int dshift,
+                                                                        uint64_t lw_keep, int pshift) {
     constexpr int CAP = SegCfg<W>::CAP, THREADS = SegCfg<W>::THREADS;
     constexpr int NWARPS = THREADS / 32;
     static_assert(THREADS >= 256, "one thread per digit bin");
@@ -242,11 +247,14 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
                 uint64_t r[W];
 #pragma unroll
                 for (int j = 0; j < W; ++j) r[j] = ok ? skey[(size_t) (bs + q) * W + j] : 0ULL;
+                const uint32_t pay = (MODE == 2) ? 1u << ((uint32_t) (r[W - 1] >> pshift) & 7u) : 0u;
+                if (MODE == 2) r[W - 1] &= lw_keep;
                 uint32_t peers = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
                 for (int j = 0; j < W; ++j) peers &= __match_any_sync(0xffffffffu, r[j]);
                 const bool is_rep = ok && ((uint32_t) lane == (uint32_t) (__ffs((int) peers) - 1));
-                const uint32_t mult = (uint32_t) __popc(peers);
+                uint32_t mult = (uint32_t) __popc(peers);
+                if (MODE == 2 && ok) mult = __reduce_or_sync(peers, pay);   // every lane of a peer group is ok and calls with the same mask
                 uint32_t R = __ballot_sync(0xffffffffu, is_rep);
                 if (t0 == 0) {   // first tile: its representatives are the list, each in its own lane
 #pragma unroll
@@ -264,9 +272,9 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
                         const uint32_t hitA = __ballot_sync(0xffffffffu, ((VA >> lane) & 1u) && kmer_eq<W>(keyA, kj));
                         const uint32_t hitB = VB ? __ballot_sync(0xffffffffu, ((VB >> lane) & 1u) && kmer_eq<W>(keyB, kj)) : 0u;
                         if (hitA) {
-                            if (lane == __ffs((int) hitA) - 1) cA += cj;
+                            if (lane == __ffs((int) hitA) - 1) cA = (MODE == 2) ? (cA | cj) : (cA + cj);
                         } else if (hitB) {
-                            if (lane == __ffs((int) hitB) - 1) cB += cj;
+                            if (lane == __ffs((int) hitB) - 1) cB = (MODE == 2) ? (cB | cj) : (cB + cj);
                         } else if (~VA) {
                             const int f = __ffs((int) ~VA) - 1;
                             if (lane == f) {
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
 #pragma unroll
                 for (int j = 0; j < W; ++j) r[j] = skey[(size_t) (bs + i) * W + j];
                 store_rec<W>(out, dst + i, r);
-                if (COUNTS) out_cnt[dst + i] = scnt[bs + i];
+                if (MODE != 0) out_cnt[dst + i] = scnt[bs + i];
             }
         }
         emitted += total_u;
