@@ -411,11 +411,14 @@ def main():
     n_words_out = (unitig_bases + 31 * n_unitigs) / 32.0 * 8     # packed unitig bytes (upper bound on padding)
     alg = {   # algorithmic bytes per STEP of every launch of the kernel
         "extract_reads_kernel<W>": total_bases / 4 + n_inst * W1,
-        "seg_chunk_kernel_": n_inst * W1 + n_kp * (W1 + 4) + 2 * n_kp * W0 + n_km * W0,     # S2 + S4: instances in, unique (+count) out
-        "seg_heads_kernel<W>": n_inst * (W1 + 0.125) + 2 * n_kp * (W0 + 0.125),
+        # S2 + S4: instances in, unique (+ count / + mask byte) out — the shared-memory group sort
+        "seg_chunk_kernel_": n_inst * W1 + n_kp * (W1 + 4) + 2 * n_kp * W0 + n_km * (W0 + 1),
         "derive_kernel_": n_kp * W1 + 2 * n_kp * W0,
         "fill_masks_kernel_": n_kp * W1 + n_km,
-        "index_of_kmers_kernel<W>": n_km * (W0 + 8),
+        "index_of_kmers_kernel<W>": n_km * (W0 + 8 + 2),
+        "links_kernel<W>": n_km * (W0 + 4 + 1 + 8),                # k-mer, idx, mask in; two link words out
+        "walk_measure_links_kernel<W>": 2 * n_km * 4,               # every link word is read once
+        "walk_emit_links_kernel<W>": n_km * 4 + n_words_out,
         "walk_measure_kernel<W>": n_km * (W0 + 1),
         "walk_emit_kernel<W>": n_km * 1 + n_words_out,
         "mphf_level0_kernel<W>": n_km * W0 + n_km * 5.8 / 8,

@@ -210,32 +210,6 @@ __global__ void double_palindromes_kernel(const uint64_t *__restrict__ recs, uin
     if (kmer_eq<W>(x, r)) counts[i] *= 2;
 }
 
-// Generic path for a dirty range of the segmented sort: full LSD sort + unique (+ run lengths) of recs[0..m) into
-// side_recs / side_cnts; returns the number of unique records (host value).
-template<int W>
-static uint32_t lsd_unique_range(sb200_ctx *ctx, uint64_t *recs, uint64_t m, int K, uint32_t B, bool marker, bool want_counts,
-                                 uint64_t *side_recs, uint32_t *side_cnts) {
-    DevBuf<uint64_t> scratch(ctx, m * W);
-    uint64_t *sorted = radix_sort_records<W>(ctx, recs, scratch.p, m, K, B, marker);
-    unsigned tiles = div_up(m, UQ_TILE);
-    DevBuf<uint32_t> tile_cnt(ctx, tiles);
-    DevBuf<uint32_t> total_dev(ctx, 1);
-    LAUNCH(ctx, unique_count_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p);
-    exclusive_scan<uint32_t>(ctx, tile_cnt.p, tiles, total_dev.p);
-    uint32_t u = 0;
-    ctx->fetch(&u, total_dev.p, 4);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    DevBuf<uint32_t> head_pos(ctx, (uint64_t) u + 1);
-    LAUNCH(ctx, unique_write_kernel<W>, tiles, UQ_THREADS, 0, sorted, m, tile_cnt.p, side_recs, head_pos.p);
-    if (want_counts) {
-        uint32_t m32 = (uint32_t) m;
-        CUDA_CHECK(cudaMemcpyAsync(head_pos.p + u, &m32, 4, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(ctx, counts_kernel<W>, div_up(u, 256), 256, 0, head_pos.p, side_recs, (uint64_t) u, K, 0, side_cnts);
-    }
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    return u;
-}
-
 template<int W>
 static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B) {
     s->bucket_starts.alloc(ctx, (uint64_t) B + 1);

@@ -244,7 +244,7 @@ static uint64_t tipclip_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_
     unsigned long long r = 0;
     ctx->fetch(&r, removed.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (r) ext->succ_valid = false;   // a junction that lost a tip may now have a single successor the racing writes did not keep
+    if (r) { ext->succ_valid = false; ext->masks_edited = true; }   // a junction that lost a tip may now have a single successor the racing writes did not keep
     return r;
 }
 

@@ -60,6 +60,7 @@ struct sb200_ext {   // DeBruijnExtensionIndex payload: masks in MPHF-index orde
     DevBuf<uint32_t> idx;       // MPHF index of every k-mer in file order
     DevBuf<uint32_t> inv;       // file position of every MPHF index
     DevBuf<uint32_t> succ;      // successor of every oriented vertex with one outgoing edge (2 * size entries)
+    bool masks_edited = false;  // tip clipping changed the masks: the file-order copy kept by the k-mer set is stale
     bool succ_valid = false;    // false once the masks were edited (tip clipping): links are then recomputed by lookup
 };
 

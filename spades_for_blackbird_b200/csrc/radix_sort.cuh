@@ -22,7 +22,7 @@ constexpr int RS_BINS = 256;
 #define RS_ITEMS_W2 8
 #endif
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 1
+#define RS_MIN_BLOCKS 3   // caps the scatter kernel at 85 registers: 96 registers / 2 CTAs per SM cost 25 % (profiles/r1b)
 #endif
 template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? RS_ITEMS_W2 : 4; };
 

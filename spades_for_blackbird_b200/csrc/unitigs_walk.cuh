@@ -122,10 +122,12 @@ constexpr uint32_t LINK_POS_MASK = 0x0FFFFFFFu;
 
 template<int W>
 __global__ void __launch_bounds__(256) links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k, const uint32_t *__restrict__ idx,
-                                                   const uint32_t *__restrict__ inv, const uint8_t *__restrict__ masks, uint32_t *__restrict__ link) {
+                                                   const uint32_t *__restrict__ inv, const uint8_t *__restrict__ masks,
+                                                   const uint8_t *__restrict__ file_masks /* masks in file order, or nullptr */,
+                                                   uint32_t *__restrict__ link) {
     uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n) return;
-    const uint32_t raw = __ldg(masks + __ldg(idx + (t >> 1)));
+    const uint32_t raw = file_masks ? (uint32_t) __ldg(file_masks + (t >> 1)) : (uint32_t) __ldg(masks + __ldg(idx + (t >> 1)));
     uint32_t out = LINK_JUNCTION;
     if (!mask_is_junction(raw)) {
         const int strand = (int) (t & 1);
@@ -329,7 +331,9 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
         if (use_links) {
             link.alloc(ctx, 2 * n);
             efirst.alloc(ctx, (uint64_t) n_e + 1);
-            LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, link.p);
+            // masks in file order (a coalesced read) are valid as long as tip clipping has not edited the index-order array
+            const uint8_t *fm = (kmers->masks_file.p && !ext->masks_edited) ? kmers->masks_file.p : nullptr;
+            LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, fm, link.p);
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
                    kflag.p, ewords.p, totals.p);
         } else {
