@@ -274,3 +274,58 @@ def test_low_complexity_reads_overflow_a_segment(ctx):
     assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
     assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
     assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+
+
+def test_baseline_config2_full_size(monkeypatch):
+    """BASELINE configs[1] at full size (4.6 Mbp genome, 2x150 at 100x, k = 55, 80 buckets: 291 M (k+1)-mer instances) — far
+    beyond what the oracle does in seconds, so: size-independent properties of the tables, and the two independent
+    implementations of the graph stage must agree (masks OR-ed inside the sort + link-table walks  vs.  masks by MPHF lookups
+    + lookup walks)."""
+    import hashlib
+    k, nb = 55, 80
+    words, word_off, lens = synth.isolate_config()
+    instances = int((lens.astype(np.int64) - k).clip(min=0).sum())
+
+    def run(ctx):
+        streams = B.ReadStreams(ctx, words, word_off, lens)
+        index = B.DeBruijnExtensionIndex(ctx, k)
+        kp = B.DeBruijnExtensionIndexBuilder().BuildExtensionIndexFromStream(index, streams, num_buckets=nb)
+        w, off, ln = B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops(packed=True)
+        return streams, index, kp, (w, off, ln)
+
+    ctx1 = B.Context(0)
+    try:
+        streams, index, kp, (w, off, ln) = run(ctx1)
+        assert kp.instances == instances
+        cnt = kp.counts()
+        assert int(cnt.astype(np.int64).sum()) == instances                                   # every window counted exactly once
+        for table in (kp, index.kmers):
+            rec = table.final_kmers()
+            st = table.bucket_starts
+            assert st[0] == 0 and st[-1] == len(rec) and np.all(np.diff(st.astype(np.int64)) > 0)
+            inc = (rec[1:, 0] > rec[:-1, 0]) | ((rec[1:, 0] == rec[:-1, 0]) & (rec[1:, 1] > rec[:-1, 1]))
+            inc[st[1:-1].astype(np.int64) - 1] = True                                         # order restarts at a bucket boundary
+            assert inc.all()                                                                  # strictly increasing = sorted + unique
+            del rec, inc
+        idx = index.idx()
+        assert len(idx) == index.size() and np.array_equal(np.sort(idx), np.arange(index.size(), dtype=idx.dtype))   # minimal perfect
+        masks = index.data()
+        pop = np.array([bin(m).count("1") for m in range(256)], dtype=np.int64)
+        assert int(pop[masks].sum()) == 2 * kp.total_kmers()                                  # every (k+1)-mer sets exactly two bits
+        edges = int((ln.astype(np.int64) - k).sum())
+        assert kp.total_kmers() <= edges <= int(1.001 * kp.total_kmers())                     # unitigs partition the edges
+        digest = [hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest() for a in (masks, w, off, ln)]
+        n_unitigs = len(ln)
+        index.free(); kp.free(); streams.free()
+    finally:
+        ctx1.close()
+    monkeypatch.setenv("SB200_NO_MASK_PAYLOAD", "1")
+    monkeypatch.setenv("SB200_NO_LINKS", "1")
+    ctx2 = B.Context(0)
+    try:
+        streams, index, kp, (w, off, ln) = run(ctx2)
+        assert len(ln) == n_unitigs
+        assert [hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest() for a in (index.data(), w, off, ln)] == digest
+        index.free(); kp.free(); streams.free()
+    finally:
+        ctx2.close()
