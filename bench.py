@@ -266,6 +266,7 @@ def main_sharded(a, world, rank, local_rank):
     def timed(e2e):
         for _ in range(a.warmup):
             step(e2e)
+        stage_acc.clear()
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,7 +287,7 @@ def main_sharded(a, world, rank, local_rank):
     sampler.start()
     ctx.kernel_launches(reset=True)
     ms_per_step, _ = timed(False)
-    stage_ms = {k_: v_ / (a.steps + a.warmup) for k_, v_ in stage_acc.items()}
+    stage_ms = {k_: v_ / a.steps for k_, v_ in stage_acc.items()}
     launches = ctx.kernel_launches()
     clocks = sampler.stop()
     ms_e2e, d2h = (None, 0) if a.no_e2e else timed(True)

@@ -131,11 +131,11 @@ typedef struct sb200_records sb200_records;   /* unsorted k-mer instances on the
 int  sb200_records_extract(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, sb200_records **out);
 int  sb200_records_derive(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_records **out);
 int  sb200_records_partition(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, unsigned n_owners, uint64_t *counts_out /* n_owners */);
-int  sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int double_palindromes, int marker, sb200_records **out);
+int  sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int flags /* = sb200_records_flags of the senders */, sb200_records **out);
 uint64_t sb200_records_size(const sb200_records *r);
 unsigned sb200_records_words(const sb200_records *r);
 unsigned sb200_records_k(const sb200_records *r);
-int  sb200_records_flags(const sb200_records *r);        /* bit 0: double_palindromes, bit 1: marker */
+int  sb200_records_flags(const sb200_records *r);        /* bit 0: double_palindromes, bit 1: marker, bit 2: mask-bit payload in the padding */
 uint64_t *sb200_records_device(sb200_records *r);        /* device pointer to n * words uint64 */
 void sb200_records_free(sb200_records *r);
 int  sb200_count_records(sb200_ctx *ctx, sb200_records *r /* consumed */, unsigned num_buckets, int want_counts, sb200_kmers **out);

@@ -489,7 +489,10 @@ static sb200_records *derive_records_w(sb200_ctx *ctx, const sb200_kmers *kp) {
     r->ctx = ctx; r->k = kp->k - 1; r->words = W; r->n = kp->size * 2;
     r->data.alloc(ctx, r->n * W);
     auto derive_kernel_ = derive_kernel<WS, W>;
-    if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, -1, r->data.p);
+    const int used = 2 * ((int) r->k - 32 * (W - 1));
+    const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
+    r->mask_payload = pshift >= 0;
+    if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, pshift, r->data.p);
     return r;
 }
 
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t *__rest
 
 template<int W>
 static void partition_records_w(sb200_ctx *ctx, sb200_records *r, uint32_t B, uint32_t n_parts, uint64_t *counts_out) {
-    DigitSel sel{-2, (int) n_parts, B, r->marker ? 1 : 0};
+    DigitSel sel{-2, (int) n_parts, B, r->marker ? 1 : 0, 0, 0, last_word_mask((int) r->k)};   // the owner hash ignores a payload
     DevBuf<unsigned long long> counts(ctx, RS_BINS);
     counts.zero();
     if (r->n) {
@@ -553,11 +556,13 @@ sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int wan
     SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
     SB200_REQUIRE(r->n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     sb200_kmers *s;
+    SB200_REQUIRE(!(r->mask_payload && want_counts), "records with a mask payload cannot be counted");
+    const int pshift = r->mask_payload ? 2 * ((int) r->k - 32 * ((int) r->words - 1)) : -1;
     switch (r->words) {
-        case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
-        case 2: s = finish_set<2>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
-        case 3: s = finish_set<3>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
-        default: s = finish_set<4>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker); break;
+        case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
+        case 2: s = finish_set<2>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
+        case 3: s = finish_set<3>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
+        default: s = finish_set<4>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
     }
     if (!want_counts) s->instances = 0;
     r->n = 0;

@@ -82,7 +82,9 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     SB200_REQUIRE(2 * e->size < 0xFFFFFFF0ull, "more than 2^31 k-mers in one index");
     e->succ_valid = false;   // the direct-walk extraction needs no links; the pointer-jumping path computes them on demand
     MphfDev m = mphf_dev(mphf);
-    const bool have_masks = !sharded && kmers->masks_file.p != nullptr;
+    // (a shard's masks are complete too — every candidate of a k-mer met at its owner — and land in this GPU's slice of the
+    // zeroed full-size array; the caller's sum over the GPUs assembles the rest)
+    const bool have_masks = kmers->masks_file.p != nullptr;
     LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
            have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
     if (!have_masks) {

@@ -30,6 +30,7 @@ struct sb200_records {   // unsorted k-mer instances / candidates on their way t
     uint64_t n = 0;
     bool double_palindromes = false;   // canonical fwd+RC counting mode: a self-reverse-complement record counts twice
     bool marker = false;               // canonical forward-only mode: all-ones records are "filtered out" markers
+    bool mask_payload = false;         // derived k-mer candidates: 3 padding bits above the k-mer carry the InOutMask bit (count.cu)
     DevBuf<uint64_t> data;
 };
 

@@ -47,13 +47,13 @@ int sb200_records_derive(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_recor
 int sb200_records_partition(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, unsigned n_owners, uint64_t *counts_out) {
     return guarded(ctx, [&] { sb200::partition_records(ctx, r, num_buckets, n_owners, counts_out); });
 }
-int sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int double_palindromes, int marker, sb200_records **out) {
+int sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int flags, sb200_records **out) {
     *out = nullptr;
     return guarded(ctx, [&] {
         SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
         sb200_records *r = new sb200_records();
         r->ctx = ctx; r->k = K; r->words = (K + 31) / 32; r->n = n;
-        r->double_palindromes = double_palindromes != 0; r->marker = marker != 0;
+        r->double_palindromes = (flags & 1) != 0; r->marker = (flags & 2) != 0; r->mask_payload = (flags & 4) != 0;
         r->data.alloc(ctx, n * r->words);
         *out = r;
     });
@@ -61,7 +61,7 @@ int sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int double_palin
 uint64_t sb200_records_size(const sb200_records *r) { return r->n; }
 unsigned sb200_records_words(const sb200_records *r) { return r->words; }
 unsigned sb200_records_k(const sb200_records *r) { return r->k; }
-int sb200_records_flags(const sb200_records *r) { return (r->double_palindromes ? 1 : 0) | (r->marker ? 2 : 0); }
+int sb200_records_flags(const sb200_records *r) { return (r->double_palindromes ? 1 : 0) | (r->marker ? 2 : 0) | (r->mask_payload ? 4 : 0); }
 uint64_t *sb200_records_device(sb200_records *r) { return r->data.p; }
 void sb200_records_free(sb200_records *r) {
     if (!r) return;

@@ -50,44 +50,95 @@ __global__ void __launch_bounds__(256) edge_list_kernel(uint64_t n, const uint32
     }
 }
 
+// Walks have very different lengths (1 .. 1000 steps): with one walk per thread a warp runs until its longest walk ends and
+// most lanes idle (ncu, profiles/r1a: 1850 thread slots per lookup step).  All walk kernels are therefore PERSISTENT: a lane
+// that finishes claims the next work item at once (one warp-aggregated atomic per refill), so every lane keeps a walk — and,
+// for the link walks, a DRAM read — in flight.  Results are indexed by the work item, so the output order is unchanged.
+constexpr uint32_t NO_WORK = 0xFFFFFFFFu;
+constexpr uint32_t WORK_CHUNK = 256;   // items a warp takes from the global queue at a time
+// Hands the next work items to the lanes that need one.  A warp draws chunks of WORK_CHUNK items from the global counter (one
+// atomic per chunk: a per-refill atomic on a single address serialised the link walks, 3.6 -> 9.6 ms) and serves its lanes from
+// the chunk; [cnext, cend) is the warp-uniform rest of the current chunk.
+__device__ __forceinline__ uint32_t claim_work(bool need, uint32_t *__restrict__ counter, uint32_t n, uint32_t &cnext, uint32_t &cend) {
+    const uint32_t m = __ballot_sync(0xffffffffu, need);
+    if (!m) return NO_WORK;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (uint32_t) __popc(m & ((1u << lane) - 1u)), cnt = (uint32_t) __popc(m);
+    const uint32_t avail = cend - cnext;
+    uint32_t item = NO_WORK;
+    if (rank < avail) item = cnext + rank;
+    if (cnt > avail) {   // warp-uniform: the chunk runs out
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, WORK_CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (rank >= avail) item = base + (rank - avail);
+        cnext = base + (cnt - avail);
+        cend = base + WORK_CHUNK;
+    } else {
+        cnext += cnt;
+    }
+    return (need && item < n) ? item : NO_WORK;
+}
+
 template<int W>
 __global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                           uint32_t n_e, const uint8_t *__restrict__ masks, uint32_t *__restrict__ elen,
                                                           uint32_t *__restrict__ kflag, unsigned long long *__restrict__ ewords,
-                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases */) {
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases */,
+                                                          uint32_t *__restrict__ work) {
     unsigned long long chain_nodes = 0, kept_bases = 0;
     uint32_t too_long = 0;
-    if (e < n_e) {
-        uint32_t code = elist[e];
-        uint32_t t = code >> 2, c = code & 3u;
-        uint64_t x[W], y[W], z[W];
-        oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
-        kmer_shl<W>(x, k, c, y);
-        uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
-        uint32_t mk = walk_mask<W>(m, masks, y, k);
-        uint32_t nn = 1;
-        while (!mask_is_junction(mk)) {
-            if (nn > WALK_LIMIT) { too_long = 1; break; }
-            prev_first = kmer_base(y, 0);
-            kmer_shl<W>(y, k, nib_next(mk & 15u), z);
+    bool active = false, exhausted = false;
+    uint32_t cnext = 0, cend = 0;
+    uint32_t e = 0, c = 0, nn = 0, prev_first = 0;
+    uint64_t x[W], y[W];
 #pragma unroll
-            for (int q = 0; q < W; ++q) y[q] = z[q];
-            mk = walk_mask<W>(m, masks, y, k);
-            ++nn;
+    for (int q = 0; q < W; ++q) { x[q] = 0; y[q] = 0; }
+    while (true) {
+        const bool need = !active && !exhausted;
+        const uint32_t item = claim_work(need, work, n_e, cnext, cend);
+        if (need) {
+            if (item == NO_WORK) exhausted = true;
+            else {
+                e = item;
+                const uint32_t code = elist[e];
+                const uint32_t t = code >> 2;
+                c = code & 3u;
+                oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+                kmer_shl<W>(x, k, c, y);
+                prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
+                nn = 1;
+                active = true;
+            }
         }
-        uint32_t len = 0;
-        if (!too_long) {
-            chain_nodes = nn - 1;
-            uint64_t rcn[W];
-            kmer_rc<W>(y, k, rcn);
-            int cmp = kmer_lex_cmp<W>(x, rcn);
-            bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
-            if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            const uint32_t mk = walk_mask<W>(m, masks, y, k);
+            const bool junction = mask_is_junction(mk);
+            if (junction || nn > WALK_LIMIT) {
+                uint32_t len = 0;
+                if (!junction) too_long += 1;
+                else {
+                    chain_nodes += nn - 1;
+                    uint64_t rcn[W];
+                    kmer_rc<W>(y, k, rcn);
+                    const int cmp = kmer_lex_cmp<W>(x, rcn);
+                    const bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
+                    if (keep) { len = nn; kept_bases += (unsigned long long) k + nn; }
+                }
+                elen[e] = len;
+                kflag[e] = len ? 1u : 0u;
+                ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
+                active = false;
+            } else {
+                uint64_t z[W];
+                prev_first = kmer_base(y, 0);
+                kmer_shl<W>(y, k, nib_next(mk & 15u), z);
+#pragma unroll
+                for (int q = 0; q < W; ++q) y[q] = z[q];
+                ++nn;
+            }
         }
-        elen[e] = len;
-        kflag[e] = len ? 1u : 0u;
-        ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
     }
     // one atomic per warp and counter
 #pragma unroll
@@ -142,6 +193,8 @@ __global__ void __launch_bounds__(256) links_kernel(MphfDev m, const uint64_t *_
     link[t] = out;
 }
 
+// (the link walks stay one thread per start edge: they are bound by random DRAM reads, and the persistent form's extra
+// registers and refill logic cost more than the idle lanes it removes: 3.6 + 1.5 ms against 4.6 + 1.8 ms)
 template<int W>
 __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                                 uint32_t n_e, const uint32_t *__restrict__ inv, const uint32_t *__restrict__ link,
@@ -242,43 +295,64 @@ __global__ void __launch_bounds__(256) walk_emit_kernel(MphfDev m, const uint64_
                                                        const uint32_t *__restrict__ klist, uint32_t n_kept, const uint8_t *__restrict__ masks,
                                                        const uint32_t *__restrict__ elen, const unsigned long long *__restrict__ ewords_scan,
                                                        uint32_t *__restrict__ seq_len, uint64_t *__restrict__ seq_word_off,
-                                                       uint64_t *__restrict__ out_words) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_kept) return;
-    uint32_t e = klist[q];
-    uint32_t code = elist[e];
-    uint32_t t = code >> 2, c = code & 3u;
-    const uint32_t nn = elen[e];
-    const unsigned long long woff = ewords_scan[e];
-    const uint32_t L = (uint32_t) k + nn;
-    seq_len[q] = L;
-    seq_word_off[q] = woff;
-    uint64_t x[W], y[W], z[W];
-    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
-    // the first k bases are the junction's k-mer: whole words of x, then the partial (last) word continues in `acc`
-    uint32_t pos = 0;
+                                                       uint64_t *__restrict__ out_words, uint32_t *__restrict__ work) {
+    bool active = false, exhausted = false;
+    uint32_t cnext = 0, cend = 0;
+    uint32_t left = 0, pos = 0;   // left = lookup steps still to take
     uint64_t acc = 0;
+    unsigned long long woff = 0;
+    uint64_t y[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-        if ((w + 1) * 32 <= k) { out_words[woff + w] = x[w]; pos = (w + 1) * 32; }
-    }
-    if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // padding bits of x are zero
-    auto push = [&](uint32_t base) {
-        acc |= (uint64_t) base << (2 * (pos & 31));
-        ++pos;
-        if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
-    };
-    push(c);
-    kmer_shl<W>(x, k, c, y);
-    for (uint32_t s = 1; s < nn; ++s) {
-        uint32_t mk = walk_mask<W>(m, masks, y, k);
-        uint32_t b = nib_next(mk & 15u);
-        push(b);
-        kmer_shl<W>(y, k, b, z);
+    for (int w = 0; w < W; ++w) y[w] = 0;
+    while (true) {
+        const bool need = !active && !exhausted;
+        const uint32_t q = claim_work(need, work, n_kept, cnext, cend);
+        if (need) {
+            if (q == NO_WORK) exhausted = true;
+            else {
+                const uint32_t e = klist[q];
+                const uint32_t code = elist[e];
+                const uint32_t t = code >> 2, c = code & 3u;
+                const uint32_t nn = elen[e];
+                woff = ewords_scan[e];
+                seq_len[q] = (uint32_t) k + nn;
+                seq_word_off[q] = woff;
+                uint64_t x[W];
+                oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+                pos = 0;
+                acc = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) y[w] = z[w];
+                for (int w = 0; w < W; ++w) {
+                    if ((w + 1) * 32 <= k) { out_words[woff + w] = x[w]; pos = (w + 1) * 32; }
+                }
+                if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // padding bits of x are zero
+                acc |= (uint64_t) c << (2 * (pos & 31));
+                ++pos;
+                if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
+                kmer_shl<W>(x, k, c, y);
+                left = nn - 1;
+                active = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            if (left == 0) {
+                if (pos & 31) out_words[woff + (pos >> 5)] = acc;
+                active = false;
+            } else {
+                const uint32_t mk = walk_mask<W>(m, masks, y, k);
+                const uint32_t b = nib_next(mk & 15u);
+                acc |= (uint64_t) b << (2 * (pos & 31));
+                ++pos;
+                if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
+                uint64_t z[W];
+                kmer_shl<W>(y, k, b, z);
+#pragma unroll
+                for (int w = 0; w < W; ++w) y[w] = z[w];
+                --left;
+            }
+        }
     }
-    if (pos & 31) out_words[woff + (pos >> 5)] = acc;
 }
 
 __global__ void __launch_bounds__(256) count_nonjunction_kernel(const uint8_t *__restrict__ masks, uint64_t n, unsigned long long *__restrict__ total) {
@@ -314,6 +388,9 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     DevBuf<uint32_t> tot32(ctx, 2);
     DevBuf<unsigned long long> totals(ctx, 6);   // [0] chain vertices seen [1] long chains [2] total words [3] non-junction k-mers [4] bases
     totals.zero();
+    DevBuf<uint32_t> work(ctx, 4);               // work-queue heads of the persistent walk kernels: [0] measure, [1] emit
+    work.zero();
+    const unsigned walk_grid = (unsigned) ctx->num_sms * 6;
     if (nt) LAUNCH(ctx, junction_degree_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p);
     exclusive_scan<uint32_t>(ctx, deg.p, nt, tot32.p);
     ctx->fetch(&st.n_edges, tot32.p, 4);
@@ -337,7 +414,8 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
                    kflag.p, ewords.p, totals.p);
         } else {
-            LAUNCH(ctx, walk_measure_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p);
+            LAUNCH(ctx, walk_measure_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p,
+                   work.p);
         }
     }
     if (check_loops) LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, n, totals.p + 3);
@@ -364,8 +442,8 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
             LAUNCH(ctx, walk_emit_links_kernel<W>, div_up(st.n_kept, 256), 256, 0, kbase, k, elist.p, klist.p, st.n_kept, link.p, elen.p, efirst.p,
                    ewords.p, out->len.p, out->word_off.p, out->words.p);
         else
-            LAUNCH(ctx, walk_emit_kernel<W>, div_up(st.n_kept, 256), 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
-                   out->len.p, out->word_off.p, out->words.p);
+            LAUNCH(ctx, walk_emit_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
+                   out->len.p, out->word_off.p, out->words.p, work.p + 1);
     }
     uint64_t tw = st.words;
     CUDA_CHECK(cudaMemcpyAsync(out->word_off.p + st.n_kept, &tw, 8, cudaMemcpyHostToDevice, ctx->stream));

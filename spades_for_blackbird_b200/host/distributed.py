@@ -178,10 +178,13 @@ class GpuShardBackend:
     def free_records(self, rec):
         self.lib.sb200_records_free(rec)
 
-    def count(self, recv, n, K, num_buckets, want_counts, double_palindromes):
-        """recv: int64 CUDA tensor with n records -> this rank's shard as a KMerDiskStorage"""
+    def records_flags(self, rec):
+        return int(self.lib.sb200_records_flags(rec))
+
+    def count(self, recv, n, K, num_buckets, want_counts, flags):
+        """recv: int64 CUDA tensor with n records (flags = records_flags of the senders) -> this rank's shard as a KMerDiskStorage"""
         rec = B.vp()
-        self.ctx.check(self.lib.sb200_records_alloc(self.ctx.h, n, K, int(double_palindromes), 0, C.byref(rec)))
+        self.ctx.check(self.lib.sb200_records_alloc(self.ctx.h, n, K, int(flags), C.byref(rec)))
         w = self.lib.sb200_records_words(rec)
         if n:
             cuda_view(self.lib.sb200_records_device(rec), n * w, "<i8", self.device).copy_(recv)
@@ -250,10 +253,11 @@ class ShardedResult:
 def count_shard(backend, comm, make_records, K, num_buckets, want_counts, double_palindromes):
     """steps 1-2 / 3-4: group by owner, all-to-all, sort/dedup/count the received records"""
     rec, view, counts, width = make_records()
+    flags = backend.records_flags(rec)   # the same on every rank: double palindromes / marker / mask payload
     recv, recv_counts = comm.all_to_all_v(view, counts, width)
     backend.sync()   # the collective ran on torch's / NCCL's stream; the library works on its own
     backend.free_records(rec)
-    return backend.count(recv, sum(recv_counts), K, num_buckets, want_counts, double_palindromes)
+    return backend.count(recv, sum(recv_counts), K, num_buckets, want_counts, flags)
 
 
 def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=False):

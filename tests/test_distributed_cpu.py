@@ -47,14 +47,17 @@ class CpuShardBackend:
         a = np.array(words, dtype=np.uint64)
         return self.O.lib().ora_bucket(a.ctypes.data_as(self.O.u64p), len(words), B)
 
-    def _group(self, recs, W, B, G):
+    def records_flags(self, rec):
+        return rec["flags"]
+
+    def _group(self, recs, W, B, G, flags=0):
         import torch
         owners = [self._bucket(r, B) * G // B for r in recs]
         order = sorted(range(len(recs)), key=lambda i: owners[i])     # stable
         flat = [w for i in order for w in recs[i]]
         counts = [owners.count(g) for g in range(G)]
         t = torch.from_numpy(np.array(flat, dtype=np.uint64).view(np.int64).copy()) if flat else torch.empty(0, dtype=torch.int64)
-        return None, t, counts, W
+        return {"flags": flags}, t, counts, W
 
     def extract_partition(self, reads, K, B, G):
         recs = []
@@ -62,7 +65,7 @@ class CpuShardBackend:
             for p in range(len(r) - K + 1):
                 x = r[p:p + K]
                 recs.append(_pack(min(x, _rc(x))))
-        return self._group(recs, (K + 31) // 32, B, G)
+        return self._group(recs, (K + 31) // 32, B, G, flags=1)   # fwd+RC canonical counting: palindromes count twice
 
     def derive_partition(self, kp, B, G):
         K = kp.K
@@ -72,7 +75,8 @@ class CpuShardBackend:
                 recs.append(_pack(min(x, _rc(x))))
         return self._group(recs, (K - 1 + 31) // 32, B, G)
 
-    def count(self, recv, n, K, B, want_counts, double_palindromes):
+    def count(self, recv, n, K, B, want_counts, flags):
+        double_palindromes = bool(flags & 1)
         W = (K + 31) // 32
         a = recv.numpy().view(np.uint64).reshape(n, W)
         keyed = {}
