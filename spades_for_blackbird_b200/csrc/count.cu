@@ -508,37 +508,33 @@ sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp) {
     return derive_records_w<4, 4>(ctx, kp);
 }
 
-template<int W>
-__global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t *__restrict__ recs, uint64_t n, DigitSel sel, unsigned long long *__restrict__ counts) {
-    __shared__ uint32_t sh[RS_BINS];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
-        uint64_t r[W];
-        load_rec<W>(recs, i, r);
-        atomicAdd(&sh[rs_digit<W>(r, sel)], 1u);
-    }
-    __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long) sh[threadIdx.x]);
+// first position of every owner's group = the scanned histogram matrix at (owner, tile 0)
+__global__ void owner_starts_kernel(const uint32_t *__restrict__ offsets, uint32_t num_tiles, uint32_t n_parts, uint32_t *__restrict__ starts) {
+    uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < n_parts) starts[o] = offsets[(uint64_t) o * num_tiles];
 }
 
+// One stable counting pass whose digit is the owner id; the per-owner counts fall out of the pass's own scanned histogram.
 template<int W>
 static void partition_records_w(sb200_ctx *ctx, sb200_records *r, uint32_t B, uint32_t n_parts, uint64_t *counts_out) {
     DigitSel sel{-2, (int) n_parts, B, r->marker ? 1 : 0, 0, 0, last_word_mask((int) r->k)};   // the owner hash ignores a payload
-    DevBuf<unsigned long long> counts(ctx, RS_BINS);
-    counts.zero();
-    if (r->n) {
-        LAUNCH(ctx, owner_count_kernel<W>, (unsigned) std::min<uint64_t>(div_up(r->n, 256), (uint64_t) ctx->num_sms * 16), 256, 0, r->data.p, r->n, sel,
-               counts.p);
-        DevBuf<uint64_t> scratch(ctx, r->n * W);
-        std::vector<DigitSel> passes{sel};
-        uint64_t *res = radix_sort_passes<W>(ctx, r->data.p, scratch.p, r->n, passes);
-        if (res == scratch.p) std::swap(r->data, scratch);   // keep the buffer that holds the grouped records
-    }
-    std::vector<unsigned long long> h(RS_BINS);
-    ctx->fetch(h.data(), counts.p, RS_BINS * 8);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t p = 0; p < n_parts; ++p) counts_out[p] = h[p];
+    for (uint32_t p = 0; p < n_parts; ++p) counts_out[p] = 0;
+    if (r->n == 0) return;
+    const uint64_t n = r->n;
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    constexpr int ITEMS = RsItems<W>::value;
+    const uint32_t num_tiles = div_up(n, RS_THREADS * ITEMS);
+    DevBuf<uint32_t> hist(ctx, (uint64_t) RS_BINS * num_tiles);
+    DevBuf<uint64_t> scratch(ctx, n * W);
+    DevBuf<uint32_t> starts(ctx, RS_BINS);
+    LAUNCH(ctx, rs_hist_kernel<W>, num_tiles, RS_THREADS, 0, r->data.p, n, sel, hist.p, num_tiles);
+    exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) RS_BINS * num_tiles, nullptr);
+    LAUNCH(ctx, owner_starts_kernel, 1, RS_BINS, 0, hist.p, num_tiles, n_parts, starts.p);
+    LAUNCH(ctx, rs_scatter_kernel<W>, num_tiles, RS_THREADS, 0, r->data.p, scratch.p, n, sel, hist.p, num_tiles);
+    std::swap(r->data, scratch);   // keep the buffer that holds the grouped records
+    std::vector<uint32_t> h(n_parts);
+    ctx->fetch(h.data(), starts.p, (size_t) n_parts * 4);
+    for (uint32_t p = 0; p < n_parts; ++p) counts_out[p] = (p + 1 < n_parts ? (uint64_t) h[p + 1] : n) - h[p];
 }
 
 void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out) {

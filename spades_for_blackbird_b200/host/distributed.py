@@ -43,12 +43,14 @@ class TorchComm:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
-    def all_to_all_v(self, send, send_counts, width):
-        """send: 1-D int64 tensor holding sum(send_counts) records of `width` words, grouped by destination."""
+    def all_to_all_v(self, send, send_counts, width, alloc=None):
+        """send: 1-D int64 tensor holding sum(send_counts) records of `width` words, grouped by destination.  alloc(n) may
+        provide the receive buffer for n records (e.g. the library's own record array: no staging copy)."""
         import torch
         counts = self.all_gather_obj([int(c) for c in send_counts])
         recv_counts = [counts[src][self.rank] for src in range(self.size)]
-        recv = torch.empty(sum(recv_counts) * width, dtype=torch.int64, device=send.device)
+        n = sum(recv_counts)
+        recv = alloc(n) if alloc else torch.empty(n * width, dtype=torch.int64, device=send.device)
         self.dist.all_to_all_single(recv, send, [c * width for c in recv_counts], [int(c) * width for c in send_counts],
                                     group=self.group)
         return recv, recv_counts
@@ -98,13 +100,22 @@ class LocalComm:
     def all_gather_obj(self, obj):
         return self._exchange(obj)
 
-    def all_to_all_v(self, send, send_counts, width):
+    def all_to_all_v(self, send, send_counts, width, alloc=None):
         import torch
         offs = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64) * width
         parts = [send[int(offs[d]):int(offs[d + 1])] for d in range(self.size)]
         allparts = self._exchange(parts)
         mine = [allparts[src][self.rank] for src in range(self.size)]
-        recv = torch.cat([p.clone() for p in mine]) if mine else send[:0]
+        if alloc:
+            recv = alloc(sum(int(p.numel()) for p in mine) // width)
+            o = 0
+            for p in mine:
+                recv[o:o + p.numel()].copy_(p)
+                o += p.numel()
+            if recv.is_cuda:
+                torch.cuda.synchronize(recv.device)
+        else:
+            recv = torch.cat([p.clone() for p in mine]) if mine else send[:0]
         self.sh.barrier.wait()   # senders keep their buffers alive until everyone has copied
         return recv, [int(p.numel()) // width for p in mine]
 
@@ -181,6 +192,21 @@ class GpuShardBackend:
     def records_flags(self, rec):
         return int(self.lib.sb200_records_flags(rec))
 
+    def alloc_records(self, n, K, flags):
+        """empty record array for n received records + its int64 view (the all-to-all writes straight into it)"""
+        rec = B.vp()
+        self.ctx.check(self.lib.sb200_records_alloc(self.ctx.h, n, K, int(flags), C.byref(rec)))
+        w = self.lib.sb200_records_words(rec)
+        return rec, cuda_view(self.lib.sb200_records_device(rec), max(n * w, 1), "<i8", self.device)[:n * w]
+
+    def count_records(self, rec, num_buckets, want_counts):
+        h = B.vp()
+        try:
+            self.ctx.check(self.lib.sb200_count_records(self.ctx.h, rec, num_buckets, int(want_counts), C.byref(h)))
+        finally:
+            self.lib.sb200_records_free(rec)
+        return B.KMerDiskStorage(self.ctx, h)
+
     def count(self, recv, n, K, num_buckets, want_counts, flags):
         """recv: int64 CUDA tensor with n records (flags = records_flags of the senders) -> this rank's shard as a KMerDiskStorage"""
         rec = B.vp()
@@ -254,8 +280,18 @@ def count_shard(backend, comm, make_records, K, num_buckets, want_counts, double
     """steps 1-2 / 3-4: group by owner, all-to-all, sort/dedup/count the received records"""
     rec, view, counts, width = make_records()
     flags = backend.records_flags(rec)   # the same on every rank: double palindromes / marker / mask payload
+    if hasattr(backend, "alloc_records"):   # receive straight into the library's record array
+        holder = {}
+
+        def alloc(n):
+            holder["rec"], v = backend.alloc_records(n, K, flags)
+            return v
+        comm.all_to_all_v(view, counts, width, alloc=alloc)
+        backend.sync()   # the collective ran on torch's / NCCL's stream; the library works on its own
+        backend.free_records(rec)
+        return backend.count_records(holder["rec"], num_buckets, want_counts)
     recv, recv_counts = comm.all_to_all_v(view, counts, width)
-    backend.sync()   # the collective ran on torch's / NCCL's stream; the library works on its own
+    backend.sync()
     backend.free_records(rec)
     return backend.count(recv, sum(recv_counts), K, num_buckets, want_counts, flags)
 
