@@ -18,6 +18,8 @@
 //   debruijn_graph::EarlyTipClipperProcessor         assembly_graph/construction/early_simplification.hpp:37-160
 //   debruijn_graph::UnbranchingPathExtractor         assembly_graph/construction/debruijn_graph_constructor.hpp:182-388
 //   utils::CoverageHashMapBuilder                    utils/ph_map/coverage_hash_map_builder.hpp:15-54
+//   debruijn_graph::FastGraphFromSequencesConstructor assembly_graph/construction/debruijn_graph_constructor.hpp:392-517  CondensedGraph
+//   gfa::GFAWriter                                   io/graph/gfa_writer.cpp:18-52                                          CondensedGraph::WriteGFA
 // Error behaviour: the reference aborts through FATAL_ERROR / VERIFY (utils/logger/logger.hpp:177-190); here every
 // nonzero ABI return becomes sb200::Error carrying sb200_last_error(), which a SPAdes build maps back to FATAL_ERROR.
 // There is no CPU fallback: Context's constructor throws when no sm_100 device is present.
@@ -27,6 +29,7 @@
 
 #include <algorithm>
 #include <fstream>
+#include <ostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -461,6 +464,80 @@ private:
 // complement (k+1)-mers count twice, coverage_hash_map_builder.hpp:31-36).  Values come in (k+1)-mer FILE order.
 struct CoverageHashMapBuilder {
     std::vector<uint32_t> FillCoverage(const KMerDiskStorage &kpomers) const { return kpomers.counts(); }
+};
+
+// ---- the step right after the path: graph from the unitigs, GFA out ------------------------------------------------------------
+// FastGraphFromSequencesConstructor::ConstructGraph: edge i gets id min_id + 2i (its conjugate the next id, the same id when
+// the sequence is its own reverse complement); every sequence leaves a start and an end LinkRecord keyed by the MPHF index of
+// its canonical first / last k-mer (one batched KMerIndex::seq_idx on the GPU instead of one lookup per record); records are
+// sorted and every distinct index becomes a vertex pair (v, conjugate v) with ids min_id + 2j, min_id + 2j + 1.  WriteGFA
+// emits what gfa::GFAWriter::WriteSegmentsAndLinks emits for that graph (no coverage: DP:f:0 KC:i:0, as spades-gbuilder
+// without -c).  Lines come in id order; the reference's order of L lines depends on its adjacency containers, so files are
+// compared after sorting the lines.
+class CondensedGraph {
+public:
+    static constexpr uint64_t ID_BIAS = 3;   // omnigraph::GraphCore::ID_BIAS (assembly_graph/core/graph_core.hpp)
+    struct Vertex { std::vector<uint64_t> incoming, outgoing; };   // oriented edge ids at the canonical vertex of the pair
+
+    CondensedGraph(const DeBruijnExtensionIndex &index, const std::vector<Sequence> &sequences) : k_(index.k()), edges_(sequences) {
+        const unsigned W = (k_ + 31) / 32;
+        const size_t n = edges_.size();
+        std::vector<uint64_t> recs(2 * n * W, 0);
+        std::vector<uint8_t> is_rc(2 * n, 0);
+        self_conj_.assign(n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            const Sequence &s = edges_[i];
+            self_conj_[i] = (s == !s) ? 1 : 0;
+            for (int end = 0; end < 2; ++end) {   // StartLink / EndLink: canonical form of the first / last k-mer
+                std::string km = s.str().substr(end ? s.size() - k_ : 0, k_);
+                Sequence fwd(km), rc = !fwd;
+                const bool minimal = fwd < rc;
+                const Sequence &c = minimal ? fwd : rc;
+                is_rc[2 * i + end] = minimal ? 0 : 1;
+                memcpy(&recs[(2 * i + end) * W], c.data(), W * 8);
+            }
+        }
+        std::vector<uint64_t> idx = index.index().seq_idx(recs, W);
+        struct Rec { uint64_t key; uint64_t edge; };
+        std::vector<Rec> records;
+        records.reserve(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t e = ID_BIAS + 2 * i;
+            records.push_back(Rec{(idx[2 * i] << 2) | ((uint64_t) is_rc[2 * i] << 1) | 1u, e});
+            if (!self_conj_[i]) records.push_back(Rec{(idx[2 * i + 1] << 2) | ((uint64_t) is_rc[2 * i + 1] << 1), e});
+        }
+        std::sort(records.begin(), records.end(), [](const Rec &a, const Rec &b) { return a.key != b.key ? a.key < b.key : a.edge < b.edge; });
+        for (size_t i = 0; i < records.size(); ++i) {
+            if (i == 0 || (records[i].key >> 2) != (records[i - 1].key >> 2)) vertices_.emplace_back();
+            Vertex &v = vertices_.back();
+            const bool rc = records[i].key & 2, start = records[i].key & 1;
+            const uint64_t e = records[i].edge, ce = conjugate(e);
+            // LinkEdge: the record attaches `e` to v (or to conjugate(v) when rc); the conjugate edge mirrors it on the other vertex
+            if (start) { if (!rc) v.outgoing.push_back(e); else v.incoming.push_back(ce); }
+            else       { if (!rc) v.incoming.push_back(e); else v.outgoing.push_back(ce); }
+        }
+    }
+    size_t k() const { return k_; }
+    size_t edge_count() const { return edges_.size(); }
+    size_t vertex_count() const { return vertices_.size(); }
+    const std::vector<Vertex> &vertices() const { return vertices_; }
+    uint64_t conjugate(uint64_t e) const { return self_conj_[(e - ID_BIAS) >> 1] ? e : (((e - ID_BIAS) ^ 1u) + ID_BIAS); }
+
+    void WriteGFA(std::ostream &os) const {
+        for (size_t i = 0; i < edges_.size(); ++i)
+            os << "S\t" << (ID_BIAS + 2 * i) << '\t' << edges_[i].str() << "\tDP:f:0\tKC:i:0\n";
+        for (const Vertex &v : vertices_)
+            for (uint64_t inc : v.incoming)
+                for (uint64_t out : v.outgoing)
+                    os << "L\t" << name(inc) << '\t' << orient(inc) << '\t' << name(out) << '\t' << orient(out) << '\t' << k_ << "M\n";
+    }
+private:
+    uint64_t name(uint64_t e) const { return std::min(e, conjugate(e)); }          // io::CanonicalEdgeHelper (io/utils/edge_namer.hpp:71-86)
+    char orient(uint64_t e) const { return e <= conjugate(e) ? '+' : '-'; }
+    size_t k_;
+    std::vector<Sequence> edges_;
+    std::vector<uint8_t> self_conj_;
+    std::vector<Vertex> vertices_;
 };
 
 }  // namespace sb200

@@ -47,6 +47,8 @@
 #include "io/reads/longest_valid_wrapper.hpp"
 #include "io/reads/converting_reader_wrapper.hpp"
 #include "io/reads/binary_converter.hpp"
+#include "assembly_graph/core/graph.hpp"
+#include "io/graph/gfa_writer.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
 
@@ -269,6 +271,12 @@ int main(int argc, char **argv) {
         if (!a.no_dump) {
             std::ofstream us(a.out + "/unitigs.txt");
             for (const auto &s : seqs) us << s.str() << '\n';
+            // spades-gbuilder --gfa (A/projects/gbuilder/main.cpp:196-219): graph from the unitigs, segments + links
+            debruijn_graph::DeBruijnGraph g(k);
+            debruijn_graph::FastGraphFromSequencesConstructor<debruijn_graph::DeBruijnGraph>(k, ext).ConstructGraph(g, seqs);
+            std::ofstream gf(a.out + "/graph.gfa");
+            gfa::GFAWriter gfa_writer(g, gf);
+            gfa_writer.WriteSegmentsAndLinks();
         }
     } else {
         std::cerr << "bad mode\n";

@@ -27,6 +27,7 @@ def load_golden(name):
     d["buckets"] = int(d["buckets"])
     d["tip_bound"] = int(d["tip_bound"])
     d["unitigs"] = [str(u) for u in d["unitigs"]]
+    d["gfa"] = [str(l) for l in d["gfa"]]
     d["name"] = name
     return d
 

@@ -79,6 +79,9 @@ def test_gbuilder_files_equal_reference(tool, tmp_path, golden):
     assert np.array_equal(np.fromfile(tmp_path / "coverage.u32", dtype=np.uint32), g["coverage"])
     assert np.array_equal(np.fromfile(tmp_path / "masks_idx.u8", dtype=np.uint8), g["masks_idx"])
     assert open(tmp_path / "unitigs.txt").read().split() == g["unitigs"]
+    # a12: link records keyed by the MPHF -> vertices -> GFA; "byte-identical after canonical ordering" (line order in the reference
+    # follows its adjacency containers)
+    assert sorted(open(tmp_path / "graph.gfa").read().splitlines()) == list(g["gfa"])
     # second run from the binary read files it wrote (io::BinaryFileStream path): same graph
     out2 = tmp_path / "o2"
     out2.mkdir()

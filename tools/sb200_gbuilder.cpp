@@ -94,6 +94,11 @@ int main(int argc, char **argv) {
         }
         std::ofstream us(out + "/unitigs.txt");
         for (const auto &e : edges) us << e.str() << "\n";
+        {   // spades-gbuilder --gfa: graph from the unitigs (link records keyed by the MPHF), segments + links
+            sb200::CondensedGraph graph(index, edges);
+            std::ofstream gf(out + "/graph.gfa");
+            graph.WriteGFA(gf);
+        }
         printf("%zu (k+1)-mers, %zu k-mers, %zu unitigs, %.3f s on device incl. transfers, %llu kernel launches\n", kpomers.total_kmers(),
                index.size(), edges.size(), t1 - t0, (unsigned long long) ctx.kernel_launches());
     } catch (const sb200::Error &e) {
