@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--k", type=int, default=55)
     ap.add_argument("--buckets", type=int, default=80)
-    ap.add_argument("--cpu-sample-reads", type=int, default=300_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_200_000,
+                    help="reads of the workload the reference CPU path is timed on (about 10-20 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel timing table to stderr")
@@ -123,20 +124,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def run_reference_cpu(a, codes, n_reads, cores):
-    """Times the unmodified reference path (KMerDiskCounter -> ExtensionIndex -> UnbranchingPathExtractor) on `n_reads`
-    reads of the workload with `cores` threads.  Returns (Gbp/s, seconds, bases)."""
-    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    if not os.path.exists(driver):
-        return None
-    reads = synth.codes_to_strings(codes[:n_reads])
-    tmp = tempfile.mkdtemp(prefix="sb200_bench_")
-    try:
-        rp = os.path.join(tmp, "reads.txt")
-        with open(rp, "w") as f:
-            f.write("\n".join(reads) + "\n")
-        out = os.path.join(tmp, "out")
-        subprocess.check_call([driver, "--mode", "gbuilder", "--reads", rp, "--out", out, "-k", str(a.k), "-t", str(cores),
+class ReferenceSample:
+    """A bounded sample of the workload for the reference's CPU path: the FIRST `n_reads` reads of the same read set (same genome,
+    same chunk seeds as make_reads), written once as plain sequences for oracle/_ref/ref_driver."""
+
+    def __init__(self, a, n_reads):
+        self.a = a
+        self.driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+        self.tmp = None
+        self.n_reads = 0
+        if not os.path.exists(self.driver):
+            return
+        n_pairs_all = int(a.genome_len * a.coverage / (2 * a.read_len))
+        n_pairs = min((n_reads + 1) // 2, n_pairs_all)
+        g = synth.random_genome(a.genome_len, 42)
+        self.tmp = tempfile.mkdtemp(prefix="sb200_bench_")
+        self.reads_path = os.path.join(self.tmp, "reads.txt")
+        with open(self.reads_path, "w") as f:
+            for s in range(0, n_pairs, 200_000):       # the chunking and seeds of make_reads: chunk c of the sample IS chunk c of the workload
+                c = synth.sample_pairs(g, min(200_000, n_pairs_all - s), a.read_len, 350 if a.read_len <= 150 else 500, 0.005, 1042 + s)
+                c = c[:2 * (n_pairs - s)]
+                f.write("\n".join(synth.codes_to_strings(c)) + "\n")
+                self.n_reads += len(c)
+
+    def available(self):
+        return self.tmp is not None
+
+    def run(self, cores):
+        """One timed pass of the unmodified reference path (KMerDiskCounter -> ExtensionIndex -> UnbranchingPathExtractor) with
+        `cores` threads.  Returns (Gbp/s, seconds, bases); read parsing and output are outside the driver's `path_total`."""
+        out = os.path.join(self.tmp, "out")
+        subprocess.call(["rm", "-rf", out])
+        subprocess.check_call([self.driver, "--mode", "gbuilder", "--reads", self.reads_path, "--out", out, "-k", str(self.a.k), "-t", str(cores),
                                "--quiet", "--no-dump"], stdout=subprocess.DEVNULL)
         t = {}
         for line in open(os.path.join(out, "timing.txt")):
@@ -145,8 +164,11 @@ def run_reference_cpu(a, codes, n_reads, cores):
         secs = t["path_total"]
         bases = int(t["bases"])
         return bases / secs / 1e9, secs, bases
-    finally:
-        subprocess.call(["rm", "-rf", tmp])
+
+    def close(self):
+        if self.tmp:
+            subprocess.call(["rm", "-rf", self.tmp])
+            self.tmp = None
 
 
 def reference_arm(a):
@@ -155,24 +177,22 @@ def reference_arm(a):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_sample = a.cpu_sample_reads
-    args_small = argparse.Namespace(**vars(a))
-    # only the first chunk of the read set is needed for the sample
-    n_pairs_needed = (n_sample + 1) // 2
-    g = synth.random_genome(a.genome_len, 42)
-    codes = synth.sample_pairs(g, min(200_000, max(n_pairs_needed, 1)), a.read_len, 350 if a.read_len <= 150 else 500, 0.005, 1042)
-    n_sample = min(n_sample, len(codes))
+    smp = ReferenceSample(a, a.cpu_sample_reads)
+    if not smp.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver is not built (no /root/reference at build time)"}))
+        return 0
     vals, secs_all = [], []
-    for i in range(a.warmup + a.steps):
-        r = run_reference_cpu(args_small, codes, n_sample, cores)
-        if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver is not built (no /root/reference at build time)"}))
-            return 0
-        if i >= a.warmup:
-            vals.append(r[0]); secs_all.append(r[1])
-        bases = r[2]
+    try:
+        for i in range(a.warmup + a.steps):
+            r = smp.run(cores)
+            if i >= a.warmup:
+                vals.append(r[0]); secs_all.append(r[1])
+            bases = r[2]
+    finally:
+        smp.close()
     v = float(np.mean(vals))
-    sample = "first %d reads (%.1f Mbp) of the workload; whole reference path incl. its temp-file I/O, -t %d" % (n_sample, bases / 1e6, cores)
+    sample = "first %d reads (%.1f Mbp) of the workload; whole reference path incl. its temp-file I/O, %.1f s per step, -t %d" % (
+        smp.n_reads, bases / 1e6, float(np.mean(secs_all)), cores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * float(np.mean(secs_all)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": workload_config(a, 1),
@@ -486,11 +506,15 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        r = run_reference_cpu(a, first_codes, min(a.cpu_sample_reads, len(first_codes)), cores)
-        if r:
+        smp = ReferenceSample(a, a.cpu_sample_reads)
+        if smp.available():
+            try:
+                r = smp.run(cores)
+            finally:
+                smp.close()
             cpu = {"value": r[0], "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "first %d reads (%.1f Mbp) of the workload, whole reference path in %.1f s, -t %d" % (
-                       min(a.cpu_sample_reads, len(first_codes)), r[2] / 1e6, r[1], cores)}
+                       smp.n_reads, r[2] / 1e6, r[1], cores)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -14,6 +14,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "segsort.cuh"
+#include "grouphash.cuh"
 
 namespace sb200 {
 
@@ -223,6 +224,25 @@ template<int W>
 static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
                                    bool double_palindromes, bool drop_marker);
 
+template<int W, typename IdxT>
+static void launch_group_hash(sb200_ctx *ctx, int mode, uint32_t n_groups, const uint64_t *grouped, const ChunkRange *ranges, uint32_t *group_unique,
+                              uint32_t *ctrl, uint64_t *out, uint32_t *out_cnt, int shift2, uint64_t lw_keep, int pshift) {
+    const size_t smem = group_hash_smem<IdxT>();
+    if (mode == 1) {
+        auto seg_chunk_kernel_ = group_hash_kernel<W, 1, IdxT>;   // profile name kept: it is the same stage of the path
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
+    } else if (mode == 2) {
+        auto seg_chunk_kernel_ = group_hash_kernel<W, 2, IdxT>;
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
+    } else {
+        auto seg_chunk_kernel_ = group_hash_kernel<W, 0, IdxT>;
+        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
+    }
+}
+
 // Sort + unique + counts + bucket table.  `inst` (n x W) is consumed.
 //   1. one or two stable counting passes group the instances by the composite key bucket << p | top p value bits, with p
 //      chosen so that a group is ~7 K records (radix_sort.cuh)
@@ -268,6 +288,8 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     DevBuf<uint32_t> group_unique(ctx, (uint64_t) n_groups + 1);
     DevBuf<uint32_t> cnt_full;   // multiplicity (or OR-ed mask bits) of the unique record at the same position of `other`
     if (want_counts || masks_mode) cnt_full.alloc(ctx, n);
+    static const bool use_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");   // A/B: the sorting kernel
+    if (use_chunk) {
     size_t smem = seg_chunk_smem<W>();
     if (want_counts) {
         auto seg_chunk_kernel_ = group_chunk_kernel<W, 1>;
@@ -282,6 +304,18 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift,
                lw_keep, 0);
+    }
+    } else {
+        // hash deduplication of every group (grouphash.cuh); groups of 65535+ records go to the 32-bit-slot instance
+        const int shift2 = dshift + 8;
+        const int mode = want_counts ? 1 : masks_mode ? 2 : 0;
+        uint32_t *cnt_out = (mode == 0) ? nullptr : cnt_full.p;
+        const int psh = (mode == 2) ? pshift : 0;
+        launch_group_hash<W, uint16_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh);
+        uint32_t flags[2] = {0, 0};
+        ctx->fetch(flags, ctrl.p, 8);
+        if (flags[1] && !flags[0])
+            launch_group_hash<W, uint32_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh);
     }
     // per-group unique counts -> offsets; the total sizes the result
     DevBuf<uint32_t> total32(ctx, 1);

@@ -1,0 +1,291 @@
+// grouphash.cuh — deduplication, counting and the final order of one GROUP of records, by hashing instead of sorting copies.
+//
+// After the counting passes (radix_sort.cuh) all records with the same composite key (bucket, top p value bits) are contiguous:
+// a group of a few thousand records (segsort.cuh explains the grouping).  At sequencing coverage most of them are COPIES: config 2
+// has 7.1 K instances but only 1.8 K distinct (k+1)-mers per group.  group_chunk_kernel (segsort.cuh) still moved every copy through
+// a shared-memory counting sort and a warp-wide match; this kernel touches a copy exactly once:
+//   (1) the group is streamed from HBM (coalesced, never staged): every record probes a shared-memory hash table whose slots hold the
+//       INDEX of the first record seen with that value (a 16-bit CAS claims a slot; the input array is immutable, so a claimed slot is
+//       immediately comparable — no publish step, no spinning); a copy adds to the slot's multiplicity (or ORs its mask payload);
+//   (2) the occupied slots are compacted to a list of distinct records (index + count);
+//   (3) only the distinct records are ordered: counting sort over 1024 bins of the 32 key bits right below the group prefix (the
+//       "tag", monotone in the record order inside a group), rank inside a bin by tag (full record compare on the rare tag tie);
+//   (4) records (+ counts / masks) leave in order to the front of the group's own range of the output buffer, as group_chunk_kernel
+//       does; seg_compact_kernel then closes the gaps.
+// Shared memory holds 2 x UMAX slots and per-distinct bookkeeping only (72 KB: three CTAs per SM), so neither the size of a group nor
+// the multiplicity of a k-mer (poly-A, high coverage) is limited by it.  A group with more than UMAX distinct records is redone in
+// R = 2, 4, ... 256 rounds over disjoint tag ranges; beyond that the fail flag sends the set to the LSD path (radix_sort.cuh).
+// Groups of 65535+ records need 32-bit slots: the 16-bit instance skips them and raises ctrl[1], the host then launches the 32-bit
+// instance for those groups only.
+#pragma once
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "segsort.cuh"
+
+namespace sb200 {
+
+#ifndef GH_UMAX
+#define GH_UMAX 4096
+#endif
+#ifndef GH_THREADS
+#define GH_THREADS 256
+#endif
+#ifndef GH_MIN_BLOCKS
+#define GH_MIN_BLOCKS 3
+#endif
+
+struct HashCfg {
+    static constexpr int THREADS = GH_THREADS;
+    static constexpr int UMAX = GH_UMAX;          // distinct records one round may hold
+    static constexpr int TS = 2 * UMAX;           // table slots (load <= 0.5)
+    static constexpr int LOG_TS = (TS == 4096) ? 12 : (TS == 8192) ? 13 : (TS == 16384) ? 14 : -1;
+    static constexpr int BINS = 1024;
+    static_assert(LOG_TS > 0, "GH_UMAX must be 2048, 4096 or 8192");
+    static_assert(BINS % THREADS == 0 || THREADS % BINS == 0, "bins per thread");
+};
+
+template<typename IdxT>
+constexpr size_t group_hash_smem() {
+    // region A: table + multiplicities, later tags + bin starts + bin cursors + binned entry ids;  region B: index + count per distinct
+    size_t a1 = (size_t) HashCfg::TS * sizeof(IdxT) + (size_t) HashCfg::TS * 4;
+    size_t a2 = (size_t) HashCfg::UMAX * 4 + (size_t) (HashCfg::BINS + 1) * 4 + (size_t) HashCfg::BINS * 4 + (size_t) HashCfg::UMAX * 2;
+    size_t a = a1 > a2 ? a1 : a2;
+    return a + (size_t) HashCfg::UMAX * sizeof(IdxT) + (size_t) HashCfg::UMAX * 4;
+}
+
+template<int W>
+__device__ __forceinline__ void gh_load(const uint64_t *base, uint64_t idx, uint64_t *r) { load_rec<W>(base, idx, r); }
+
+template<int W>
+__device__ __forceinline__ uint32_t gh_slot(const uint64_t *k) {
+    uint64_t h = k[0] * 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int j = 1; j < W; ++j) h = (h ^ k[j]) * 0xC2B2AE3D27D4EB4FULL + (h >> 31);
+    h ^= h >> 29;
+    h *= 0xD6E8FEB86659FD93ULL;
+    return (uint32_t) (h >> (64 - HashCfg::LOG_TS));
+}
+
+// The shared memory of one CTA (see group_hash_smem): every phase gets the same view.
+template<typename IdxT>
+struct GhSmem {
+    IdxT *table;          // first life of region A: slot -> index of the first record with that value (EMPTY = all ones)
+    uint32_t *cnt;        //                         slot -> multiplicity / OR-ed payload
+    uint32_t *ltag;       // second life of region A: tag of every distinct record
+    uint32_t *binstart;   //   BINS + 1
+    uint32_t *cursor;     //   BINS
+    uint16_t *binned;     //   entry ids grouped by bin
+    uint32_t *lc;         // region B: multiplicity of every distinct record
+    IdxT *lq;             //           index of its first occurrence in the group
+};
+
+template<typename IdxT>
+__device__ __forceinline__ GhSmem<IdxT> gh_views(unsigned char *raw) {
+    constexpr int UMAX = HashCfg::UMAX, TS = HashCfg::TS, BINS = HashCfg::BINS;
+    constexpr size_t A1 = (size_t) TS * sizeof(IdxT) + (size_t) TS * 4;
+    constexpr size_t A2 = (size_t) UMAX * 4 + (size_t) (BINS + 1) * 4 + (size_t) BINS * 4 + (size_t) UMAX * 2;
+    constexpr size_t A = A1 > A2 ? A1 : A2;
+    GhSmem<IdxT> v;
+    v.table = reinterpret_cast<IdxT *>(raw);
+    v.cnt = reinterpret_cast<uint32_t *>(raw + (size_t) TS * sizeof(IdxT));
+    v.ltag = reinterpret_cast<uint32_t *>(raw);
+    v.binstart = v.ltag + UMAX;
+    v.cursor = v.binstart + BINS + 1;
+    v.binned = reinterpret_cast<uint16_t *>(v.cursor + BINS);
+    v.lc = reinterpret_cast<uint32_t *>(raw + A);
+    v.lq = reinterpret_cast<IdxT *>(v.lc + UMAX);
+    return v;
+}
+
+// Phase 1+2: stream the records of the group whose tag falls into the round's range through the hash table, then compact the occupied
+// slots to the list (lq, lc).  Returns the number of distinct records, or ~0u when the table got crowded (more than UMAX distinct).
+template<int W, int MODE, typename IdxT>
+__device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__restrict__ g, uint32_t gcnt, int shift2, uint64_t lw_keep, int pshift,
+                                          int lgR, uint32_t round, uint32_t *s_U, uint32_t *s_overflow) {
+    constexpr int THREADS = HashCfg::THREADS, UMAX = HashCfg::UMAX, TS = HashCfg::TS;
+    constexpr IdxT EMPTY = (IdxT) ~(IdxT) 0;
+    constexpr int MAX_PROBES = 512;
+    const GhSmem<IdxT> sm = gh_views<IdxT>(raw);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < (uint32_t) TS; i += THREADS) { sm.table[i] = EMPTY; sm.cnt[i] = 0; }
+    if (threadIdx.x == 0) { *s_U = 0; *s_overflow = 0; }
+    __syncthreads();
+    for (uint32_t q0 = 0; q0 < gcnt; q0 += THREADS * 4) {
+        uint64_t in[4][W];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t q = q0 + i * THREADS + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < W; ++j) in[i][j] = 0;
+            if (q < gcnt) gh_load<W>(g, q, in[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t q = q0 + i * THREADS + threadIdx.x;
+            const uint32_t val = (MODE == 2) ? 1u << ((uint32_t) (in[i][W - 1] >> pshift) & 7u) : 1u;
+            if (MODE == 2) in[i][W - 1] &= lw_keep;
+            bool todo = q < gcnt;
+            if (lgR) todo = todo && (seg_tag(in[i][0], shift2) >> (32 - lgR)) == round;
+            uint32_t h = gh_slot<W>(in[i]);
+            int probes = 0;
+            while (todo && probes < MAX_PROBES) {
+                IdxT v = sm.table[h];
+                if (v == EMPTY) v = atomicCAS(&sm.table[h], EMPTY, (IdxT) q);
+                bool mine = (v == EMPTY);
+                if (!mine) {
+                    uint64_t o[W];
+                    gh_load<W>(g, (uint32_t) v, o);
+                    if (MODE == 2) o[W - 1] &= lw_keep;
+                    mine = kmer_eq<W>(o, in[i]);
+                }
+                if (mine) {
+                    if (MODE == 2) atomicOr(&sm.cnt[h], val);
+                    else if (MODE == 1) atomicAdd(&sm.cnt[h], 1u);
+                    todo = false;
+                } else {
+                    h = (h + 1) & (TS - 1);
+                    ++probes;
+                }
+            }
+            if (todo) atomicExch(s_overflow, 1u);   // crowded table: far more than UMAX distinct records
+        }
+    }
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < (uint32_t) TS; i0 += THREADS) {
+        const uint32_t h = i0 + threadIdx.x;
+        const IdxT v = sm.table[h];
+        const uint32_t occ = __ballot_sync(0xffffffffu, v != EMPTY);
+        uint32_t base = 0;
+        if (lane == 0 && occ) base = atomicAdd(s_U, (uint32_t) __popc(occ));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (v != EMPTY) {
+            const uint32_t e = base + (uint32_t) __popc(occ & ((1u << lane) - 1u));
+            if (e < (uint32_t) UMAX) { sm.lq[e] = v; sm.lc[e] = sm.cnt[h]; }
+        }
+    }
+    __syncthreads();
+    const uint32_t U = *s_U;
+    const uint32_t ov = *s_overflow;
+    __syncthreads();   // everybody has read the two words before the next round resets them
+    return (ov || U > (uint32_t) UMAX) ? ~0u : U;
+}
+
+// Phase 3+4: order the U distinct records (bins over the tag, rank inside the bin) and write them (+ counts) to out[obase ...).
+template<int W, int MODE, typename IdxT>
+__device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restrict__ g, uint32_t U, int shift2, uint64_t lw_keep, int lgR,
+                                     uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, unsigned long long obase, uint32_t *s_wtot) {
+    constexpr int THREADS = HashCfg::THREADS, BINS = HashCfg::BINS;
+    const GhSmem<IdxT> sm = gh_views<IdxT>(raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < (uint32_t) BINS + 1; i += THREADS) sm.binstart[i] = 0;
+    __syncthreads();
+    const int bshift = 22 - lgR;   // bin = the 10 tag bits below the lgR bits that select the round
+    for (uint32_t e = threadIdx.x; e < U; e += THREADS) {
+        uint64_t k[W];
+        gh_load<W>(g, sm.lq[e], k);
+        const uint32_t t = seg_tag(k[0], shift2);
+        sm.ltag[e] = t;
+        atomicAdd(&sm.binstart[(t >> bshift) & (BINS - 1)], 1u);
+    }
+    __syncthreads();
+    {
+        constexpr int PER = BINS / THREADS;
+        uint32_t c[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { c[i] = sm.binstart[threadIdx.x * PER + i]; sum += c[i]; }
+        const uint32_t inc = warp_inclusive_scan(sum);
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t ex = inc - sum, tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) {
+            const uint32_t x = s_wtot[w];
+            if (w < warp) ex += x;
+            tot += x;
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { sm.binstart[threadIdx.x * PER + i] = ex; sm.cursor[threadIdx.x * PER + i] = 0; ex += c[i]; }
+        if (threadIdx.x == 0) sm.binstart[BINS] = tot;
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < U; e += THREADS) {
+        const uint32_t d = (sm.ltag[e] >> bshift) & (BINS - 1);
+        sm.binned[sm.binstart[d] + atomicAdd(&sm.cursor[d], 1u)] = (uint16_t) e;
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < U; e += THREADS) {
+        const uint32_t t = sm.ltag[e];
+        const uint32_t d = (t >> bshift) & (BINS - 1);
+        uint64_t me[W];
+        gh_load<W>(g, sm.lq[e], me);
+        if (MODE == 2) me[W - 1] &= lw_keep;
+        uint32_t less = 0;
+        const uint32_t i0 = sm.binstart[d], i1 = sm.binstart[d + 1];
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t o = sm.binned[i];
+            const uint32_t to = sm.ltag[o];
+            if (to < t) {
+                ++less;
+            } else if (to == t && o != e) {   // tag tie: two distinct records agree on the upper part of word 0
+                uint64_t other[W];
+                gh_load<W>(g, sm.lq[o], other);
+                if (MODE == 2) other[W - 1] &= lw_keep;
+                less += rec_less_bf<W>(other, me);
+            }
+        }
+        const unsigned long long pos = obase + i0 + less;
+        store_rec<W>(out, pos, me);
+        if (MODE != 0) out_cnt[pos] = sm.lc[e];
+    }
+    __syncthreads();   // the next round reuses every array
+}
+
+// shift2: the group prefix ends at bit `shift2` of word 0; the tag is the 32 bits below it.
+// MODE 0 records only, 1 + multiplicities, 2 + OR of the 3-bit mask payload at bit pshift of the last word (count.cu derive_kernel).
+template<int W, int MODE, typename IdxT>
+__global__ void __launch_bounds__(HashCfg::THREADS, GH_MIN_BLOCKS)
+group_hash_kernel(const uint64_t *__restrict__ recs, const ChunkRange *__restrict__ ranges, uint32_t *__restrict__ group_unique,
+                  uint32_t *__restrict__ ctrl, uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, int shift2, uint64_t lw_keep, int pshift) {
+    constexpr bool SMALL = sizeof(IdxT) == 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_U, s_overflow;
+    __shared__ uint32_t s_wtot[HashCfg::THREADS / 32];
+
+    const uint32_t b = blockIdx.x;
+    const ChunkRange cr = ranges[b];
+    const uint32_t s = cr.s, gcnt = cr.e - cr.s;
+    if (SMALL ? (gcnt >= 65535u) : (gcnt < 65535u)) {   // the other instance's groups
+        if (SMALL && threadIdx.x == 0) { group_unique[b] = 0; atomicExch(&ctrl[1], 1u); }
+        return;
+    }
+    if (gcnt == 0) {
+        if (threadIdx.x == 0) group_unique[b] = 0;
+        return;
+    }
+    const uint64_t *__restrict__ g = recs + (uint64_t) s * W;
+
+    uint32_t emitted = 0;
+    int lgR = 0;
+    while (true) {                 // R = 1 << lgR rounds over disjoint tag ranges
+        emitted = 0;
+        bool bad = false;
+        const uint32_t R = 1u << lgR;
+        for (uint32_t round = 0; round < R; ++round) {
+            const uint32_t U = gh_dedup<W, MODE, IdxT>(smem_raw, g, gcnt, shift2, lw_keep, pshift, lgR, round, &s_U, &s_overflow);
+            if (U == ~0u) { bad = true; break; }   // block-uniform
+            gh_emit<W, MODE, IdxT>(smem_raw, g, U, shift2, lw_keep, lgR, out, out_cnt, (unsigned long long) s + emitted, s_wtot);
+            emitted += U;
+        }
+        if (!bad) break;
+        if (lgR == 8) {   // a single 8-bit digit still holds more than UMAX distinct records
+            if (threadIdx.x == 0) { group_unique[b] = 0; atomicExch(&ctrl[0], 1u); }
+            return;
+        }
+        ++lgR;
+    }
+    if (threadIdx.x == 0) group_unique[b] = emitted;
+}
+
+}  // namespace sb200

@@ -301,8 +301,22 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
                 if (lane == 0) atomicExch(fail_flag, 1u);
                 continue;
             }
-            // rank every entry among the entries (all distinct): number of smaller values, branch-free word-wise compare
+            // rank every entry among the entries (all distinct): number of smaller values.  Fast path (no second slot, and the 32 key
+            // bits right below the digit — monotone in the record order inside a segment — tell all entries apart, which fails only
+            // when two k-mers of one bucket agree on the whole of word 0's upper part): one 32-bit shuffle + compare per entry.
             uint32_t lessA = 0, lessB = 0;
+            const uint32_t tagA = seg_tag(keyA[0], dshift);
+            bool by_tag = (VB == 0u);
+            if (by_tag) {
+                const uint32_t same = __match_any_sync(0xffffffffu, tagA) & VA;
+                by_tag = !__any_sync(0xffffffffu, ((VA >> lane) & 1u) && same != (1u << lane));
+            }
+            if (by_tag) {
+                for (uint32_t E = VA; E; E &= E - 1u) {
+                    const uint32_t te = __shfl_sync(0xffffffffu, tagA, __ffs((int) E) - 1);
+                    lessA += (te < tagA) ? 1u : 0u;
+                }
+            } else {
             for (uint32_t E = VA; E; E &= E - 1u) {
                 const int e = __ffs((int) E) - 1;
                 uint64_t ke[W];
@@ -318,6 +332,7 @@ __global__ void __launch_bounds__(SegCfg<W>::THREADS) group_chunk_kernel(const u
                 for (int j = 0; j < W; ++j) ke[j] = __shfl_sync(0xffffffffu, keyB[j], e);
                 lessA += rec_less_bf<W>(ke, keyA);
                 lessB += rec_less_bf<W>(ke, keyB);
+            }
             }
             __syncwarp();
             if ((VA >> lane) & 1u) {
