@@ -4,19 +4,22 @@
 // a group of a few thousand records (segsort.cuh explains the grouping).  At sequencing coverage most of them are COPIES: config 2
 // has 7.1 K instances but only 1.8 K distinct (k+1)-mers per group.  group_chunk_kernel (segsort.cuh) still moved every copy through
 // a shared-memory counting sort and a warp-wide match; this kernel touches a copy exactly once:
-//   (1) the group is streamed from HBM (coalesced, never staged): every record probes a shared-memory hash table whose slots hold the
-//       INDEX of the first record seen with that value (a 16-bit CAS claims a slot; the input array is immutable, so a claimed slot is
-//       immediately comparable — no publish step, no spinning); a copy adds to the slot's multiplicity (or ORs its mask payload);
+//   (1) the group is streamed from HBM (coalesced, never staged): every record probes a shared-memory hash table whose slot words hold
+//       the INDEX of the first record seen with that value next to its multiplicity (one native CAS claims the slot and leaves the first
+//       count; the input array is immutable, so a claimed slot is immediately comparable — no publish step, no spinning); a copy adds 1
+//       to the same word (or ORs its mask payload into it);
 //   (2) the occupied slots are compacted to a list of distinct records (index + count);
 //   (3) only the distinct records are ordered: counting sort over 1024 bins of the 32 key bits right below the group prefix (the
 //       "tag", monotone in the record order inside a group), rank inside a bin by tag (full record compare on the rare tag tie);
 //   (4) records (+ counts / masks) leave in order to the front of the group's own range of the output buffer, as group_chunk_kernel
 //       does; seg_compact_kernel then closes the gaps.
-// Shared memory holds 2 x UMAX slots and per-distinct bookkeeping only (72 KB: three CTAs per SM), so neither the size of a group nor
-// the multiplicity of a k-mer (poly-A, high coverage) is limited by it.  A group with more than UMAX distinct records is redone in
+// Shared memory holds 2 x UMAX slot words and per-distinct bookkeeping only (48 KB: four CTAs per SM), so the size of a group is not
+// limited by it (a k-mer with 65535+ copies in a group of fewer records than that cannot exist; such groups take the 64-bit slots).  A group with more than UMAX distinct records is redone in
 // R = 2, 4, ... 256 rounds over disjoint tag ranges; beyond that the fail flag sends the set to the LSD path (radix_sort.cuh).
-// Groups of 65535+ records need 32-bit slots: the 16-bit instance skips them and raises ctrl[1], the host then launches the 32-bit
-// instance for those groups only.
+// Groups of 65535+ records need 64-bit slot words: the 32-bit instance skips them and raises ctrl[1], the host then launches the
+// 64-bit instance for those groups only.
+// The phases are separate __noinline__ functions on purpose: as one function body nvcc 12.9 -O3 produced code that lost shared-memory
+// updates between phases (correct at -G, -Xcicc -O0 and -Xptxas -O0; tools/gh_test.cu is the harness that showed it).
 #pragma once
 #include "common.cuh"
 #include "kmer_ops.cuh"
@@ -33,7 +36,7 @@ namespace sb200 {
 #define GH_THREADS 256
 #endif
 #ifndef GH_MIN_BLOCKS
-#define GH_MIN_BLOCKS 3
+#define GH_MIN_BLOCKS 4
 #endif
 
 struct HashCfg {
@@ -46,13 +49,27 @@ struct HashCfg {
     static_assert(BINS % THREADS == 0 || THREADS % BINS == 0, "bins per thread");
 };
 
+// Slot word: (index of the first record with that value + 1) in the upper half, multiplicity (or OR-ed payload) in the lower half;
+// 0 = empty.  One native CAS claims the slot AND leaves the first count; a copy adds 1 to the same word.
+//   IdxT = uint16_t: 32-bit slots, groups below 65535 records (a multiplicity is at most the group size, so the count cannot carry)
+//   IdxT = uint32_t: 64-bit slots, any group
+template<typename IdxT> struct GhSlot;
+template<> struct GhSlot<uint16_t> { using type = uint32_t; static constexpr int HB = 16; };
+template<> struct GhSlot<uint32_t> { using type = unsigned long long; static constexpr int HB = 32; };
+
 template<typename IdxT>
-constexpr size_t group_hash_smem() {
-    // region A: table + multiplicities, later tags + bin starts + bin cursors + binned entry ids;  region B: index + count per distinct
-    size_t a1 = (size_t) HashCfg::TS * sizeof(IdxT) + (size_t) HashCfg::TS * 4;
+constexpr size_t gh_region_a() {
+    // first life: the slot words; second life: tags + bin starts + bin cursors + binned entry ids
+    size_t a1 = (size_t) HashCfg::TS * sizeof(typename GhSlot<IdxT>::type);
     size_t a2 = (size_t) HashCfg::UMAX * 4 + (size_t) (HashCfg::BINS + 1) * 4 + (size_t) HashCfg::BINS * 4 + (size_t) HashCfg::UMAX * 2;
     size_t a = a1 > a2 ? a1 : a2;
-    return a + (size_t) HashCfg::UMAX * sizeof(IdxT) + (size_t) HashCfg::UMAX * 4;
+    return (a + 15) & ~(size_t) 15;
+}
+
+template<typename IdxT>
+constexpr size_t group_hash_smem() {
+    // region B: multiplicity + first index of every distinct record
+    return gh_region_a<IdxT>() + (size_t) HashCfg::UMAX * sizeof(IdxT) * 2;
 }
 
 template<int W>
@@ -71,31 +88,26 @@ __device__ __forceinline__ uint32_t gh_slot(const uint64_t *k) {
 // The shared memory of one CTA (see group_hash_smem): every phase gets the same view.
 template<typename IdxT>
 struct GhSmem {
-    IdxT *table;          // first life of region A: slot -> index of the first record with that value (EMPTY = all ones)
-    uint32_t *cnt;        //                         slot -> multiplicity / OR-ed payload
+    typename GhSlot<IdxT>::type *slot;   // first life of region A
     uint32_t *ltag;       // second life of region A: tag of every distinct record
     uint32_t *binstart;   //   BINS + 1
     uint32_t *cursor;     //   BINS
     uint16_t *binned;     //   entry ids grouped by bin
-    uint32_t *lc;         // region B: multiplicity of every distinct record
+    IdxT *lc;             // region B: multiplicity of every distinct record
     IdxT *lq;             //           index of its first occurrence in the group
 };
 
 template<typename IdxT>
 __device__ __forceinline__ GhSmem<IdxT> gh_views(unsigned char *raw) {
-    constexpr int UMAX = HashCfg::UMAX, TS = HashCfg::TS, BINS = HashCfg::BINS;
-    constexpr size_t A1 = (size_t) TS * sizeof(IdxT) + (size_t) TS * 4;
-    constexpr size_t A2 = (size_t) UMAX * 4 + (size_t) (BINS + 1) * 4 + (size_t) BINS * 4 + (size_t) UMAX * 2;
-    constexpr size_t A = A1 > A2 ? A1 : A2;
+    constexpr int UMAX = HashCfg::UMAX, BINS = HashCfg::BINS;
     GhSmem<IdxT> v;
-    v.table = reinterpret_cast<IdxT *>(raw);
-    v.cnt = reinterpret_cast<uint32_t *>(raw + (size_t) TS * sizeof(IdxT));
+    v.slot = reinterpret_cast<typename GhSlot<IdxT>::type *>(raw);
     v.ltag = reinterpret_cast<uint32_t *>(raw);
     v.binstart = v.ltag + UMAX;
     v.cursor = v.binstart + BINS + 1;
     v.binned = reinterpret_cast<uint16_t *>(v.cursor + BINS);
-    v.lc = reinterpret_cast<uint32_t *>(raw + A);
-    v.lq = reinterpret_cast<IdxT *>(v.lc + UMAX);
+    v.lc = reinterpret_cast<IdxT *>(raw + gh_region_a<IdxT>());
+    v.lq = v.lc + UMAX;
     return v;
 }
 
@@ -104,12 +116,13 @@ __device__ __forceinline__ GhSmem<IdxT> gh_views(unsigned char *raw) {
 template<int W, int MODE, typename IdxT>
 __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__restrict__ g, uint32_t gcnt, int shift2, uint64_t lw_keep, int pshift,
                                           int lgR, uint32_t round, uint32_t *s_U, uint32_t *s_overflow) {
-    constexpr int THREADS = HashCfg::THREADS, UMAX = HashCfg::UMAX, TS = HashCfg::TS;
-    constexpr IdxT EMPTY = (IdxT) ~(IdxT) 0;
+    using SlotT = typename GhSlot<IdxT>::type;
+    constexpr int THREADS = HashCfg::THREADS, UMAX = HashCfg::UMAX, TS = HashCfg::TS, HB = GhSlot<IdxT>::HB;
+    constexpr SlotT LOW = ((SlotT) 1 << HB) - 1;
     constexpr int MAX_PROBES = 512;
     const GhSmem<IdxT> sm = gh_views<IdxT>(raw);
     const int lane = threadIdx.x & 31;
-    for (uint32_t i = threadIdx.x; i < (uint32_t) TS; i += THREADS) { sm.table[i] = EMPTY; sm.cnt[i] = 0; }
+    for (uint32_t i = threadIdx.x; i < (uint32_t) TS; i += THREADS) sm.slot[i] = 0;
     if (threadIdx.x == 0) { *s_U = 0; *s_overflow = 0; }
     __syncthreads();
     for (uint32_t q0 = 0; q0 < gcnt; q0 += THREADS * 4) {
@@ -121,48 +134,81 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
             for (int j = 0; j < W; ++j) in[i][j] = 0;
             if (q < gcnt) gh_load<W>(g, q, in[i]);
         }
+        // Four records per thread move through the stages together, so that the four look-ups of the first occurrences (an L2 hit of
+        // several hundred cycles each: the copy of a k-mer finds its slot taken and has to see the record that took it) overlap.
+        uint32_t h[4], val[4];
+        SlotT v[4];
+        bool todo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t q = q0 + i * THREADS + threadIdx.x;
-            const uint32_t val = (MODE == 2) ? 1u << ((uint32_t) (in[i][W - 1] >> pshift) & 7u) : 1u;
+            val[i] = (MODE == 2) ? 1u << ((uint32_t) (in[i][W - 1] >> pshift) & 7u) : (MODE == 1) ? 1u : 0u;
             if (MODE == 2) in[i][W - 1] &= lw_keep;
-            bool todo = q < gcnt;
-            if (lgR) todo = todo && (seg_tag(in[i][0], shift2) >> (32 - lgR)) == round;
-            uint32_t h = gh_slot<W>(in[i]);
-            int probes = 0;
-            while (todo && probes < MAX_PROBES) {
-                IdxT v = sm.table[h];
-                if (v == EMPTY) v = atomicCAS(&sm.table[h], EMPTY, (IdxT) q);
-                bool mine = (v == EMPTY);
-                if (!mine) {
-                    uint64_t o[W];
-                    gh_load<W>(g, (uint32_t) v, o);
-                    if (MODE == 2) o[W - 1] &= lw_keep;
-                    mine = kmer_eq<W>(o, in[i]);
-                }
-                if (mine) {
-                    if (MODE == 2) atomicOr(&sm.cnt[h], val);
-                    else if (MODE == 1) atomicAdd(&sm.cnt[h], 1u);
-                    todo = false;
+            todo[i] = q < gcnt;
+            if (lgR) todo[i] = todo[i] && (seg_tag(in[i][0], shift2) >> (32 - lgR)) == round;
+            h[i] = gh_slot<W>(in[i]);
+            v[i] = 0;
+            if (todo[i]) {
+                v[i] = sm.slot[h[i]];
+                if (v[i] == 0) v[i] = atomicCAS(&sm.slot[h[i]], (SlotT) 0, ((SlotT) (q + 1) << HB) | val[i]);
+                if (v[i] == 0) todo[i] = false;   // claimed: the CAS left index and first count
+            }
+        }
+        uint64_t o[4][W];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) o[i][j] = 0;
+            if (todo[i]) gh_load<W>(g, (uint32_t) (v[i] >> HB) - 1u, o[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!todo[i]) continue;
+            if (MODE == 2) o[i][W - 1] &= lw_keep;
+            if (kmer_eq<W>(o[i], in[i])) {
+                if (MODE == 2) atomicOr(&sm.slot[h[i]], (SlotT) val[i]);
+                else if (MODE == 1) atomicAdd(&sm.slot[h[i]], (SlotT) 1);   // cannot carry: a count is below the group size
+                todo[i] = false;
+            } else {
+                h[i] = (h[i] + 1) & (TS - 1);
+            }
+        }
+        // leftovers: the slot held a different value; probe on, one record at a time
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t q = q0 + i * THREADS + threadIdx.x;
+            int probes = 1;
+            uint32_t hh = h[i];
+            bool td = todo[i];
+            while (td && probes < MAX_PROBES) {
+                SlotT w = sm.slot[hh];
+                if (w == 0) w = atomicCAS(&sm.slot[hh], (SlotT) 0, ((SlotT) (q + 1) << HB) | val[i]);
+                if (w == 0) { td = false; break; }
+                uint64_t k2[W];
+                gh_load<W>(g, (uint32_t) (w >> HB) - 1u, k2);
+                if (MODE == 2) k2[W - 1] &= lw_keep;
+                if (kmer_eq<W>(k2, in[i])) {
+                    if (MODE == 2) atomicOr(&sm.slot[hh], (SlotT) val[i]);
+                    else if (MODE == 1) atomicAdd(&sm.slot[hh], (SlotT) 1);
+                    td = false;
                 } else {
-                    h = (h + 1) & (TS - 1);
+                    hh = (hh + 1) & (TS - 1);
                     ++probes;
                 }
             }
-            if (todo) atomicExch(s_overflow, 1u);   // crowded table: far more than UMAX distinct records
+            if (td) atomicExch(s_overflow, 1u);   // crowded table: far more than UMAX distinct records
         }
     }
     __syncthreads();
     for (uint32_t i0 = 0; i0 < (uint32_t) TS; i0 += THREADS) {
-        const uint32_t h = i0 + threadIdx.x;
-        const IdxT v = sm.table[h];
-        const uint32_t occ = __ballot_sync(0xffffffffu, v != EMPTY);
+        const SlotT v = sm.slot[i0 + threadIdx.x];
+        const uint32_t occ = __ballot_sync(0xffffffffu, v != 0);
         uint32_t base = 0;
         if (lane == 0 && occ) base = atomicAdd(s_U, (uint32_t) __popc(occ));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (v != EMPTY) {
+        if (v != 0) {
             const uint32_t e = base + (uint32_t) __popc(occ & ((1u << lane) - 1u));
-            if (e < (uint32_t) UMAX) { sm.lq[e] = v; sm.lc[e] = sm.cnt[h]; }
+            if (e < (uint32_t) UMAX) { sm.lq[e] = (IdxT) ((v >> HB) - 1); sm.lc[e] = (IdxT) (v & LOW); }
         }
     }
     __syncthreads();
@@ -182,12 +228,24 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
     for (uint32_t i = threadIdx.x; i < (uint32_t) BINS + 1; i += THREADS) sm.binstart[i] = 0;
     __syncthreads();
     const int bshift = 22 - lgR;   // bin = the 10 tag bits below the lgR bits that select the round
-    for (uint32_t e = threadIdx.x; e < U; e += THREADS) {
-        uint64_t k[W];
-        gh_load<W>(g, sm.lq[e], k);
-        const uint32_t t = seg_tag(k[0], shift2);
-        sm.ltag[e] = t;
-        atomicAdd(&sm.binstart[(t >> bshift) & (BINS - 1)], 1u);
+    for (uint32_t e0 = 0; e0 < U; e0 += THREADS * 4) {   // four first-occurrence look-ups in flight per thread
+        uint64_t k[4][W];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t e = e0 + i * THREADS + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < W; ++j) k[i][j] = 0;
+            if (e < U) gh_load<W>(g, sm.lq[e], k[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t e = e0 + i * THREADS + threadIdx.x;
+            if (e < U) {
+                const uint32_t t = seg_tag(k[i][0], shift2);
+                sm.ltag[e] = t;
+                atomicAdd(&sm.binstart[(t >> bshift) & (BINS - 1)], 1u);
+            }
+        }
     }
     __syncthreads();
     {
@@ -215,29 +273,40 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
         sm.binned[sm.binstart[d] + atomicAdd(&sm.cursor[d], 1u)] = (uint16_t) e;
     }
     __syncthreads();
-    for (uint32_t e = threadIdx.x; e < U; e += THREADS) {
-        const uint32_t t = sm.ltag[e];
-        const uint32_t d = (t >> bshift) & (BINS - 1);
-        uint64_t me[W];
-        gh_load<W>(g, sm.lq[e], me);
-        if (MODE == 2) me[W - 1] &= lw_keep;
-        uint32_t less = 0;
-        const uint32_t i0 = sm.binstart[d], i1 = sm.binstart[d + 1];
-        for (uint32_t i = i0; i < i1; ++i) {
-            const uint32_t o = sm.binned[i];
-            const uint32_t to = sm.ltag[o];
-            if (to < t) {
-                ++less;
-            } else if (to == t && o != e) {   // tag tie: two distinct records agree on the upper part of word 0
-                uint64_t other[W];
-                gh_load<W>(g, sm.lq[o], other);
-                if (MODE == 2) other[W - 1] &= lw_keep;
-                less += rec_less_bf<W>(other, me);
-            }
+    for (uint32_t e0 = 0; e0 < U; e0 += THREADS * 4) {
+        uint64_t me[4][W];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t e = e0 + i * THREADS + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < W; ++j) me[i][j] = 0;
+            if (e < U) gh_load<W>(g, sm.lq[e], me[i]);
         }
-        const unsigned long long pos = obase + i0 + less;
-        store_rec<W>(out, pos, me);
-        if (MODE != 0) out_cnt[pos] = sm.lc[e];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t e = e0 + i * THREADS + threadIdx.x;
+            if (e >= U) continue;
+            const uint32_t t = sm.ltag[e];
+            const uint32_t d = (t >> bshift) & (BINS - 1);
+            if (MODE == 2) me[i][W - 1] &= lw_keep;
+            uint32_t less = 0;
+            const uint32_t i0 = sm.binstart[d], i1 = sm.binstart[d + 1];
+            for (uint32_t x = i0; x < i1; ++x) {
+                const uint32_t o = sm.binned[x];
+                const uint32_t to = sm.ltag[o];
+                if (to < t) {
+                    ++less;
+                } else if (to == t && o != e) {   // tag tie: two distinct records agree on the upper part of word 0
+                    uint64_t other[W];
+                    gh_load<W>(g, sm.lq[o], other);
+                    if (MODE == 2) other[W - 1] &= lw_keep;
+                    less += rec_less_bf<W>(other, me[i]);
+                }
+            }
+            const unsigned long long pos = obase + i0 + less;
+            store_rec<W>(out, pos, me[i]);
+            if (MODE != 0) out_cnt[pos] = sm.lc[e];
+        }
     }
     __syncthreads();   // the next round reuses every array
 }
