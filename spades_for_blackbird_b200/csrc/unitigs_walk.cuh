@@ -162,35 +162,39 @@ __global__ void __launch_bounds__(256) kept_list_kernel(const uint32_t *__restri
 
 // ---- link table: the walks as pointer chasing ----------------------------------------------------------------------------
 // With the whole k-mer table on this GPU every chain vertex (in = out = 1) gets one 32-bit word, indexed by its oriented
-// FILE position t = 2 * file index + strand:
-//     bits 0-27  oriented file position of its successor      bits 28-29  nucleotide appended by the step
+// MPHF position v = 2 * MPHF index + strand (strand 1 = the reverse complement of the stored k-mer):
+//     bits 0-27  oriented MPHF position of its successor      bits 28-29  nucleotide appended by the step
 //     bits 30-31 first base of the vertex itself (the reverse path's tie-breaker)        junctions hold LINK_JUNCTION.
-// Building it costs one MPHF lookup per chain vertex in a fully parallel, coalesced kernel; the walks then cost one 4-byte
-// read per step instead of a canonicalisation, two XXH3 hashes, the level probes and a rank per step (ncu, profiles/r1a:
-// the lookup walks executed 13.5 G warp instructions and pulled 25 GB through DRAM for 210 M steps).
+// Building it costs one MPHF lookup per chain vertex in a fully parallel kernel; the walks then cost one 4-byte read per step
+// instead of a canonicalisation, two XXH3 hashes, the level probes and a rank per step (ncu, profiles/r1a: the lookup walks
+// executed 13.5 G warp instructions and pulled 25 GB through DRAM for 210 M steps).  The table lives in MPHF order, not file
+// order, so that the successor's position IS the lookup result: a table in file order needed inv[lookup] per vertex, a random
+// 4-byte read that DRAM serves as a 128-byte fetch (17 of the 25 GB links_kernel read, profiles/r1b); the price is that every
+// vertex stores its word at a random place instead (the two strands of a k-mer are neighbours: one 8-byte store per k-mer).
 constexpr uint32_t LINK_JUNCTION = 0xFFFFFFFFu;
 constexpr uint32_t LINK_POS_MASK = 0x0FFFFFFFu;
 
 template<int W>
 __global__ void __launch_bounds__(256) links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, uint64_t n, int k, const uint32_t *__restrict__ idx,
-                                                   const uint32_t *__restrict__ inv, const uint8_t *__restrict__ masks,
+                                                   const uint8_t *__restrict__ masks,
                                                    const uint8_t *__restrict__ file_masks /* masks in file order, or nullptr */,
                                                    uint32_t *__restrict__ link) {
     uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n) return;
-    const uint32_t raw = file_masks ? (uint32_t) __ldg(file_masks + (t >> 1)) : (uint32_t) __ldg(masks + __ldg(idx + (t >> 1)));
+    const uint32_t me = __ldg(idx + (t >> 1));
+    const uint32_t raw = file_masks ? (uint32_t) __ldg(file_masks + (t >> 1)) : (uint32_t) __ldg(masks + me);
+    const int strand = (int) (t & 1);
     uint32_t out = LINK_JUNCTION;
     if (!mask_is_junction(raw)) {
-        const int strand = (int) (t & 1);
         const uint32_t c = nib_next((strand ? mask_conj(raw) : raw) & 15u);
         uint64_t x[W], y[W];
         oriented_kmer<W>(kmers, t >> 1, strand, k, x);
         kmer_shl<W>(x, k, c, y);
         bool minimal;
         const uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-        out = (2u * __ldg(inv + idy) + (minimal ? 0u : 1u)) | (c << 28) | (kmer_base(x, 0) << 30);
+        out = (2u * idy + (minimal ? 0u : 1u)) | (c << 28) | (kmer_base(x, 0) << 30);
     }
-    link[t] = out;
+    link[2u * me + (uint32_t) strand] = out;
 }
 
 // (the link walks stay one thread per start edge: they are bound by random DRAM reads, and the persistent form's extra
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         kmer_shl<W>(x, k, c, y);
         bool minimal;
         const uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-        uint32_t v = 2u * __ldg(inv + idy) + (minimal ? 0u : 1u);
+        uint32_t v = 2u * idy + (minimal ? 0u : 1u);   // oriented MPHF position: the index space of the link table
         efirst[e] = v;
         uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
         uint32_t nn = 1;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         if (!too_long) {
             chain_nodes = nn - 1;
             uint64_t rcn[W];
-            oriented_kmer<W>(kmers, v >> 1, (v & 1) ? 0 : 1, k, rcn);   // rc of the end vertex
+            oriented_kmer<W>(kmers, __ldg(inv + (v >> 1)), (v & 1) ? 0 : 1, k, rcn);   // rc of the end vertex (file position of its index)
             int cmp = kmer_lex_cmp<W>(x, rcn);
             bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
             if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
@@ -410,7 +414,7 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
             efirst.alloc(ctx, (uint64_t) n_e + 1);
             // masks in file order (a coalesced read) are valid as long as tip clipping has not edited the index-order array
             const uint8_t *fm = (kmers->masks_file.p && !ext->masks_edited) ? kmers->masks_file.p : nullptr;
-            LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->inv.p, ext->masks.p, fm, link.p);
+            LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, fm, link.p);
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
                    kflag.p, ewords.p, totals.p);
         } else {
