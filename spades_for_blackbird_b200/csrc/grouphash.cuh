@@ -134,11 +134,12 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
             for (int j = 0; j < W; ++j) in[i][j] = 0;
             if (q < gcnt) gh_load<W>(g, q, in[i]);
         }
-        // Four records per thread move through the stages together, so that the four look-ups of the first occurrences (an L2 hit of
-        // several hundred cycles each: the copy of a k-mer finds its slot taken and has to see the record that took it) overlap.
+        // Four records per thread move through the probe rounds together, so that their look-ups of the first occurrences (an L2 hit of
+        // several hundred cycles each: the copy of a k-mer finds its slot taken and has to see the record that took it) overlap.  A
+        // record whose slot holds a different value steps to the next slot and takes part in the next round.
         uint32_t h[4], val[4];
-        SlotT v[4];
         bool todo[4];
+        bool any = false;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t q = q0 + i * THREADS + threadIdx.x;
@@ -147,57 +148,43 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
             todo[i] = q < gcnt;
             if (lgR) todo[i] = todo[i] && (seg_tag(in[i][0], shift2) >> (32 - lgR)) == round;
             h[i] = gh_slot<W>(in[i]);
-            v[i] = 0;
-            if (todo[i]) {
-                v[i] = sm.slot[h[i]];
-                if (v[i] == 0) v[i] = atomicCAS(&sm.slot[h[i]], (SlotT) 0, ((SlotT) (q + 1) << HB) | val[i]);
-                if (v[i] == 0) todo[i] = false;   // claimed: the CAS left index and first count
-            }
+            any |= todo[i];
         }
-        uint64_t o[4][W];
+        for (int probes = 0; any && probes < MAX_PROBES; ++probes) {
+            SlotT v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int j = 0; j < W; ++j) o[i][j] = 0;
-            if (todo[i]) gh_load<W>(g, (uint32_t) (v[i] >> HB) - 1u, o[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (!todo[i]) continue;
-            if (MODE == 2) o[i][W - 1] &= lw_keep;
-            if (kmer_eq<W>(o[i], in[i])) {
-                if (MODE == 2) atomicOr(&sm.slot[h[i]], (SlotT) val[i]);
-                else if (MODE == 1) atomicAdd(&sm.slot[h[i]], (SlotT) 1);   // cannot carry: a count is below the group size
-                todo[i] = false;
-            } else {
-                h[i] = (h[i] + 1) & (TS - 1);
-            }
-        }
-        // leftovers: the slot held a different value; probe on, one record at a time
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t q = q0 + i * THREADS + threadIdx.x;
-            int probes = 1;
-            uint32_t hh = h[i];
-            bool td = todo[i];
-            while (td && probes < MAX_PROBES) {
-                SlotT w = sm.slot[hh];
-                if (w == 0) w = atomicCAS(&sm.slot[hh], (SlotT) 0, ((SlotT) (q + 1) << HB) | val[i]);
-                if (w == 0) { td = false; break; }
-                uint64_t k2[W];
-                gh_load<W>(g, (uint32_t) (w >> HB) - 1u, k2);
-                if (MODE == 2) k2[W - 1] &= lw_keep;
-                if (kmer_eq<W>(k2, in[i])) {
-                    if (MODE == 2) atomicOr(&sm.slot[hh], (SlotT) val[i]);
-                    else if (MODE == 1) atomicAdd(&sm.slot[hh], (SlotT) 1);
-                    td = false;
-                } else {
-                    hh = (hh + 1) & (TS - 1);
-                    ++probes;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t q = q0 + i * THREADS + threadIdx.x;
+                v[i] = 0;
+                if (todo[i]) {
+                    v[i] = sm.slot[h[i]];
+                    if (v[i] == 0) v[i] = atomicCAS(&sm.slot[h[i]], (SlotT) 0, ((SlotT) (q + 1) << HB) | val[i]);
+                    if (v[i] == 0) todo[i] = false;   // claimed: the CAS left index and first count
                 }
             }
-            if (td) atomicExch(s_overflow, 1u);   // crowded table: far more than UMAX distinct records
+            uint64_t o[4][W];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) o[i][j] = 0;
+                if (todo[i]) gh_load<W>(g, (uint32_t) (v[i] >> HB) - 1u, o[i]);
+            }
+            any = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!todo[i]) continue;
+                if (MODE == 2) o[i][W - 1] &= lw_keep;
+                if (kmer_eq<W>(o[i], in[i])) {
+                    if (MODE == 2) atomicOr(&sm.slot[h[i]], (SlotT) val[i]);
+                    else if (MODE == 1) atomicAdd(&sm.slot[h[i]], (SlotT) 1);   // cannot carry: a count is below the group size
+                    todo[i] = false;
+                } else {
+                    h[i] = (h[i] + 1) & (TS - 1);
+                    any = true;
+                }
+            }
         }
+        if (any) atomicExch(s_overflow, 1u);   // crowded table: far more than UMAX distinct records
     }
     __syncthreads();
     for (uint32_t i0 = 0; i0 < (uint32_t) TS; i0 += THREADS) {
