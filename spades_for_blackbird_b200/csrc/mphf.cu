@@ -50,50 +50,78 @@ __global__ void __launch_bounds__(256) mphf_level0_kernel(const uint64_t *__rest
     active[i] = a;
 }
 
-// level l >= 1: keep the keys that were not placed at level l-1, insert them into level l (if l is a bit level)
+// level l >= 1: keep the keys that were not placed at level l-1, insert them into level l (if l is a bit level).
+// The survivors are appended to `out` with ONE global atomic per CTA pass of 1024 keys: a warp-aggregated atomic per 32 keys put
+// 2.3 M atomics on a single address for level 1 (all 73 M keys are examined there), and those serialise in L2 — 3.8 ms for a
+// kernel whose memory traffic is worth 0.4 ms (profiles/r1b launch list).  The order of the survivors does not matter: the bits a
+// level sets do not depend on it.
+constexpr int MPHF_LEVEL_ITEMS = 4;
 __global__ void __launch_bounds__(256) mphf_level_kernel(int level, const ActiveKey *__restrict__ in, const uint32_t *__restrict__ n_in,
                                                         ActiveKey *__restrict__ out, uint32_t *__restrict__ n_out,
                                                         const uint64_t *__restrict__ domain, const uint64_t *__restrict__ word_off,
                                                         unsigned long long *__restrict__ bits, unsigned long long *__restrict__ coll) {
+    constexpr int ITEMS = MPHF_LEVEL_ITEMS;
+    __shared__ uint32_t s_wcnt[8];
+    __shared__ uint32_t s_base;
     const uint32_t n = *n_in;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t base = (uint64_t) blockIdx.x * blockDim.x; base < n; base += (uint64_t) gridDim.x * blockDim.x) {
-        uint64_t i = base + threadIdx.x;
-        bool keep = false;
-        ActiveKey a;
-        if (i < n) a = in[i];
-        // Position this key probed at level-1.  For levels >= 2 the hash was xs_next() = new s1 + old s1, and after
-        // that call s0 holds the old s1, so it can be rebuilt from the saved state.
-        uint64_t prev_hash = 0;
-        if (i < n) {
-            if (level - 1 == 0) prev_hash = a.s0;
-            else if (level - 1 == 1) prev_hash = a.s1;
-            else prev_hash = a.s1 + a.s0;   // xs_next returned (new s1 + old s1); after the call s0 == old s1
-            uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS + (level - 1);
-            uint64_t pos = __umul64hi(prev_hash, domain[t]);
-            uint64_t w = word_off[t] + (pos >> 6);
-            unsigned long long bit = 1ULL << (pos & 63);
-            bool placed = (bits[w] & bit) && !(coll[w] & bit);
-            keep = !placed;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t) blockDim.x * ITEMS;
+    for (uint64_t base = (uint64_t) blockIdx.x * tile; base < n; base += (uint64_t) gridDim.x * tile) {
+        ActiveKey a[ITEMS];
+        bool keep[ITEMS];
+        uint32_t before[ITEMS];   // survivors of this warp ahead of this lane's item j
+        uint32_t wtotal = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint64_t i = base + (uint64_t) j * blockDim.x + threadIdx.x;
+            keep[j] = false;
+            if (i < n) {
+                a[j] = in[i];
+                // Position this key probed at level-1.  For levels >= 2 the hash was xs_next() = new s1 + old s1, and after
+                // that call s0 holds the old s1, so it can be rebuilt from the saved state.
+                uint64_t prev_hash;
+                if (level - 1 == 0) prev_hash = a[j].s0;
+                else if (level - 1 == 1) prev_hash = a[j].s1;
+                else prev_hash = a[j].s1 + a[j].s0;   // xs_next returned (new s1 + old s1); after the call s0 == old s1
+                const uint64_t t = (uint64_t) a[j].bucket * MPHF_LEVELS + (level - 1);
+                const uint64_t pos = __umul64hi(prev_hash, domain[t]);
+                const uint64_t w = word_off[t] + (pos >> 6);
+                const unsigned long long bit = 1ULL << (pos & 63);
+                const bool placed = (bits[w] & bit) && !(coll[w] & bit);
+                keep[j] = !placed;
+            }
         }
-        uint32_t m = __ballot_sync(0xffffffffu, keep);
-        uint32_t slot = 0;
-        if (m) {
-            if (lane == (__ffs(m) - 1)) slot = atomicAdd(n_out, (uint32_t) __popc(m));
-            slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t m = __ballot_sync(0xffffffffu, keep[j]);
+            before[j] = wtotal + (uint32_t) __popc(m & ((1u << lane) - 1u));
+            wtotal += (uint32_t) __popc(m);
         }
-        if (keep) {
+        if (lane == 0) s_wcnt[warp] = wtotal;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(n_out, tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t wbase = s_base + s_wcnt[warp];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (!keep[j]) continue;
             if (level < MPHF_LEVELS - 1) {
-                uint64_t h = (level == 1) ? a.s1 : xs_next(a.s0, a.s1);
-                uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS + level;
-                uint64_t pos = __umul64hi(h, domain[t]);
-                uint64_t w = word_off[t] + (pos >> 6);
-                unsigned long long bit = 1ULL << (pos & 63);
-                unsigned long long old = atomicOr(&bits[w], bit);
+                uint64_t h = (level == 1) ? a[j].s1 : xs_next(a[j].s0, a[j].s1);
+                const uint64_t t = (uint64_t) a[j].bucket * MPHF_LEVELS + level;
+                const uint64_t pos = __umul64hi(h, domain[t]);
+                const uint64_t w = word_off[t] + (pos >> 6);
+                const unsigned long long bit = 1ULL << (pos & 63);
+                const unsigned long long old = atomicOr(&bits[w], bit);
                 if (old & bit) atomicOr(&coll[w], bit);
             }
-            out[slot + __popc(m & ((1u << lane) - 1u))] = a;
+            out[wbase + before[j]] = a[j];
         }
+        __syncthreads();   // s_wcnt / s_base are rewritten by the next pass
     }
 }
 
@@ -200,7 +228,7 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
            (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
     ActiveKey *src = act_a.p, *dst = act_b.p;
-    unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256), (uint64_t) ctx->num_sms * 16);
+    unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256 * MPHF_LEVEL_ITEMS), (uint64_t) ctx->num_sms * 16);
     for (int l = 1; l < MPHF_LEVELS; ++l) {
         LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
                (unsigned long long *) m->bits.p, (unsigned long long *) coll.p);

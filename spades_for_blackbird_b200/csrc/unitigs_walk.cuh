@@ -147,10 +147,20 @@ __global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint
         kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
         too_long += __shfl_down_sync(0xffffffffu, too_long, d);
     }
+    // one set of global atomics per CTA (per-warp atomics on three addresses serialise in L2)
+    __shared__ unsigned long long s_tot[3];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-        if (chain_nodes) atomicAdd(&totals[0], chain_nodes);
-        if (too_long) atomicAdd(&totals[1], (unsigned long long) too_long);
-        if (kept_bases) atomicAdd(&totals[4], kept_bases);
+        if (chain_nodes) atomicAdd(&s_tot[0], chain_nodes);
+        if (too_long) atomicAdd(&s_tot[1], (unsigned long long) too_long);
+        if (kept_bases) atomicAdd(&s_tot[2], kept_bases);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tot[0]) atomicAdd(&totals[0], s_tot[0]);
+        if (s_tot[1]) atomicAdd(&totals[1], s_tot[1]);
+        if (s_tot[2]) atomicAdd(&totals[4], s_tot[2]);
     }
 }
 
@@ -246,10 +256,20 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
         too_long += __shfl_down_sync(0xffffffffu, too_long, d);
     }
+    // one set of global atomics per CTA (per-warp atomics on three addresses serialise in L2)
+    __shared__ unsigned long long s_tot[3];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-        if (chain_nodes) atomicAdd(&totals[0], chain_nodes);
-        if (too_long) atomicAdd(&totals[1], (unsigned long long) too_long);
-        if (kept_bases) atomicAdd(&totals[4], kept_bases);
+        if (chain_nodes) atomicAdd(&s_tot[0], chain_nodes);
+        if (too_long) atomicAdd(&s_tot[1], (unsigned long long) too_long);
+        if (kept_bases) atomicAdd(&s_tot[2], kept_bases);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tot[0]) atomicAdd(&totals[0], s_tot[0]);
+        if (s_tot[1]) atomicAdd(&totals[1], s_tot[1]);
+        if (s_tot[2]) atomicAdd(&totals[4], s_tot[2]);
     }
 }
 
