@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--k", type=int, default=55)
     ap.add_argument("--buckets", type=int, default=80)
-    ap.add_argument("--cpu-sample-reads", type=int, default=1_200_000,
+    ap.add_argument("--cpu-sample-reads", type=int, default=3_000_000,
                     help="reads of the workload the reference CPU path is timed on (about 10-20 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
