@@ -68,6 +68,7 @@ struct sb200_ctx {
     // SB200_TRACE=1: host-side wall time between trace points (each point drains the stream first), to stderr
     bool trace = false;
     double trace_t0 = 0;
+    bool group_chunk = false;       // SB200_GROUP_KERNEL=chunk: the sorting group kernel (segsort.cuh) instead of the hashing one (grouphash.cuh)
     bool no_mask_payload = false;   // SB200_NO_MASK_PAYLOAD=1: masks by MPHF lookups (fill_masks_kernel) even when the k-mer sort could carry them
     bool no_links = false;          // SB200_NO_LINKS=1: direct walks by MPHF lookup even when the link table applies (tests cover both)
     bool force_jump_path = false;   // SB200_FORCE_JUMP=1: always extract unitigs by pointer jumping (tests cover both paths)

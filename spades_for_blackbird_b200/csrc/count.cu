@@ -288,8 +288,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     DevBuf<uint32_t> group_unique(ctx, (uint64_t) n_groups + 1);
     DevBuf<uint32_t> cnt_full;   // multiplicity (or OR-ed mask bits) of the unique record at the same position of `other`
     if (want_counts || masks_mode) cnt_full.alloc(ctx, n);
-    static const bool use_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");   // A/B: the sorting kernel
-    if (use_chunk) {
+    if (ctx->group_chunk) {   // A/B and cross-check: the sorting kernel
     size_t smem = seg_chunk_smem<W>();
     if (want_counts) {
         auto seg_chunk_kernel_ = group_chunk_kernel<W, 1>;

@@ -22,7 +22,7 @@ constexpr int RS_BINS = 256;
 #define RS_ITEMS_W2 8
 #endif
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 3   // caps the scatter kernel at 85 registers: 96 registers / 2 CTAs per SM cost 25 % (profiles/r1b)
+#define RS_MIN_BLOCKS 4   // caps the scatter kernel at 64 registers (4 CTAs per SM): 96 registers / 2 CTAs cost 25 %, 85 / 3 another 3 % (profiles/r1b, r1c)
 #endif
 template<int W> struct RsItems { static constexpr int value = (W == 1) ? 16 : (W == 2) ? RS_ITEMS_W2 : 4; };
 

@@ -246,25 +246,64 @@ def test_clumpy_groups_take_several_rounds(ctx, k, nb, cov):
     assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
 
 
-def test_massively_repeated_kmer_falls_back_to_lsd(ctx):
-    """One read repeated 12 000 times: a single digit bin exceeds the shared-memory capacity, the group kernel raises its fail
-    flag and the set is redone by the generic LSD path — multiplicities included."""
+@pytest.mark.parametrize("copies", [12000, 70000])
+def test_massively_repeated_kmer(ctx, copies):
+    """One read repeated 12 000 / 70 000 times.  The hashing group kernel keeps one slot per DISTINCT record, so the multiplicity
+    does not matter to it (the sorting kernel overflowed its shared memory and sent the set to the LSD path); a group of 65535+
+    records (70 000 copies) goes to the 64-bit-slot instance of the kernel.  Multiplicities included."""
     genome = synth.random_genome(400, 11)
     base = synth.codes_to_strings(synth.sample_pairs(genome, 40, 100, 250, 0.0, 12))
-    reads = base + [base[0]] * 12000
+    reads = base + [base[0]] * copies
     k, nb = 31, 10
     want = O.gbuilder(reads, k, nb)
     streams, index, kpomers = build_index(ctx, reads, k, nb)
     assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
     assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
-    assert int(kpomers.counts().max()) >= 12000
+    assert int(kpomers.counts().max()) >= copies
     assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
     assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
 
 
+@pytest.mark.parametrize("k,nb,pairs,read_len", [(31, 1, 800, 100), (63, 2, 1280, 150)])
+def test_groups_of_mostly_distinct_records_take_tag_rounds(ctx, k, nb, pairs, read_len):
+    """Coverage ~1: almost every record of a group is distinct, so groups hold more than the 4096 distinct records one round of the
+    hashing kernel keeps; they are redone in rounds over disjoint tag ranges (grouphash.cuh).  Same sets, counts, unitigs."""
+    genome = synth.random_genome(300000, 900 + k)   # ~110 K instances per bucket: groups of ~7 K records, ~5 K of them distinct
+    codes = synth.sample_pairs(genome, pairs, read_len, 2 * read_len + 50, 0.002, 901 + k)
+    reads = synth.codes_to_strings(codes)
+    want = O.gbuilder(reads, k, nb)
+    streams, index, kpomers = build_index(ctx, reads, k, nb)
+    assert np.array_equal(kpomers.final_kmers(), want["kpomers"].data)
+    assert np.array_equal(kpomers.counts(), want["kpomers"].counts)
+    assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+    assert np.array_equal(index.data(), want["masks_idx"])
+    assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+
+
+def test_multi_k_on_resident_reads(ctx):
+    """BASELINE configs[2]: K = 21, 33, 55, 77 back to back on the SAME device-resident packed reads (the reference re-reads its binary
+    read files for every K; nothing else is shared between the iterations), each against the oracle."""
+    genome = synth.random_genome(20000, 77)
+    codes = synth.sample_pairs(genome, 2000, 150, 350, 0.005, 78)
+    reads = synth.codes_to_strings(codes)
+    words, word_off, lens = O.pack_reads(reads)
+    streams = B.ReadStreams(ctx, words, word_off, lens)
+    for k in (21, 33, 55, 77):
+        want = O.gbuilder(reads, k, 80)
+        index = B.DeBruijnExtensionIndex(ctx, k)
+        kp = B.DeBruijnExtensionIndexBuilder().BuildExtensionIndexFromStream(index, streams, num_buckets=80)
+        assert np.array_equal(kp.final_kmers(), want["kpomers"].data)
+        assert np.array_equal(kp.counts(), want["kpomers"].counts)
+        assert np.array_equal(index.kmers.final_kmers(), want["kmers"].data)
+        assert np.array_equal(index.data(), want["masks_idx"])
+        assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
+        index.free(); kp.free()
+
+
 def test_low_complexity_reads_overflow_a_segment(ctx):
     """Reads that are 90 % A: thousands of distinct k-mers share their leading bits, one shared-memory segment holds more
-    distinct values than a warp keeps in registers, the fail flag sends the set to the generic LSD path."""
+    distinct values than a warp of the sorting kernel keeps in registers (fail flag -> LSD path); the hashing kernel bins them by the
+    key bits below the shared prefix and takes tag rounds when a group holds too many."""
     rng = np.random.default_rng(5)
     reads = ["".join("ACGT"[c] for c in np.where(rng.random(70) < 0.9, 0, rng.integers(0, 4, 70))) for _ in range(4000)]
     k, nb = 21, 10
@@ -279,8 +318,8 @@ def test_low_complexity_reads_overflow_a_segment(ctx):
 def test_baseline_config2_full_size(monkeypatch):
     """BASELINE configs[1] at full size (4.6 Mbp genome, 2x150 at 100x, k = 55, 80 buckets: 291 M (k+1)-mer instances) — far
     beyond what the oracle does in seconds, so: size-independent properties of the tables, and the two independent
-    implementations of the graph stage must agree (masks OR-ed inside the sort + link-table walks  vs.  masks by MPHF lookups
-    + lookup walks)."""
+    implementations of the path must agree (hashing group kernel + masks OR-ed inside the sort + link-table walks  vs.  sorting
+    group kernel + masks by MPHF lookups + lookup walks)."""
     import hashlib
     k, nb = 55, 80
     words, word_off, lens = synth.isolate_config()
@@ -321,6 +360,7 @@ def test_baseline_config2_full_size(monkeypatch):
         ctx1.close()
     monkeypatch.setenv("SB200_NO_MASK_PAYLOAD", "1")
     monkeypatch.setenv("SB200_NO_LINKS", "1")
+    monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
     ctx2 = B.Context(0)
     try:
         streams, index, kp, (w, off, ln) = run(ctx2)
