@@ -211,10 +211,20 @@ __global__ void double_palindromes_kernel(const uint64_t *__restrict__ recs, uin
     if (kmer_eq<W>(x, r)) counts[i] *= 2;
 }
 
+// The same table from the group offsets of the grouped path: group g = bucket << p | prefix, so bucket b starts where its first
+// group starts (no pass over the records, no hash per record)
+__global__ void bucket_starts_from_groups_kernel(const uint32_t *__restrict__ group_off, int p, uint32_t B, uint64_t u, uint64_t *__restrict__ starts) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    starts[b] = (b < B) ? (uint64_t) group_off[(uint64_t) b << p] : u;
+    if (b < B && starts[b] > u) starts[b] = u;   // a dropped marker record was the last record of the last bucket
+}
+
 template<int W>
-static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B) {
+static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B, const uint32_t *group_off = nullptr, int p = 0) {
     s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
-    LAUNCH(ctx, bucket_starts_kernel<W>, div_up(s->size, 256), 256, 0, s->data.p, s->size, B, s->bucket_starts.p);
+    if (group_off) LAUNCH(ctx, bucket_starts_from_groups_kernel, div_up((uint64_t) B + 1, 256), 256, 0, group_off, p, B, s->size, s->bucket_starts.p);
+    else LAUNCH(ctx, bucket_starts_kernel<W>, div_up(s->size, 256), 256, 0, s->data.p, s->size, B, s->bucket_starts.p);
     s->bucket_starts_host.resize((size_t) B + 1);
     ctx->fetch(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -361,7 +371,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     s->size = u;
     if (want_counts && double_palindromes && (K % 2 == 0))
         LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
-    finish_tables<W>(ctx, s, B);
+    finish_tables<W>(ctx, s, B, group_unique.p, p);   // group_unique holds the exclusive scan of the per-group unique counts
     inst.release();
     ctx->trace_point("  shrink + tables");
     return s;

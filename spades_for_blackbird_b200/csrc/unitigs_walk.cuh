@@ -24,29 +24,55 @@ __device__ __forceinline__ uint32_t walk_mask(const MphfDev &m, const uint8_t *_
     return minimal ? raw : mask_conj(raw);
 }
 
-// out-degree of every oriented junction (0 for everything else); t = 2 * (file index - first) + strand
-__global__ void __launch_bounds__(256) junction_degree_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
-                                                             uint32_t *__restrict__ deg) {
-    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n) return;
-    uint32_t raw = masks[idx[t >> 1]];
-    uint32_t mk = (t & 1) ? mask_conj(raw) : raw;
-    deg[t] = mask_is_junction(raw) ? (uint32_t) __popc(mk & 15u) : 0u;
+// Work list of start edges, in the reference's discovery order: every outgoing edge of every oriented junction, t = 2 * (file index -
+// first) + strand, elist[e] = (t << 2) | nucleotide.  Two passes over tiles of 1024 oriented vertices — count, scan of the tile counts,
+// emit with a block scan inside the tile — so nothing of the size of the vertex set is written (the first version stored and scanned a
+// degree per oriented vertex: 2.3 GB of traffic for a 29 MB list).  `file_masks` (masks in file order, a coalesced read) replaces the
+// random masks[idx[.]] reads when the index-order array has not been edited by the tip clipper.
+constexpr int EL_ITEMS = 4;
+constexpr int EL_TILE = 256 * EL_ITEMS;
+
+__device__ __forceinline__ uint32_t junction_out_mask(uint64_t t, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
+                                                      const uint8_t *__restrict__ file_masks) {
+    const uint32_t raw = file_masks ? (uint32_t) __ldg(file_masks + (t >> 1)) : (uint32_t) __ldg(masks + __ldg(idx + (t >> 1)));
+    if (!mask_is_junction(raw)) return 0u;
+    return ((t & 1) ? mask_conj(raw) : raw) & 15u;
 }
 
-// work list: elist[e] = (t << 2) | nucleotide
+__global__ void __launch_bounds__(256) junction_degree_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
+                                                             const uint8_t *__restrict__ file_masks, uint32_t *__restrict__ tile_cnt) {
+    __shared__ uint32_t sm[256 / 32 + 1];
+    const uint64_t t0 = (uint64_t) blockIdx.x * EL_TILE + (uint64_t) threadIdx.x * EL_ITEMS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < EL_ITEMS; ++i)
+        if (t0 + i < 2 * n) c += (uint32_t) __popc(junction_out_mask(t0 + i, idx, masks, file_masks));
+    uint32_t total;
+    block_exclusive_scan<uint32_t, 256>(c, &total, sm);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
 __global__ void __launch_bounds__(256) edge_list_kernel(uint64_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ masks,
-                                                       const uint32_t *__restrict__ deg_scan, uint32_t *__restrict__ elist) {
-    uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n) return;
-    uint32_t raw = masks[idx[t >> 1]];
-    if (!mask_is_junction(raw)) return;
-    uint32_t mk = ((t & 1) ? mask_conj(raw) : raw) & 15u;
-    uint32_t o = deg_scan[t];
-    while (mk) {
-        uint32_t c = (uint32_t) __ffs((int) mk) - 1u;
-        mk &= mk - 1u;
-        elist[o++] = ((uint32_t) t << 2) | c;
+                                                       const uint8_t *__restrict__ file_masks, const uint32_t *__restrict__ tile_off,
+                                                       uint32_t *__restrict__ elist) {
+    __shared__ uint32_t sm[256 / 32 + 1];
+    const uint64_t t0 = (uint64_t) blockIdx.x * EL_TILE + (uint64_t) threadIdx.x * EL_ITEMS;
+    uint32_t mk[EL_ITEMS], c = 0;
+#pragma unroll
+    for (int i = 0; i < EL_ITEMS; ++i) {
+        mk[i] = (t0 + i < 2 * n) ? junction_out_mask(t0 + i, idx, masks, file_masks) : 0u;
+        c += (uint32_t) __popc(mk[i]);
+    }
+    uint32_t total;
+    uint32_t o = tile_off[blockIdx.x] + block_exclusive_scan<uint32_t, 256>(c, &total, sm);
+#pragma unroll
+    for (int i = 0; i < EL_ITEMS; ++i) {
+        uint32_t m = mk[i];
+        while (m) {
+            const uint32_t nuc = (uint32_t) __ffs((int) m) - 1u;
+            m &= m - 1u;
+            elist[o++] = ((uint32_t) (t0 + i) << 2) | nuc;
+        }
     }
 }
 
@@ -408,15 +434,19 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     SB200_REQUIRE(2 * n_range < (1ull << 30), "more than 2^29 k-mers in one extraction range: shard the input");
     WalkStats st;
     uint64_t nt = 2 * n_range;
-    DevBuf<uint32_t> deg(ctx, nt + 1);
+    const uint32_t n_tiles = (uint32_t) div_up(std::max<uint64_t>(nt, 1), EL_TILE);
+    DevBuf<uint32_t> deg(ctx, (uint64_t) n_tiles + 1);   // start edges per tile of EL_TILE oriented vertices, then their exclusive scan
+    // masks in file order (a coalesced read) are valid as long as tip clipping has not edited the index-order array
+    const uint8_t *fm = (kmers->masks_file.p && !ext->masks_edited) ? kmers->masks_file.p + first : nullptr;
     DevBuf<uint32_t> tot32(ctx, 2);
     DevBuf<unsigned long long> totals(ctx, 6);   // [0] chain vertices seen [1] long chains [2] total words [3] non-junction k-mers [4] bases
     totals.zero();
     DevBuf<uint32_t> work(ctx, 4);               // work-queue heads of the persistent walk kernels: [0] measure, [1] emit
     work.zero();
     const unsigned walk_grid = (unsigned) ctx->num_sms * 6;
-    if (nt) LAUNCH(ctx, junction_degree_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p);
-    exclusive_scan<uint32_t>(ctx, deg.p, nt, tot32.p);
+    if (nt) LAUNCH(ctx, junction_degree_kernel, n_tiles, 256, 0, n_range, ext->idx.p + first, ext->masks.p, fm, deg.p);
+    else deg.zero();
+    exclusive_scan<uint32_t>(ctx, deg.p, n_tiles, tot32.p);
     ctx->fetch(&st.n_edges, tot32.p, 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     uint32_t n_e = st.n_edges;
@@ -428,12 +458,10 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     const bool use_links = !ctx->no_links && first == 0 && last == n && ext->n_local == ext->size && ext->inv.p != nullptr && 2 * n <= LINK_POS_MASK;
     DevBuf<uint32_t> link, efirst;
     if (n_e) {
-        LAUNCH(ctx, edge_list_kernel, div_up(nt, 256), 256, 0, n_range, ext->idx.p + first, ext->masks.p, deg.p, elist.p);
+        LAUNCH(ctx, edge_list_kernel, n_tiles, 256, 0, n_range, ext->idx.p + first, ext->masks.p, fm, deg.p, elist.p);
         if (use_links) {
             link.alloc(ctx, 2 * n);
             efirst.alloc(ctx, (uint64_t) n_e + 1);
-            // masks in file order (a coalesced read) are valid as long as tip clipping has not edited the index-order array
-            const uint8_t *fm = (kmers->masks_file.p && !ext->masks_edited) ? kmers->masks_file.p : nullptr;
             LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, fm, link.p);
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
                    kflag.p, ewords.p, totals.p);
