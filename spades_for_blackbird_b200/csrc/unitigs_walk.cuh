@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(256) links_kernel(MphfDev m, const uint64_t *_
 template<int W>
 __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                                 uint32_t n_e, const uint32_t *__restrict__ inv, const uint32_t *__restrict__ link,
-                                                                uint32_t *__restrict__ elen, uint32_t *__restrict__ efirst, uint32_t *__restrict__ kflag,
+                                                                uint32_t *__restrict__ elen, uint32_t *__restrict__ efirst,
+                                                                unsigned long long *__restrict__ ebases, uint32_t *__restrict__ kflag,
                                                                 unsigned long long *__restrict__ ewords, unsigned long long *__restrict__ totals) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long chain_nodes = 0, kept_bases = 0;
@@ -256,8 +257,10 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
         uint32_t nn = 1;
         uint32_t L = __ldg(link + v);
+        unsigned long long bases = 0;   // the first 32 nucleotides the chain appends after c: the emitting walk of a short path needs no link reads
         while (L != LINK_JUNCTION) {
             if (nn > WALK_LIMIT) { too_long = 1; break; }
+            if (nn <= 32) bases |= (unsigned long long) ((L >> 28) & 3u) << (2 * (nn - 1));
             prev_first = L >> 30;
             v = L & LINK_POS_MASK;
             L = __ldg(link + v);
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
             if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
         }
         elen[e] = len;
+        if (len) ebases[e] = bases;
         kflag[e] = len ? 1u : 0u;
         ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
     }
@@ -303,6 +307,7 @@ template<int W>
 __global__ void __launch_bounds__(256) walk_emit_links_kernel(const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                              const uint32_t *__restrict__ klist, uint32_t n_kept, const uint32_t *__restrict__ link,
                                                              const uint32_t *__restrict__ elen, const uint32_t *__restrict__ efirst,
+                                                             const unsigned long long *__restrict__ ebases,
                                                              const unsigned long long *__restrict__ ewords_scan, uint32_t *__restrict__ seq_len,
                                                              uint64_t *__restrict__ seq_word_off, uint64_t *__restrict__ out_words) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,11 +335,16 @@ __global__ void __launch_bounds__(256) walk_emit_links_kernel(const uint64_t *__
         if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
     };
     push(c);
-    uint32_t v = efirst[e];
-    for (uint32_t s = 1; s < nn; ++s) {
-        const uint32_t lw = __ldg(link + v);
-        push((lw >> 28) & 3u);
-        v = lw & LINK_POS_MASK;
+    if (nn <= 33) {   // short path: the measuring walk left its nucleotides
+        unsigned long long bases = ebases[e];
+        for (uint32_t s = 1; s < nn; ++s) { push((uint32_t) bases & 3u); bases >>= 2; }
+    } else {
+        uint32_t v = efirst[e];
+        for (uint32_t s = 1; s < nn; ++s) {
+            const uint32_t lw = __ldg(link + v);
+            push((lw >> 28) & 3u);
+            v = lw & LINK_POS_MASK;
+        }
     }
     if (pos & 31) out_words[woff + (pos >> 5)] = acc;
 }
@@ -457,14 +467,16 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     // large for 28-bit positions) walks by MPHF lookups instead
     const bool use_links = !ctx->no_links && first == 0 && last == n && ext->n_local == ext->size && ext->inv.p != nullptr && 2 * n <= LINK_POS_MASK;
     DevBuf<uint32_t> link, efirst;
+    DevBuf<unsigned long long> ebases;
     if (n_e) {
         LAUNCH(ctx, edge_list_kernel, n_tiles, 256, 0, n_range, ext->idx.p + first, ext->masks.p, fm, deg.p, elist.p);
         if (use_links) {
             link.alloc(ctx, 2 * n);
             efirst.alloc(ctx, (uint64_t) n_e + 1);
+            ebases.alloc(ctx, (uint64_t) n_e + 1);
             LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, fm, link.p);
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
-                   kflag.p, ewords.p, totals.p);
+                   ebases.p, kflag.p, ewords.p, totals.p);
         } else {
             LAUNCH(ctx, walk_measure_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p,
                    work.p);
@@ -492,7 +504,7 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
         LAUNCH(ctx, kept_list_kernel, div_up(n_e, 256), 256, 0, kflag.p, elen.p, n_e, klist.p);
         if (use_links)
             LAUNCH(ctx, walk_emit_links_kernel<W>, div_up(st.n_kept, 256), 256, 0, kbase, k, elist.p, klist.p, st.n_kept, link.p, elen.p, efirst.p,
-                   ewords.p, out->len.p, out->word_off.p, out->words.p);
+                   ebases.p, ewords.p, out->len.p, out->word_off.p, out->words.p);
         else
             LAUNCH(ctx, walk_emit_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
                    out->len.p, out->word_off.p, out->words.p, work.p + 1);
