@@ -139,6 +139,10 @@ int  sb200_records_flags(const sb200_records *r);        /* bit 0: double_palind
 uint64_t *sb200_records_device(sb200_records *r);        /* device pointer to n * words uint64 */
 void sb200_records_free(sb200_records *r);
 int  sb200_count_records(sb200_ctx *ctx, sb200_records *r /* consumed */, unsigned num_buckets, int want_counts, sb200_kmers **out);
+/* The same when every record lies in the buckets [first_bucket, first_bucket + n_owned) — the owner's share after the exchange: the
+ * grouping key then spends its bits on the value prefix instead of buckets this GPU does not own (same result, fewer oversize groups). */
+int  sb200_count_records_owned(sb200_ctx *ctx, sb200_records *r /* consumed */, unsigned num_buckets, unsigned first_bucket, unsigned n_owned,
+                               int want_counts, sb200_kmers **out);
 int  sb200_mphf_build_sharded(sb200_ctx *ctx, const sb200_kmers *local_kmers, const uint64_t *global_bucket_sizes /* B */, sb200_mphf **out);
 int  sb200_mphf_arrays(const sb200_mphf *m, uint64_t **bits, uint64_t *n_words, uint64_t **ranks, uint64_t *n_ranks);   /* device */
 int  sb200_ext_masks_device(const sb200_ext *e, uint8_t **masks, uint64_t *size_padded);                                /* device */

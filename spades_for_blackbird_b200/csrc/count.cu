@@ -213,17 +213,22 @@ __global__ void double_palindromes_kernel(const uint64_t *__restrict__ recs, uin
 
 // The same table from the group offsets of the grouped path: group g = bucket << p | prefix, so bucket b starts where its first
 // group starts (no pass over the records, no hash per record)
-__global__ void bucket_starts_from_groups_kernel(const uint32_t *__restrict__ group_off, int p, uint32_t B, uint64_t u, uint64_t *__restrict__ starts) {
+__global__ void bucket_starts_from_groups_kernel(const uint32_t *__restrict__ group_off, int p, uint32_t B, uint32_t first_bucket, uint32_t n_owned,
+                                                 uint64_t u, uint64_t *__restrict__ starts) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > B) return;
-    starts[b] = (b < B) ? (uint64_t) group_off[(uint64_t) b << p] : u;
-    if (b < B && starts[b] > u) starts[b] = u;   // a dropped marker record was the last record of the last bucket
+    uint64_t v = u;                                             // buckets behind the owned range, and the end of the table
+    if (b < first_bucket) v = 0;                                // buckets ahead of the owned range are empty
+    else if (b < first_bucket + n_owned) v = group_off[(uint64_t) (b - first_bucket) << p];
+    starts[b] = v > u ? u : v;                                  // a dropped marker record was the last record of the last bucket
 }
 
 template<int W>
-static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B, const uint32_t *group_off = nullptr, int p = 0) {
+static void finish_tables(sb200_ctx *ctx, sb200_kmers *s, uint32_t B, const uint32_t *group_off = nullptr, int p = 0, uint32_t first_bucket = 0,
+                          uint32_t n_owned = 0) {
     s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
-    if (group_off) LAUNCH(ctx, bucket_starts_from_groups_kernel, div_up((uint64_t) B + 1, 256), 256, 0, group_off, p, B, s->size, s->bucket_starts.p);
+    if (group_off) LAUNCH(ctx, bucket_starts_from_groups_kernel, div_up((uint64_t) B + 1, 256), 256, 0, group_off, p, B, first_bucket, n_owned, s->size,
+                          s->bucket_starts.p);
     else LAUNCH(ctx, bucket_starts_kernel<W>, div_up(s->size, 256), 256, 0, s->data.p, s->size, B, s->bucket_starts.p);
     s->bucket_starts_host.resize((size_t) B + 1);
     ctx->fetch(s->bucket_starts_host.data(), s->bucket_starts.p, ((size_t) B + 1) * 8);
@@ -262,7 +267,10 @@ static void launch_group_hash(sb200_ctx *ctx, int mode, uint32_t n_groups, const
 // comes with masks_file.
 template<int W>
 static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
-                               bool double_palindromes, bool drop_marker, int pshift = -1) {
+                               bool double_palindromes, bool drop_marker, int pshift = -1, uint32_t first_bucket = 0, uint32_t n_owned = 0) {
+    // [first_bucket, first_bucket + n_owned): the buckets the records can lie in (sharded path: this GPU's share; 0 = all B).  The group
+    // key counts buckets from first_bucket, so that its 16 bits (two counting passes) go to the value prefix instead of empty buckets.
+    if (n_owned == 0) { first_bucket = 0; n_owned = B; }
     SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     const uint64_t lw_keep = last_word_mask(K);
     const bool masks_mode = pshift >= 0 && !want_counts;
@@ -273,17 +281,17 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     using Cfg = SegCfg<W>;
     const int top = (W == 1) ? 2 * K : 64;
     int bbits = 0;
-    while ((1ull << bbits) < B) ++bbits;
+    while ((1ull << bbits) < n_owned) ++bbits;
     const int pmax = std::min(24 - std::min(bbits, 24), top - 8);
     int p = 0;
-    while (p < pmax && (double) n / (double) ((uint64_t) B << p) > (double) Cfg::TARGET) ++p;
-    const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
+    while (p < pmax && (double) n / (double) ((uint64_t) n_owned << p) > (double) Cfg::TARGET) ++p;
+    const uint32_t n_groups = (uint32_t) ((uint64_t) n_owned << p);
     const int dshift = top - p - 8;
-    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top, lw_keep};
+    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top, lw_keep, first_bucket};
 
     DevBuf<uint64_t> scratch(ctx, n * W);
     ctx->trace_point("  instances ready");
-    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker, lw_keep));
+    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker, lw_keep, first_bucket));
     ctx->trace_point("  group passes");
     uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
 
@@ -371,7 +379,7 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     s->size = u;
     if (want_counts && double_palindromes && (K % 2 == 0))
         LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
-    finish_tables<W>(ctx, s, B, group_unique.p, p);   // group_unique holds the exclusive scan of the per-group unique counts
+    finish_tables<W>(ctx, s, B, group_unique.p, p, first_bucket, n_owned);   // group_unique holds the exclusive scan of the per-group unique counts
     inst.release();
     ctx->trace_point("  shrink + tables");
     return s;
@@ -591,17 +599,18 @@ void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_
     }
 }
 
-sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts) {
+sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned) {
     SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
+    SB200_REQUIRE((uint64_t) first_bucket + n_owned <= B, "owned bucket range exceeds num_buckets");
     SB200_REQUIRE(r->n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     sb200_kmers *s;
     SB200_REQUIRE(!(r->mask_payload && want_counts), "records with a mask payload cannot be counted");
     const int pshift = r->mask_payload ? 2 * ((int) r->k - 32 * ((int) r->words - 1)) : -1;
     switch (r->words) {
-        case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
-        case 2: s = finish_set<2>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
-        case 3: s = finish_set<3>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
-        default: s = finish_set<4>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift); break;
+        case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift, first_bucket, n_owned); break;
+        case 2: s = finish_set<2>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift, first_bucket, n_owned); break;
+        case 3: s = finish_set<3>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift, first_bucket, n_owned); break;
+        default: s = finish_set<4>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift, first_bucket, n_owned); break;
     }
     if (!want_counts) s->instances = 0;
     r->n = 0;

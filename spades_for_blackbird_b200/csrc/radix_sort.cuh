@@ -36,6 +36,7 @@ struct DigitSel {
     int p;        // composite only: prefix bits of the value
     int top;      // composite only: significant bits of word 0 (64, or 2K for one-word records)
     uint64_t lw_keep = ~0ULL;   // bits of the LAST word that belong to the k-mer (the padding above may carry a payload, count.cu)
+    uint32_t bucket_base = 0;   // composite only: first bucket this GPU owns (sharded path: every record lies in an owned bucket)
 };
 
 template<int W>
@@ -57,7 +58,7 @@ __device__ __forceinline__ uint32_t rs_bucket(const uint64_t *r, const DigitSel 
 template<int W>
 __device__ __forceinline__ uint32_t rs_composite(const uint64_t *r, const DigitSel &d) {
     const uint32_t pre = d.p ? (uint32_t) ((r[0] >> (d.top - d.p)) & ((1ULL << d.p) - 1ULL)) : 0u;
-    return (rs_bucket<W>(r, d) << d.p) | pre;
+    return ((rs_bucket<W>(r, d) - d.bucket_base) << d.p) | pre;
 }
 
 template<int W>
@@ -303,9 +304,9 @@ inline std::vector<DigitSel> full_passes(int W, int K, uint32_t num_buckets, boo
 }
 
 // the composite group key (segsort.cuh), least significant byte first: `bits` = bucket bits + p
-inline std::vector<DigitSel> composite_passes(int bits, int p, int top, uint32_t num_buckets, bool marker, uint64_t lw_keep) {
+inline std::vector<DigitSel> composite_passes(int bits, int p, int top, uint32_t num_buckets, bool marker, uint64_t lw_keep, uint32_t bucket_base = 0) {
     std::vector<DigitSel> passes;
-    for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{-3, s, num_buckets, marker ? 1 : 0, p, top, lw_keep});
+    for (int s = 0; s < bits; s += 8) passes.push_back(DigitSel{-3, s, num_buckets, marker ? 1 : 0, p, top, lw_keep, bucket_base});
     return passes;
 }
 

@@ -13,7 +13,7 @@ namespace sb200 {
 sb200_records *extract_records(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc);
 sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp);
 void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
-sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts);
+sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
 sb200_unitigs *extract_unitigs_local(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, uint64_t *stats);
 }  // namespace sb200
@@ -70,7 +70,12 @@ void sb200_records_free(sb200_records *r) {
 }
 int sb200_count_records(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, int want_counts, sb200_kmers **out) {
     *out = nullptr;
-    return guarded(ctx, [&] { *out = sb200::count_records(ctx, r, num_buckets, want_counts); });
+    return guarded(ctx, [&] { *out = sb200::count_records(ctx, r, num_buckets, want_counts, 0, 0); });
+}
+int sb200_count_records_owned(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, unsigned first_bucket, unsigned n_owned, int want_counts,
+                              sb200_kmers **out) {
+    *out = nullptr;
+    return guarded(ctx, [&] { *out = sb200::count_records(ctx, r, num_buckets, want_counts, first_bucket, n_owned); });
 }
 
 int sb200_mphf_build_sharded(sb200_ctx *ctx, const sb200_kmers *local_kmers, const uint64_t *global_bucket_sizes, sb200_mphf **out) {

@@ -102,6 +102,7 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_records_device": (vp, [vp]),
     "sb200_records_free": (None, [vp]),
     "sb200_count_records": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.POINTER(vp)]),
+    "sb200_count_records_owned": (C.c_int, [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.POINTER(vp)]),
     "sb200_mphf_build_sharded": (C.c_int, [vp, vp, u64p, C.POINTER(vp)]),
     "sb200_mphf_arrays": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(vp), u64p]),
     "sb200_ext_masks_device": (C.c_int, [vp, C.POINTER(vp), u64p]),

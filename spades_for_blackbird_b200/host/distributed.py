@@ -199,10 +199,15 @@ class GpuShardBackend:
         w = self.lib.sb200_records_words(rec)
         return rec, cuda_view(self.lib.sb200_records_device(rec), max(n * w, 1), "<i8", self.device)[:n * w]
 
-    def count_records(self, rec, num_buckets, want_counts):
+    def count_records(self, rec, num_buckets, want_counts, owned=None):
+        """owned = (first_bucket, n_owned): the bucket range every received record lies in (this rank's share)"""
         h = B.vp()
         try:
-            self.ctx.check(self.lib.sb200_count_records(self.ctx.h, rec, num_buckets, int(want_counts), C.byref(h)))
+            if owned is None:
+                self.ctx.check(self.lib.sb200_count_records(self.ctx.h, rec, num_buckets, int(want_counts), C.byref(h)))
+            else:
+                self.ctx.check(self.lib.sb200_count_records_owned(self.ctx.h, rec, num_buckets, int(owned[0]), int(owned[1]), int(want_counts),
+                                                                  C.byref(h)))
         finally:
             self.lib.sb200_records_free(rec)
         return B.KMerDiskStorage(self.ctx, h)
@@ -289,7 +294,8 @@ def count_shard(backend, comm, make_records, K, num_buckets, want_counts, double
         comm.all_to_all_v(view, counts, width, alloc=alloc)
         backend.sync()   # the collective ran on torch's / NCCL's stream; the library works on its own
         backend.free_records(rec)
-        return backend.count_records(holder["rec"], num_buckets, want_counts)
+        n_owned = num_buckets // comm.size   # owner g holds buckets [g B/G, (g+1) B/G): sb200_records_partition's owner function
+        return backend.count_records(holder["rec"], num_buckets, want_counts, owned=(comm.rank * n_owned, n_owned))
     recv, recv_counts = comm.all_to_all_v(view, counts, width)
     backend.sync()
     backend.free_records(rec)
