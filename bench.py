@@ -10,7 +10,8 @@ A step = one pass of the whole hot path over that read set:
 `value`  : input bases / device time with the packed reads already resident in HBM (CUDA events on the library's stream)
 `e2e`    : the same through sb200_construct() with pinned HOST buffers on both sides (H2D of the reads and D2H of
            (k+1)-mers + counts, k-mers, masks, MPHF and unitigs inside the timed region)
-`roofline`: the dominant kernel (LSD radix scatter pass) — algorithmic bytes per launch / its mean launch duration,
+`e2e_graph_only`: the same call without the two k-mer tables (masks, index and unitigs come home; the tables stay on the device)
+`roofline`: the kernel with the largest measured share of the step — algorithmic bytes per launch / its mean launch duration,
            measured live with CUDA events around every launch of the timed steps
 `cpu_baseline` / --impl reference: the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from /root/reference)
            on the box's host cores over a bounded sample of the same read set.
