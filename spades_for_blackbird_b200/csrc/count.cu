@@ -356,7 +356,8 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     s->data.alloc(ctx, u * W);   // right-sized: the instance-sized ping-pong buffers go back to the allocator
     if (want_counts) {
         s->counts.alloc(ctx, u);
-        LAUNCH(ctx, (seg_compact_kernel<W, 1>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p, s->counts.p);
+        LAUNCH(ctx, (seg_compact_kernel<W, 1>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p, s->counts.p,
+               (double_palindromes && (K % 2 == 0)) ? K : 0);
     } else if (masks_mode) {
         s->masks_file.alloc(ctx, u + 4);
         LAUNCH(ctx, (seg_compact_kernel<W, 2>), n_groups, 256, 0, other, cnt_full.p, ranges.p, group_unique.p, n_groups, u32, s->data.p,
@@ -377,8 +378,6 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
         }
     }
     s->size = u;
-    if (want_counts && double_palindromes && (K % 2 == 0))
-        LAUNCH(ctx, double_palindromes_kernel<W>, div_up(u, 256), 256, 0, s->data.p, u, K, s->counts.p);
     finish_tables<W>(ctx, s, B, group_unique.p, p, first_bucket, n_owned);   // group_unique holds the exclusive scan of the per-group unique counts
     inst.release();
     ctx->trace_point("  shrink + tables");

@@ -100,12 +100,13 @@ __device__ __forceinline__ uint32_t seg_tag(uint64_t w0, int shift) {
 
 // Moves the unique records every group packed at the front of its own range to their final, contiguous place.
 // One CTA per group; tile_off = exclusive scan of the per-group unique counts.
-// MODE: 0 records only, 1 + multiplicities (uint32), 2 + OR-ed mask payload (out_cnt points to bytes)
+// MODE: 0 records only, 1 + multiplicities (uint32; double_pal_K = K doubles those of self-reverse-complement records), 2 + OR-ed
+// mask payload (out_cnt points to bytes)
 template<int W, int MODE>
 __global__ void __launch_bounds__(256) seg_compact_kernel(const uint64_t *__restrict__ tmp, const uint32_t *__restrict__ tmp_cnt,
                                                          const ChunkRange *__restrict__ ranges, const uint32_t *__restrict__ tile_off,
                                                          uint32_t n_chunks, uint32_t total, uint64_t *__restrict__ out,
-                                                         uint32_t *__restrict__ out_cnt) {
+                                                         uint32_t *__restrict__ out_cnt, int double_pal_K = 0) {
     const uint32_t b = blockIdx.x;
     const uint32_t o = tile_off[b];
     const uint32_t cnt = (b + 1 < n_chunks ? tile_off[b + 1] : total) - o;
@@ -114,7 +115,15 @@ __global__ void __launch_bounds__(256) seg_compact_kernel(const uint64_t *__rest
         uint64_t r[W];
         load_rec<W>(tmp, src + i, r);
         store_rec<W>(out, (uint64_t) o + i, r);
-        if (MODE == 1) out_cnt[o + i] = tmp_cnt[src + i];
+        if (MODE == 1) {
+            uint32_t c = tmp_cnt[src + i];
+            if (double_pal_K) {   // a self-reverse-complement record is seen by both of the reference's streams: count it twice (count.cu)
+                uint64_t rc[W];
+                kmer_rc<W>(r, double_pal_K, rc);
+                if (kmer_eq<W>(r, rc)) c *= 2;
+            }
+            out_cnt[o + i] = c;
+        }
         if (MODE == 2) reinterpret_cast<uint8_t *>(out_cnt)[o + i] = (uint8_t) tmp_cnt[src + i];
     }
 }
