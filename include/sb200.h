@@ -131,6 +131,10 @@ typedef struct sb200_records sb200_records;   /* unsorted k-mer instances on the
 int  sb200_records_extract(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, sb200_records **out);
 int  sb200_records_derive(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_records **out);
 int  sb200_records_partition(sb200_ctx *ctx, sb200_records *r, unsigned num_buckets, unsigned n_owners, uint64_t *counts_out /* n_owners */);
+/* records_extract + records_partition in one step: for the canonical modes the extraction itself stores every record at its owner's
+ * cursor (count pass, scan, write pass) and the instances cross HBM once; the order inside an owner's group is unspecified. */
+int  sb200_records_extract_partitioned(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, unsigned num_buckets,
+                                       unsigned n_owners, uint64_t *counts_out /* n_owners */, sb200_records **out);
 int  sb200_records_alloc(sb200_ctx *ctx, uint64_t n, unsigned K, int flags /* = sb200_records_flags of the senders */, sb200_records **out);
 uint64_t sb200_records_size(const sb200_records *r);
 unsigned sb200_records_words(const sb200_records *r);

@@ -523,6 +523,125 @@ static sb200_records *extract_records_w(sb200_ctx *ctx, const sb200_reads *rd, i
     return r;
 }
 
+// ---- extraction straight into the owner groups (canonical modes: one record per window) ----------------------------------
+// extract + partition_records read and wrote every instance twice more (histogram pass, scatter pass) just to group them by owner.
+// Here the extraction itself does it: a first pass counts, per read and owner, the windows that belong to that owner (the same warp
+// per read, nothing written but G counters per read); after one scan of the [owner][read] matrix a second pass recomputes the windows
+// and stores every record at its owner's cursor, ranked inside the warp with one ballot per owner.  Instances cross HBM once.
+constexpr int MAX_FUSED_OWNERS = 32;
+
+template<int W>
+__device__ __forceinline__ uint32_t window_owner(const uint64_t *seq, uint32_t nw, uint32_t p, int K, int mode, uint32_t B, uint32_t G, uint64_t *y) {
+    uint64_t x[W];
+    kmer_window<W>(seq, nw, p, K, x);
+    const bool minimal = kmer_canonical<W>(x, K, y);
+    uint32_t b;
+    if (mode == MODE_CANON_FWD && !minimal) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) y[j] = ~0ULL;   // marker: belongs to the last bucket (rs_bucket)
+        b = B - 1;
+    } else {
+        b = kmer_bucket<W>(y, B);
+    }
+    return (uint32_t) (((uint64_t) b * G) / B);
+}
+
+template<int W, bool WRITE>
+__global__ void __launch_bounds__(256) extract_owner_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
+                                                           const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode, uint32_t B, uint32_t G,
+                                                           uint32_t *__restrict__ cnt /* [G][n_reads]: counts (pass 1) / exclusive scan (pass 2) */,
+                                                           uint64_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t warps_total = (uint64_t) gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = (uint64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_reads; r += warps_total) {
+        const uint32_t l = len[r];
+        uint32_t acc = 0;   // lane g: windows of owner g so far (pass 1) / owner g's cursor (pass 2)
+        if (WRITE && (uint32_t) lane < G) acc = cnt[(uint64_t) lane * n_reads + r];
+        if (l >= (uint32_t) K) {
+            const uint32_t nwin = l - K + 1;
+            const uint64_t *seq = words + word_off[r];
+            const uint32_t nw = (l + 31) >> 5;
+            for (uint32_t p0 = 0; p0 < nwin; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const bool ok = p < nwin;
+                uint64_t y[W];
+                uint32_t o = 0xFFFFFFFFu;
+                if (ok) o = window_owner<W>(seq, nw, p, K, mode, B, G, y);
+                uint32_t pos = 0;
+                for (uint32_t g = 0; g < G; ++g) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, o == g);
+                    if (WRITE) {
+                        const uint32_t base = __shfl_sync(0xffffffffu, acc, (int) g);
+                        if (o == g) pos = base + (uint32_t) __popc(m & lt);
+                    }
+                    if ((uint32_t) lane == g) acc += (uint32_t) __popc(m);
+                }
+                if (WRITE && ok) store_rec<W>(out, pos, y);
+            }
+        }
+        if (!WRITE && (uint32_t) lane < G) cnt[(uint64_t) lane * n_reads + r] = acc;
+    }
+}
+
+__global__ void owner_totals_kernel(const uint32_t *__restrict__ off, uint64_t per_owner, uint32_t G, const uint32_t *__restrict__ total,
+                                    uint32_t *__restrict__ counts) {
+    const uint32_t g = threadIdx.x;
+    if (g >= G) return;
+    const uint32_t end = (g + 1 < G) ? off[(uint64_t) (g + 1) * per_owner] : *total;
+    counts[g] = end - off[(uint64_t) g * per_owner];
+}
+
+template<int W>
+static sb200_records *extract_partitioned_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int mode, uint32_t B, uint32_t G, uint64_t *counts_out) {
+    const uint64_t nr = rd->n_reads;
+    sb200_records *r = new sb200_records();
+    r->ctx = ctx; r->k = (unsigned) K; r->words = W; r->n = 0;
+    r->double_palindromes = mode == MODE_CANON_RC; r->marker = mode == MODE_CANON_FWD;
+    for (uint32_t g = 0; g < G; ++g) counts_out[g] = 0;
+    if (nr == 0) return r;
+    DevBuf<uint32_t> cnt(ctx, (uint64_t) G * nr + 1);
+    DevBuf<uint32_t> total_dev(ctx, 1), counts_dev(ctx, MAX_FUSED_OWNERS);
+    const unsigned grid = (unsigned) std::min<uint64_t>((nr + 7) / 8, (uint64_t) ctx->num_sms * 32);
+    auto count_pass = extract_owner_kernel<W, false>;
+    auto write_pass = extract_owner_kernel<W, true>;
+    LAUNCH(ctx, count_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, nr, K, mode, B, G, cnt.p, (uint64_t *) nullptr);
+    exclusive_scan<uint32_t>(ctx, cnt.p, (uint64_t) G * nr, total_dev.p);
+    LAUNCH(ctx, owner_totals_kernel, 1, MAX_FUSED_OWNERS, 0, cnt.p, nr, G, total_dev.p, counts_dev.p);
+    uint32_t h[MAX_FUSED_OWNERS + 1];
+    ctx->fetch(h, counts_dev.p, (size_t) G * 4);
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < G; ++g) { counts_out[g] = h[g]; n += h[g]; }
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    r->n = n;
+    r->data.alloc(ctx, n * W);
+    if (n) LAUNCH(ctx, write_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, nr, K, mode, B, G, cnt.p, r->data.p);
+    return r;
+}
+
+// Records of the reads grouped by owner, counts_out[g] = records of owner g.  Canonical modes take the fused kernels above; the
+// modes that keep both strands extract first and partition afterwards.
+sb200_records *extract_records(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc);
+void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
+sb200_records *extract_records_partitioned(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B, unsigned G,
+                                           uint64_t *counts_out) {
+    SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
+    SB200_REQUIRE(G >= 1 && G <= 256, "number of owners out of range [1,256]");
+    SB200_REQUIRE(B >= 1 && B <= 65536 && B % G == 0, "num_buckets must be a multiple of the number of owners");
+    if (!canonical_only || G > (unsigned) MAX_FUSED_OWNERS || ctx->no_fused_partition) {
+        sb200_records *r = extract_records(ctx, rd, K, canonical_only, add_rc);
+        partition_records(ctx, r, B, G, counts_out);
+        return r;
+    }
+    const int mode = add_rc ? MODE_CANON_RC : MODE_CANON_FWD;
+    switch ((K + 31) / 32) {
+        case 1: return extract_partitioned_w<1>(ctx, rd, (int) K, mode, B, G, counts_out);
+        case 2: return extract_partitioned_w<2>(ctx, rd, (int) K, mode, B, G, counts_out);
+        case 3: return extract_partitioned_w<3>(ctx, rd, (int) K, mode, B, G, counts_out);
+        default: return extract_partitioned_w<4>(ctx, rd, (int) K, mode, B, G, counts_out);
+    }
+}
+
 sb200_records *extract_records(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc) {
     SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
     switch ((K + 31) / 32) {

@@ -11,6 +11,8 @@
 
 namespace sb200 {
 sb200_records *extract_records(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc);
+sb200_records *extract_records_partitioned(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B, unsigned G,
+                                           uint64_t *counts_out);
 sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp);
 void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
 sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
@@ -39,6 +41,11 @@ extern "C" {
 int sb200_records_extract(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, sb200_records **out) {
     *out = nullptr;
     return guarded(ctx, [&] { *out = sb200::extract_records(ctx, reads, K, canonical_only, add_rc); });
+}
+int sb200_records_extract_partitioned(sb200_ctx *ctx, const sb200_reads *reads, unsigned K, int canonical_only, int add_rc, unsigned num_buckets,
+                                      unsigned n_owners, uint64_t *counts_out, sb200_records **out) {
+    *out = nullptr;
+    return guarded(ctx, [&] { *out = sb200::extract_records_partitioned(ctx, reads, K, canonical_only, add_rc, num_buckets, n_owners, counts_out); });
 }
 int sb200_records_derive(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_records **out) {
     *out = nullptr;

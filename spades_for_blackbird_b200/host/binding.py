@@ -94,6 +94,7 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_records_extract": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.c_int, C.POINTER(vp)]),
     "sb200_records_derive": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "sb200_records_partition": (C.c_int, [vp, vp, C.c_uint, C.c_uint, u64p]),
+    "sb200_records_extract_partitioned": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.c_int, C.c_uint, C.c_uint, u64p, C.POINTER(vp)]),
     "sb200_records_alloc": (C.c_int, [vp, C.c_uint64, C.c_uint, C.c_int, C.POINTER(vp)]),
     "sb200_records_size": (C.c_uint64, [vp]),
     "sb200_records_words": (C.c_uint, [vp]),

@@ -176,9 +176,12 @@ class GpuShardBackend:
 
     def extract_partition(self, reads, K, num_buckets, n_owners):
         rec = B.vp()
-        self.ctx.check(self.lib.sb200_records_extract(self.ctx.h, reads.h, K, 1, 1, C.byref(rec)))
-        view, counts, w = self._partition(rec, num_buckets, n_owners)
-        return rec, view, counts, w
+        counts = np.zeros(n_owners, dtype=np.uint64)
+        self.ctx.check(self.lib.sb200_records_extract_partitioned(self.ctx.h, reads.h, K, 1, 1, num_buckets, n_owners,
+                                                                  counts.ctypes.data_as(B.u64p), C.byref(rec)))
+        n, w = self.lib.sb200_records_size(rec), self.lib.sb200_records_words(rec)
+        view = cuda_view(self.lib.sb200_records_device(rec), max(n * w, 1), "<i8", self.device)[:n * w]
+        return rec, view, counts.astype(np.int64).tolist(), w
 
     def derive_partition(self, kpomers, num_buckets, n_owners):
         rec = B.vp()
