@@ -65,6 +65,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->force_jump_path = getenv("SB200_FORCE_JUMP") != nullptr;
         ctx->no_links = getenv("SB200_NO_LINKS") != nullptr;
         ctx->no_mask_payload = getenv("SB200_NO_MASK_PAYLOAD") != nullptr;
+        ctx->no_place = getenv("SB200_NO_PLACE") != nullptr;
         ctx->no_fused_partition = getenv("SB200_NO_FUSED_PARTITION") != nullptr;
         ctx->group_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");
         ctx->trace_t0 = sb200_ctx::now_s();

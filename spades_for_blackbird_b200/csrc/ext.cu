@@ -40,6 +40,22 @@ __global__ void __launch_bounds__(256) index_of_kmers_kernel(MphfDev m, const ui
     if (file_masks) masks[id] = file_masks[i];
 }
 
+// The same from the build's own record of where every key landed (sb200_mphf::place): index = set bits before the key's bit.  Two reads
+// from tables that stay in L2 instead of the k-mer, two XXH3 hashes and the level probes.
+__global__ void __launch_bounds__(256) index_from_place_kernel(const uint32_t *__restrict__ place, const uint32_t *__restrict__ pc_scan,
+                                                              const uint64_t *__restrict__ bits, uint64_t n, uint32_t *__restrict__ idx,
+                                                              uint32_t *__restrict__ inv, const uint8_t *__restrict__ file_masks,
+                                                              uint8_t *__restrict__ masks) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = place[i];
+    const uint32_t w = g >> 6;
+    const uint32_t id = __ldg(pc_scan + w) + (uint32_t) __popcll(__ldg(bits + w) & ((1ULL << (g & 63u)) - 1ULL));
+    idx[i] = id;
+    if (inv) inv[id] = (uint32_t) i;
+    if (file_masks) masks[id] = file_masks[i];
+}
+
 // Besides the two mask bits, every (k+1)-mer x = y -> z also records the link itself: succ[y] = z and, for the other
 // strand, succ[rc(z)] = rc(y) (oriented vertex = 2 * index + strand).  A vertex with a single outgoing edge receives
 // exactly one such write, so the unitig stage gets its successor links without a second round of MPHF lookups;
@@ -85,8 +101,12 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     // (a shard's masks are complete too — every candidate of a k-mer met at its owner — and land in this GPU's slice of the
     // zeroed full-size array; the caller's sum over the GPUs assembles the rest)
     const bool have_masks = kmers->masks_file.p != nullptr;
-    LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
-           have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
+    if (mphf->place.p && mphf->place.n == kmers->size && !ctx->no_place)   // the index was built over exactly this table on this GPU
+        LAUNCH(ctx, index_from_place_kernel, div_up(kmers->size, 256), 256, 0, mphf->place.p, mphf->pc_scan.p, mphf->bits.p, kmers->size, e->idx.p,
+               e->inv.p, have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
+    else
+        LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
+               have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
     if (!have_masks) {
         auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
         LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,

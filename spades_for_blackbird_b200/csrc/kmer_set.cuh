@@ -49,6 +49,10 @@ struct sb200_mphf {
     DevBuf<uint64_t> domain, word_off, rank_off, segment_starts;   // device copies of the tables
     DevBuf<uint64_t> bits;    // all bit-vectors
     DevBuf<uint64_t> ranks;   // all rank samples
+    // Whole-table builds on one GPU also keep where every key landed: place[i] = global bit position (word << 6 | bit) of key i of the
+    // set the index was built over, and pc_scan[w] = set bits before word w.  The index of key i is then pc_scan[w] + popc(bits below) —
+    // no hashing, no level probing (ext.cu index_from_place_kernel).
+    DevBuf<uint32_t> place, pc_scan;
     uint64_t final_level_keys = 0;
 };
 

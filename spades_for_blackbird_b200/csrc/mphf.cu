@@ -24,7 +24,7 @@ namespace sb200 {
 struct ActiveKey {
     uint64_t s0, s1;   // BooPHF hash state (levels >= 2 advance it with xorshift128*)
     uint32_t bucket;
-    uint32_t pad;
+    uint32_t pad;      // index of the key in the set
 };
 
 // level 0: hash every key, set its level-0 bit, start the active list (all keys, file order)
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) mphf_level0_kernel(const uint64_t *__rest
     load_rec<W>(keys, i, r);
     ActiveKey a;
     a.bucket = kmer_bucket<W>(r, B);
-    a.pad = 0;
+    a.pad = (uint32_t) i;   // position in the key set: where mphf_level_kernel reports the key's final bit
     xxh3_128<W>(r, a.s0, a.s1);
     uint64_t t = (uint64_t) a.bucket * MPHF_LEVELS;
     uint64_t pos = __umul64hi(a.s0, domain[t]);
@@ -59,7 +59,8 @@ constexpr int MPHF_LEVEL_ITEMS = 4;
 __global__ void __launch_bounds__(256) mphf_level_kernel(int level, const ActiveKey *__restrict__ in, const uint32_t *__restrict__ n_in,
                                                         ActiveKey *__restrict__ out, uint32_t *__restrict__ n_out,
                                                         const uint64_t *__restrict__ domain, const uint64_t *__restrict__ word_off,
-                                                        unsigned long long *__restrict__ bits, unsigned long long *__restrict__ coll) {
+                                                        unsigned long long *__restrict__ bits, unsigned long long *__restrict__ coll,
+                                                        uint32_t *__restrict__ place /* or nullptr */) {
     constexpr int ITEMS = MPHF_LEVEL_ITEMS;
     __shared__ uint32_t s_wcnt[8];
     __shared__ uint32_t s_base;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) mphf_level_kernel(int level, const Active
                 const unsigned long long bit = 1ULL << (pos & 63);
                 const bool placed = (bits[w] & bit) && !(coll[w] & bit);
                 keep[j] = !placed;
+                if (placed && place) place[a[j].pad] = (uint32_t) ((w << 6) | (pos & 63));
             }
         }
 #pragma unroll
@@ -221,6 +223,9 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     DevBuf<uint64_t> coll(ctx, words + 1); coll.zero();
 
     uint64_t n = ks->size;
+    // whole-table build with 32-bit bit positions: remember where every key lands (see sb200_mphf::place)
+    const bool keep_place = global_sizes == nullptr && (words + 1) * 64 < (1ull << 32) && n > 0;
+    if (keep_place) m->place.alloc(ctx, n);
     DevBuf<ActiveKey> act_a(ctx, n), act_b(ctx, n);
     DevBuf<uint32_t> counters(ctx, MPHF_LEVELS + 1); counters.zero();
     uint32_t n32 = (uint32_t) n;
@@ -231,21 +236,24 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256 * MPHF_LEVEL_ITEMS), (uint64_t) ctx->num_sms * 16);
     for (int l = 1; l < MPHF_LEVELS; ++l) {
         LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
-               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p);
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
         std::swap(src, dst);
     }
     uint32_t final_keys = 0;
     ctx->fetch(&final_keys, counters.p + (MPHF_LEVELS - 1), 4);
 
-    DevBuf<uint32_t> pc(ctx, words + 1);
+    DevBuf<uint32_t> pc;
+    if (keep_place) m->pc_scan.alloc(ctx, words + 1);
+    else pc.alloc(ctx, words + 1);
+    uint32_t *pcp = keep_place ? m->pc_scan.p : pc.p;
     LAUNCH(ctx, mphf_clear_popc_kernel, div_up(words + 1, 256), 256, 0, (unsigned long long *) m->bits.p,
-           (const unsigned long long *) coll.p, words + 1, pc.p);
-    exclusive_scan<uint32_t>(ctx, pc.p, words + 1, nullptr);
-    LAUNCH(ctx, mphf_ranks_kernel, (unsigned) NL, 128, 0, pc.p, m->word_off.p, m->rank_off.p, nchar_dev.p, (uint64_t) NL, m->ranks.p);
+           (const unsigned long long *) coll.p, words + 1, pcp);
+    exclusive_scan<uint32_t>(ctx, pcp, words + 1, nullptr);
+    LAUNCH(ctx, mphf_ranks_kernel, (unsigned) NL, 128, 0, pcp, m->word_off.p, m->rank_off.p, nchar_dev.p, (uint64_t) NL, m->ranks.p);
     // _lastbitsetrank per bucket = set bits of the whole bucket
     std::vector<uint32_t> ends(B + 1, 0);
     DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
-    LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pc.p, m->word_off.p, B, words, ends_dev.p);
+    LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pcp, m->word_off.p, B, words, ends_dev.p);
     ctx->fetch(ends.data(), ends_dev.p, ((size_t) B + 1) * 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];

@@ -361,6 +361,7 @@ def test_baseline_config2_full_size(monkeypatch):
     monkeypatch.setenv("SB200_NO_MASK_PAYLOAD", "1")
     monkeypatch.setenv("SB200_NO_LINKS", "1")
     monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
+    monkeypatch.setenv("SB200_NO_PLACE", "1")            # and k-mer indices by MPHF lookups instead of the build's placement record
     ctx2 = B.Context(0)
     try:
         streams, index, kp, (w, off, ln) = run(ctx2)
