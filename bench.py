@@ -438,6 +438,7 @@ def main():
         "derive_kernel_": n_kp * W1 + 2 * n_kp * W0,
         "fill_masks_kernel_": n_kp * W1 + n_km,
         "index_of_kmers_kernel<W>": n_km * (W0 + 8 + 2),
+        "index_from_place_kernel": n_km * (4 + 8 + 2),            # placement in; idx, inv, mask byte (read + write) out
         "links_kernel<W>": n_km * (W0 + 4 + 1 + 8),                # k-mer, idx, mask in; two link words out
         "walk_measure_links_kernel<W>": 2 * n_km * 4,               # every link word is read once
         "walk_emit_links_kernel<W>": n_km * 4 + n_words_out,

@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --
 # full capture: the first launches of the heavy kernels of one step (report kept under 45 MB: gpurun_out/ is capped at 64 MiB)
 REP=/tmp/full_$tag
 timeout 900 ncu --set full --clock-control none \
-  -k regex:"${NCU_KERNELS:-group_hash_kernel|group_chunk_kernel|rs_scatter_kernel|links_kernel|walk_measure_links_kernel|walk_emit_links_kernel|extract_reads_kernel|index_of_kmers_kernel|derive_kernel|mphf_level0_kernel|rs_hist_kernel}" \
+  -k regex:"${NCU_KERNELS:-group_hash_kernel|group_chunk_kernel|rs_scatter_kernel|links_kernel|walk_measure_links_kernel|walk_emit_links_kernel|extract_reads_kernel|index_of_kmers_kernel|index_from_place_kernel|derive_kernel|mphf_level0_kernel|rs_hist_kernel}" \
   -c ${NCU_COUNT:-20} -o $REP -f python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
 ncu -i $REP.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 ncu -i $REP.ncu-rep --page details --csv > gpurun_out/full_${tag}_details.csv 2>/dev/null
