@@ -14,6 +14,7 @@ struct MphfDev {
     const uint64_t *segment_starts;  // [B+1]
     const uint64_t *bits;
     const uint64_t *ranks;
+    const uint32_t *pc_scan;         // set bits before every word of `bits` (whole-table builds on one GPU), or nullptr
     uint32_t num_buckets;
 };
 
@@ -43,6 +44,10 @@ __device__ __forceinline__ uint64_t mphf_lookup(const MphfDev &m, const uint64_t
         const uint64_t *bv = m.bits + __ldg(m.word_off + (uint64_t) b * MPHF_LEVELS + l);
         uint64_t word = __ldg(bv + (pos >> 6));
         if ((word >> (pos & 63)) & 1ULL) {
+            if (m.pc_scan) {   // the buckets' bit-vectors follow each other and a bucket sets as many bits as it has keys: global rank = index
+                const uint64_t gw = __ldg(m.word_off + (uint64_t) b * MPHF_LEVELS + l) + (pos >> 6);
+                return (uint64_t) __ldg(m.pc_scan + gw) + __popcll(word & ((1ULL << (pos & 63)) - 1ULL));
+            }
             uint64_t r = __ldg(m.ranks + __ldg(m.rank_off + (uint64_t) b * MPHF_LEVELS + l) + (pos >> 9));
             uint64_t w0 = (pos >> 9) << 3, w1 = pos >> 6;
             for (uint64_t w = w0; w < w1; ++w) r += __popcll(__ldg(bv + w));
