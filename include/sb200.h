@@ -149,6 +149,9 @@ int  sb200_count_records_owned(sb200_ctx *ctx, sb200_records *r /* consumed */, 
                                int want_counts, sb200_kmers **out);
 int  sb200_mphf_build_sharded(sb200_ctx *ctx, const sb200_kmers *local_kmers, const uint64_t *global_bucket_sizes /* B */, sb200_mphf **out);
 int  sb200_mphf_arrays(const sb200_mphf *m, uint64_t **bits, uint64_t *n_words, uint64_t **ranks, uint64_t *n_ranks);   /* device */
+/* Call once the arrays above hold the sum over all GPUs: builds the lookup acceleration table (set bits before every word) that a
+ * whole-table build on one GPU gets for free. */
+int  sb200_mphf_complete(sb200_ctx *ctx, sb200_mphf *m);
 int  sb200_ext_masks_device(const sb200_ext *e, uint8_t **masks, uint64_t *size_padded);                                /* device */
 int  sb200_unitigs_extract_local(sb200_ctx *ctx, const sb200_kmers *local_kmers, const sb200_mphf *mphf, const sb200_ext *ext,
                                  uint64_t *stats /* 6: chain vertices, long chains, edges, kept, bases, non-junction k-mers */,

@@ -274,6 +274,22 @@ sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *gl
     }
 }
 
+__global__ void mphf_popc_kernel(const uint64_t *__restrict__ bits, uint64_t nwords, uint32_t *__restrict__ pc) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) pc[i] = (uint32_t) __popcll(bits[i]);
+}
+
+// After the shards' bit-vectors have been summed (all-reduce), every GPU holds the complete index: the per-word prefix popcounts that
+// let a lookup rank with one read (mphf_lookup) can be built for it too.
+void mphf_complete(sb200_ctx *ctx, sb200_mphf *m) {
+    const uint64_t words = m->total_words;
+    if ((words + 1) * 64 >= (1ull << 32) || m->total == 0) return;
+    m->pc_scan.alloc(ctx, words + 1);
+    LAUNCH(ctx, mphf_popc_kernel, div_up(words + 1, 256), 256, 0, m->bits.p, words + 1, m->pc_scan.p);
+    exclusive_scan<uint32_t>(ctx, m->pc_scan.p, words + 1, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 MphfDev mphf_dev(const sb200_mphf *m) {
     MphfDev d;
     d.domain = m->domain.p; d.word_off = m->word_off.p; d.rank_off = m->rank_off.p; d.segment_starts = m->segment_starts.p;

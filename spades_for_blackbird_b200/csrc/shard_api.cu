@@ -17,6 +17,7 @@ sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp);
 void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
 sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
+void mphf_complete(sb200_ctx *ctx, sb200_mphf *m);
 sb200_unitigs *extract_unitigs_local(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, uint64_t *stats);
 }  // namespace sb200
 
@@ -92,6 +93,9 @@ int sb200_mphf_build_sharded(sb200_ctx *ctx, const sb200_kmers *local_kmers, con
 int sb200_mphf_arrays(const sb200_mphf *m, uint64_t **bits, uint64_t *n_words, uint64_t **ranks, uint64_t *n_ranks) {
     *bits = m->bits.p; *n_words = m->total_words; *ranks = m->ranks.p; *n_ranks = m->total_ranks;
     return 0;
+}
+int sb200_mphf_complete(sb200_ctx *ctx, sb200_mphf *m) {
+    return guarded(ctx, [&] { sb200::mphf_complete(ctx, m); });
 }
 int sb200_ext_masks_device(const sb200_ext *e, uint8_t **masks, uint64_t *size_padded) {
     *masks = e->masks.p; *size_padded = (e->size + 3) & ~3ULL;

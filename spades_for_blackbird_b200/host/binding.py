@@ -106,6 +106,7 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_count_records_owned": (C.c_int, [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.POINTER(vp)]),
     "sb200_mphf_build_sharded": (C.c_int, [vp, vp, u64p, C.POINTER(vp)]),
     "sb200_mphf_arrays": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(vp), u64p]),
+    "sb200_mphf_complete": (C.c_int, [vp, vp]),
     "sb200_ext_masks_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
     "sb200_unitigs_extract_local": (C.c_int, [vp, vp, vp, vp, u64p, C.POINTER(vp)]),
     "sb200_unitigs_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),

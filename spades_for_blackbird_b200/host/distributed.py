@@ -245,6 +245,10 @@ class GpuShardBackend:
         self.lib.sb200_mphf_arrays(index.h, C.byref(bits), C.byref(nb), C.byref(ranks), C.byref(nr))
         return cuda_view(bits.value, nb.value, "<i8", self.device), cuda_view(ranks.value, nr.value, "<i8", self.device)
 
+    def mphf_complete(self, index):
+        """after the all-reduce of the bit-vectors: per-word prefix popcounts for one-read ranks"""
+        self.ctx.check(self.lib.sb200_mphf_complete(self.ctx.h, index.h))
+
     def ext_build(self, kpomers, kmers, index):
         h = B.vp()
         self.ctx.check(self.lib.sb200_ext_build(self.ctx.h, kpomers.h, kmers.h, index.h, C.byref(h)))
@@ -334,6 +338,8 @@ def construct_sharded(backend, comm, reads, k, num_buckets, gather_to=0, keep=Fa
         comm.all_reduce_sum_(bits)
         comm.all_reduce_sum_(ranks)
         backend.sync()
+    if hasattr(backend, "mphf_complete"):
+        backend.mphf_complete(res.index)   # the index is whole now (also for G = 1 through this driver: the build saw global sizes)
     mark("mphf (build + all-reduce)")
     # 7. masks
     res.ext = backend.ext_build(res.kpomers, res.kmers, res.index)
