@@ -13,9 +13,10 @@
 //       "tag", monotone in the record order inside a group), rank inside a bin by tag (full record compare on the rare tag tie);
 //   (4) records (+ counts / masks) leave in order to the front of the group's own range of the output buffer, as group_chunk_kernel
 //       does; seg_compact_kernel then closes the gaps.
-// Shared memory holds 2 x UMAX slot words and per-distinct bookkeeping only (48 KB; two CTAs of 512 threads per SM), so the size of a group is not
-// limited by it (a k-mer with 65535+ copies in a group of fewer records than that cannot exist; such groups take the 64-bit slots).  A group with more than UMAX distinct records is redone in
-// R = 2, 4, ... 256 rounds over disjoint tag ranges; beyond that the fail flag sends the set to the LSD path (radix_sort.cuh).
+// Shared memory holds 2 x UMAX slot words and per-distinct bookkeeping only (48 KB; two CTAs of 512 threads per SM), so the size of a
+// group is not limited by it, and neither is the multiplicity of a k-mer (it is at most the group size, and groups of 65535+ records
+// take the 64-bit slots).  A group with more than UMAX distinct records is redone in R = 2, 4, ... 256 rounds over disjoint tag ranges;
+// beyond that the fail flag sends the set to the LSD path (radix_sort.cuh).
 // Groups of 65535+ records need 64-bit slot words: the 32-bit instance skips them and raises ctrl[1], the host then launches the
 // 64-bit instance for those groups only.
 // The phases are separate __noinline__ functions on purpose: as one function body nvcc 12.9 -O3 produced code that lost shared-memory
