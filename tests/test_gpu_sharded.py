@@ -91,3 +91,20 @@ def test_sharded_random_vs_oracle():
     assert np.array_equal(np.concatenate([r["kmers"] for r in res]), want["kmers"].data)
     assert np.array_equal(res[0]["masks"][:len(want["masks_idx"])], want["masks_idx"])
     assert res[0]["unitigs"] == want["unitigs"]
+
+
+@pytest.mark.parametrize("env", ["SB200_NO_FUSED_PARTITION", "SB200_NO_PLACE"])
+def test_sharded_alternative_paths_agree(monkeypatch, env):
+    """The sharded path with one of its shortcuts switched off — extraction straight into the owner groups (then: extract, partition
+    pass), one-read ranks through the rebuilt prefix popcounts (then: rank samples) — gives the same shards, masks and unitigs."""
+    k, nb, G = 33, 40, 4
+    genome = synth.random_genome(12000, 321)
+    reads = synth.codes_to_strings(synth.sample_pairs(genome, 900, 120, 300, 0.005, 322))
+    want = O.gbuilder(reads, k, nb)
+    monkeypatch.setenv(env, "1")
+    res = run_virtual_ranks(G, reads, k, nb)
+    assert np.array_equal(np.concatenate([r["kpomers"] for r in res]), want["kpomers"].data)
+    assert np.array_equal(np.concatenate([r["counts"] for r in res]), want["kpomers"].counts)
+    assert np.array_equal(np.concatenate([r["kmers"] for r in res]), want["kmers"].data)
+    assert np.array_equal(res[0]["masks"][:len(want["masks_idx"])], want["masks_idx"])
+    assert res[0]["unitigs"] == want["unitigs"]
