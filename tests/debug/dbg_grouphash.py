@@ -1,7 +1,7 @@
 """Debug helper: count the (k+1)-mers and k-mers of a golden fixture with the group kernel under test, report the first differences."""
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_golden
 import oracle_lib as O
