@@ -20,6 +20,7 @@
 //   utils::CoverageHashMapBuilder                    utils/ph_map/coverage_hash_map_builder.hpp:15-54
 //   debruijn_graph::FastGraphFromSequencesConstructor assembly_graph/construction/debruijn_graph_constructor.hpp:392-517  CondensedGraph
 //   gfa::GFAWriter                                   io/graph/gfa_writer.cpp:18-52                                          CondensedGraph::WriteGFA
+//   io::FastgWriter                                  io/graph/fastg_writer.cpp:35-46                                        CondensedGraph::WriteFASTG
 // Error behaviour: the reference aborts through FATAL_ERROR / VERIFY (utils/logger/logger.hpp:177-190); here every
 // nonzero ABI return becomes sb200::Error carrying sb200_last_error(), which a SPAdes build maps back to FATAL_ERROR.
 // There is no CPU fallback: Context's constructor throws when no sm_100 device is present.
@@ -507,11 +508,15 @@ public:
             if (!self_conj_[i]) records.push_back(Rec{(idx[2 * i + 1] << 2) | ((uint64_t) is_rc[2 * i + 1] << 1), e});
         }
         std::sort(records.begin(), records.end(), [](const Rec &a, const Rec &b) { return a.key != b.key ? a.key < b.key : a.edge < b.edge; });
+        end_of_.assign(2 * n, End{0, false});
         for (size_t i = 0; i < records.size(); ++i) {
             if (i == 0 || (records[i].key >> 2) != (records[i - 1].key >> 2)) vertices_.emplace_back();
             Vertex &v = vertices_.back();
             const bool rc = records[i].key & 2, start = records[i].key & 1;
             const uint64_t e = records[i].edge, ce = conjugate(e);
+            // where the edge (or, for a start record, its conjugate) ENDS: the vertex of the record or its conjugate
+            if (start) end_of_[ce - ID_BIAS] = End{vertices_.size() - 1, !rc};
+            else end_of_[e - ID_BIAS] = End{vertices_.size() - 1, rc};
             // LinkEdge: the record attaches `e` to v (or to conjugate(v) when rc); the conjugate edge mirrors it on the other vertex
             if (start) { if (!rc) v.outgoing.push_back(e); else v.incoming.push_back(ce); }
             else       { if (!rc) v.incoming.push_back(e); else v.outgoing.push_back(ce); }
@@ -531,13 +536,44 @@ public:
                 for (uint64_t out : v.outgoing)
                     os << "L\t" << name(inc) << '\t' << orient(inc) << '\t' << name(out) << '\t' << orient(out) << '\t' << k_ << "M\n";
     }
+    // io::FastgWriter::WriteSegmentsAndLinks (io/graph/fastg_writer.cpp:35-46) with spades-gbuilder's default naming
+    // (BasicNamingF, io/utils/edge_namer.hpp:29-35: EDGE_<id>_length_<bases>_cov_<coverage>, "'" for the conjugate): one FASTA record per
+    // ORIENTED edge, the header lists the edges that leave its end vertex (a std::set of names: string order), sequence wrapped at 60.
+    // Records come in id order; the reference's order follows its edge iterator, so files are compared record by record after sorting.
+    void WriteFASTG(std::ostream &os) const {
+        for (size_t i = 0; i < edges_.size(); ++i) {
+            const uint64_t e = ID_BIAS + 2 * i;
+            for (int o = 0; o < (self_conj_[i] ? 1 : 2); ++o) {
+                const uint64_t x = e + o;
+                const End &end = end_of_[x - ID_BIAS];
+                const Vertex &v = vertices_[end.vertex];
+                std::vector<std::string> next;
+                if (!end.conj) for (uint64_t y : v.outgoing) next.push_back(fastg_name(y));
+                else for (uint64_t y : v.incoming) next.push_back(fastg_name(conjugate(y)));
+                std::sort(next.begin(), next.end());
+                next.erase(std::unique(next.begin(), next.end()), next.end());
+                os << '>' << fastg_name(x);
+                for (size_t j = 0; j < next.size(); ++j) os << (j ? ',' : ':') << next[j];
+                os << ";\n";
+                const std::string seq = o ? (!edges_[i]).str() : edges_[i].str();
+                for (size_t p = 0; p < seq.size(); p += 60) os << seq.substr(p, 60) << '\n';
+            }
+        }
+    }
 private:
+    struct End { size_t vertex; bool conj; };
+    std::string fastg_name(uint64_t e) const {
+        const uint64_t c = name(e);
+        return "EDGE_" + std::to_string(c) + "_length_" + std::to_string(edges_[(c - ID_BIAS) >> 1].size()) + "_cov_" + std::to_string(0.0) +
+               (e == c ? "" : "'");
+    }
     uint64_t name(uint64_t e) const { return std::min(e, conjugate(e)); }          // io::CanonicalEdgeHelper (io/utils/edge_namer.hpp:71-86)
     char orient(uint64_t e) const { return e <= conjugate(e) ? '+' : '-'; }
     size_t k_;
     std::vector<Sequence> edges_;
     std::vector<uint8_t> self_conj_;
     std::vector<Vertex> vertices_;
+    std::vector<End> end_of_;   // by oriented edge (id - ID_BIAS)
 };
 
 }  // namespace sb200

@@ -49,6 +49,7 @@
 #include "io/reads/binary_converter.hpp"
 #include "assembly_graph/core/graph.hpp"
 #include "io/graph/gfa_writer.hpp"
+#include "io/graph/fastg_writer.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
 
@@ -277,6 +278,10 @@ int main(int argc, char **argv) {
             std::ofstream gf(a.out + "/graph.gfa");
             gfa::GFAWriter gfa_writer(g, gf);
             gfa_writer.WriteSegmentsAndLinks();
+            // spades-gbuilder --fastg (main.cpp:218-220)
+            const std::string fastg_name = a.out + "/graph.fastg";
+            io::FastgWriter fastg_writer(g, fastg_name);
+            fastg_writer.WriteSegmentsAndLinks();
         }
     } else {
         std::cerr << "bad mode\n";

@@ -11,7 +11,9 @@ Reference lines followed (A = /root/reference/assembler/src/common):
   GFAWriter             A/io/graph/gfa_writer.cpp:18-52   S lines for canonical edges, L lines = incoming x outgoing of canonical vertices
   CanonicalEdgeHelper   A/io/utils/edge_namer.hpp:71-86   name = min(e, conj e), '+' iff e <= conj e
   ID_BIAS = 3           A/assembly_graph/core/graph_core.hpp (first id handed out)
-Pinned by tests/golden/*.npz["gfa"] (the unmodified reference's own graph.gfa, lines sorted).
+  FastgWriter           A/io/graph/fastg_writer.cpp:19-46   one record per oriented edge, header = name:sorted set of successors;
+  BasicNamingF          A/io/utils/edge_namer.hpp:29-35     EDGE_<id>_length_<bases>_cov_<std::to_string(coverage)>, "'" for the conjugate
+Pinned by tests/golden/*.npz["gfa"] / ["fastg"] (the unmodified reference's own graph.gfa / graph.fastg, lines / records sorted).
 """
 
 ID_BIAS = 3
@@ -28,9 +30,9 @@ def _rtseq_less(a, b):
     return a < b
 
 
-def gfa_lines(unitigs, k, seq_idx):
-    """unitigs: list[str] in extractor order; seq_idx(str canonical k-mer) -> MPHF index.  Returns the GFA lines in id order."""
-    n = len(unitigs)
+def _graph(unitigs, k, seq_idx):
+    """-> (conj, vertices, end): vertices = list of (incoming, outgoing) oriented edge ids of the canonical vertex of every pair;
+    end[e] = (vertex index, at the conjugate vertex?) for every oriented edge e"""
     self_conj = [u == _rc(u) for u in unitigs]
 
     def conj(e):
@@ -48,22 +50,54 @@ def gfa_lines(unitigs, k, seq_idx):
             is_rc = not _rtseq_less(km, r)
             records.append(((seq_idx(r if is_rc else km) << 2) | (int(is_rc) << 1) | int(start), e))
     records.sort()
-    lines = ["S\t%d\t%s\tDP:f:0\tKC:i:0" % (ID_BIAS + 2 * i, u) for i, u in enumerate(unitigs)]
+    vertices, end = [], {}
     pos = 0
     while pos < len(records):
-        end = pos
+        j = pos
         inc, out = [], []
-        while end < len(records) and (records[end][0] >> 2) == (records[pos][0] >> 2):
-            key, e = records[end]
+        while j < len(records) and (records[j][0] >> 2) == (records[pos][0] >> 2):
+            key, e = records[j]
             is_rc, start = bool(key & 2), bool(key & 1)
-            if start:
+            if start:   # LinkOutgoingEdge(v or conj v, e): e starts there, so conj(e) ends at the conjugate of that vertex
                 (inc if is_rc else out).append(conj(e) if is_rc else e)
-            else:
+                end[conj(e)] = (len(vertices), not is_rc)
+            else:       # LinkIncomingEdge(v or conj v, e)
                 (out if is_rc else inc).append(conj(e) if is_rc else e)
-            end += 1
+                end[e] = (len(vertices), is_rc)
+            j += 1
+        vertices.append((inc, out))
+        pos = j
+    return conj, vertices, end
+
+
+def gfa_lines(unitigs, k, seq_idx):
+    """unitigs: list[str] in extractor order; seq_idx(str canonical k-mer) -> MPHF index.  Returns the GFA lines in id order."""
+    conj, vertices, _ = _graph(unitigs, k, seq_idx)
+    lines = ["S\t%d\t%s\tDP:f:0\tKC:i:0" % (ID_BIAS + 2 * i, u) for i, u in enumerate(unitigs)]
+    for inc, out in vertices:
         for a in inc:
             for b in out:
                 lines.append("L\t%d\t%s\t%d\t%s\t%dM" % (min(a, conj(a)), "+" if a <= conj(a) else "-",
                                                          min(b, conj(b)), "+" if b <= conj(b) else "-", k))
-        pos = end
     return lines
+
+
+def fastg_records(unitigs, k, seq_idx):
+    """FASTG records (header line + sequence wrapped at 60) of every oriented edge, in id order."""
+    conj, vertices, end = _graph(unitigs, k, seq_idx)
+
+    def name(e):
+        c = min(e, conj(e))
+        return "EDGE_%d_length_%d_cov_%s%s" % (c, len(unitigs[(c - ID_BIAS) >> 1]), "%.6f" % 0.0, "" if e == c else "'")
+
+    recs = []
+    for i, u in enumerate(unitigs):
+        e = ID_BIAS + 2 * i
+        for x in ([e] if conj(e) == e else [e, e + 1]):
+            v, at_conj = end[x]
+            inc, out = vertices[v]
+            nxt = sorted({name(y) for y in out} if not at_conj else {name(conj(y)) for y in inc})
+            seq = u if x == e else _rc(u)
+            head = ">" + name(x) + (":" + ",".join(nxt) if nxt else "") + ";"
+            recs.append("\n".join([head] + [seq[p:p + 60] for p in range(0, len(seq), 60)]))
+    return recs

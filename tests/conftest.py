@@ -28,6 +28,7 @@ def load_golden(name):
     d["tip_bound"] = int(d["tip_bound"])
     d["unitigs"] = [str(u) for u in d["unitigs"]]
     d["gfa"] = [str(l) for l in d["gfa"]]
+    d["fastg"] = [str(l) for l in d["fastg"]]
     d["name"] = name
     return d
 

@@ -8,7 +8,7 @@ Each fixture holds the input reads and every artefact the reference produced for
   kpomers / kp_bucket_sizes / coverage    sorted-unique canonical (k+1)-mers per hash bucket, their multiplicities
   kmers / idx / masks_idx / index_bin     final_kmers, MPHF index of each, InOutMask array in index order, KMerIndex::serialize
   unitigs / clipped                       UnbranchingPathExtractor output (reference order) / tip-clipper count
-  gfa                                     FastGraphFromSequencesConstructor + gfa::GFAWriter on those unitigs, lines sorted
+  gfa / fastg                             FastGraphFromSequencesConstructor + gfa::GFAWriter / io::FastgWriter on those unitigs, lines / records sorted
   kc_final                                spades-kmercount style final_kmers (non-canonical, 16 buckets)
 """
 import os
@@ -60,6 +60,9 @@ def run_ref(reads, k, buckets, mode="gbuilder", tip_bound=None, coverage=True, t
         # spades-gbuilder --gfa on the same unitigs: the line ORDER depends on the reference's adjacency containers, the SET does not
         with open(os.path.join(out, "graph.gfa")) as f:
             res["gfa"] = np.array(sorted(l.rstrip("\n") for l in f if l.strip()))
+        # spades-gbuilder --fastg: one FASTA record per oriented edge; compared record by record after sorting
+        with open(os.path.join(out, "graph.fastg")) as f:
+            res["fastg"] = np.array(sorted(">" + r.rstrip("\n") for r in f.read().split(">") if r.strip()))
         clipped = 0
         for line in open(os.path.join(out, "timing.txt")):
             if line.startswith("clipped "):

@@ -82,6 +82,7 @@ def test_gbuilder_files_equal_reference(tool, tmp_path, golden):
     # a12: link records keyed by the MPHF -> vertices -> GFA; "byte-identical after canonical ordering" (line order in the reference
     # follows its adjacency containers)
     assert sorted(open(tmp_path / "graph.gfa").read().splitlines()) == list(g["gfa"])
+    assert sorted(">" + r.rstrip("\n") for r in open(tmp_path / "graph.fastg").read().split(">") if r.strip()) == list(g["fastg"])
     # second run from the binary read files it wrote (io::BinaryFileStream path): same graph
     out2 = tmp_path / "o2"
     out2.mkdir()

@@ -98,6 +98,8 @@ int main(int argc, char **argv) {
             sb200::CondensedGraph graph(index, edges);
             std::ofstream gf(out + "/graph.gfa");
             graph.WriteGFA(gf);
+            std::ofstream fg(out + "/graph.fastg");   // spades-gbuilder --fastg
+            graph.WriteFASTG(fg);
         }
         printf("%zu (k+1)-mers, %zu k-mers, %zu unitigs, %.3f s on device incl. transfers, %llu kernel launches\n", kpomers.total_kmers(),
                index.size(), edges.size(), t1 - t0, (unsigned long long) ctx.kernel_launches());
