@@ -122,9 +122,9 @@ void sb200_unitigs_free(sb200_unitigs *u);
  *      order — so the shards concatenated in rank order are the single-GPU (= reference) result.  The reference has no
  *      counterpart (it shuffles through kmers_raw<i> files, kmer_splitter.hpp:140-161); the caller moves the byte ranges
  *      between GPUs (NCCL all-to-all / all-reduce; spades_for_blackbird_b200/host/distributed.py).
- *        records_extract | records_derive  -> records_partition (grouped by owner, counts per owner)
- *        [exchange] -> records_alloc + copy -> count_records            : this GPU's shard of KMerDiskStorage
- *        mphf_build_sharded + [sum bits/ranks over GPUs]                  : the whole KMerIndex on every GPU
+ *        records_extract_partitioned | records_derive -> records_partition   (grouped by owner, counts per owner)
+ *        [exchange into records_alloc] -> count_records_owned            : this GPU's shard of KMerDiskStorage
+ *        mphf_build_sharded + [sum bits/ranks over GPUs] + mphf_complete  : the whole KMerIndex on every GPU
  *        ext_build(local (k+1)-mers, local k-mers, whole index) + [sum masks over GPUs]
  *        unitigs_extract_local                                            : sequences whose start junction is in the shard */
 typedef struct sb200_records sb200_records;   /* unsorted k-mer instances on their way through the shuffle */
