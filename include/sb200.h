@@ -3,7 +3,7 @@
  * The reference has no plugin/FFI layer on this path: the boundary is the set of C++ template interfaces its three
  * callers use (spades-core's Construction stage, spades-gbuilder, spades-kmercount).  Each entry point below names
  * the reference interface it stands in for (paths relative to /root/reference/assembler/src/common); the C++ adapter
- * that plugs them back into SPAdes is spades_for_blackbird_b200/host/sb200_adapters.hpp, and INTEGRATION.md shows the
+ * that plugs them back into SPAdes is include/sb200_adapters.hpp, and INTEGRATION.md shows the
  * reference-side edit.
  *
  * Conventions

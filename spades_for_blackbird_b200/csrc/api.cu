@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <mutex>
 
 #include "../../include/sb200.h"
@@ -67,6 +68,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->no_mask_payload = getenv("SB200_NO_MASK_PAYLOAD") != nullptr;
         ctx->no_place = getenv("SB200_NO_PLACE") != nullptr;
         ctx->no_fused_partition = getenv("SB200_NO_FUSED_PARTITION") != nullptr;
+        ctx->atomic_partition = getenv("SB200_ATOMIC_PARTITION") != nullptr;
         ctx->group_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");
         ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -102,6 +104,8 @@ void sb200_destroy(sb200_ctx *ctx) {
         cudaStreamDestroy(ctx->stream);
         cudaStreamDestroy(ctx->copy_stream);
         delete ctx;
+    } else {
+        ctx->destroyed = true;   // every later dev_free returns its block to the driver; the last one deletes the context (common.cuh)
     }
 }
 
@@ -168,7 +172,7 @@ int sb200_reads_upload(sb200_ctx *ctx, const uint64_t *words, const uint64_t *wo
     return guarded(ctx, [&] {
         SB200_REQUIRE(word_off && len && (words || n_reads == 0), "null read buffers");
         uint64_t n_words = n_reads ? word_off[n_reads] : 0;
-        sb200_reads *r = new sb200_reads();
+        std::unique_ptr<sb200_reads> r(new sb200_reads());   // released if an allocation or copy below throws
         r->ctx = ctx; r->n_reads = n_reads; r->n_words = n_words;
         r->words.alloc(ctx, n_words + 2);
         r->word_off.alloc(ctx, n_reads + 1);
@@ -176,9 +180,9 @@ int sb200_reads_upload(sb200_ctx *ctx, const uint64_t *words, const uint64_t *wo
         CUDA_CHECK(cudaMemcpyAsync(r->words.p, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(r->word_off.p, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(r->len.p, len, n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
-        reads_stats(r, len, n_reads);
+        reads_stats(r.get(), len, n_reads);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        *out = r;
+        *out = r.release();
     });
 }
 
@@ -186,7 +190,7 @@ int sb200_reads_wrap_device(sb200_ctx *ctx, const uint64_t *d_words, const uint6
                             uint64_t n_words, sb200_reads **out) {
     *out = nullptr;
     return guarded(ctx, [&] {
-        sb200_reads *r = new sb200_reads();
+        std::unique_ptr<sb200_reads> r(new sb200_reads());
         r->ctx = ctx; r->n_reads = n_reads; r->n_words = n_words;
         r->words.alloc(ctx, n_words + 2);
         r->word_off.alloc(ctx, n_reads + 1);
@@ -195,7 +199,7 @@ int sb200_reads_wrap_device(sb200_ctx *ctx, const uint64_t *d_words, const uint6
         CUDA_CHECK(cudaMemcpyAsync(r->word_off.p, d_word_off, (n_reads + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(r->len.p, d_len, n_reads * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        *out = r;
+        *out = r.release();
     });
 }
 

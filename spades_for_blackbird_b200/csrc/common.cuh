@@ -69,6 +69,7 @@ struct sb200_ctx {
     bool trace = false;
     double trace_t0 = 0;
     bool group_chunk = false;       // SB200_GROUP_KERNEL=chunk: the sorting group kernel (segsort.cuh) instead of the hashing one (grouphash.cuh)
+    bool atomic_partition = false;     // SB200_ATOMIC_PARTITION=1: one-pass partition through L2 atomics (partition.cuh) instead of extract / derive + counting passes (A/B, cross-check)
     bool no_fused_partition = false;   // SB200_NO_FUSED_PARTITION=1: sharded path extracts first and partitions afterwards (cross-check)
     bool no_place = false;          // SB200_NO_PLACE=1: k-mer indices by MPHF lookups even when the build recorded the placements (cross-check)
     bool no_mask_payload = false;   // SB200_NO_MASK_PAYLOAD=1: masks by MPHF lookups (fill_masks_kernel) even when the k-mer sort could carry them
@@ -120,9 +121,22 @@ struct sb200_ctx {
         dev_bytes_total += bytes;
         return p;
     }
+    bool destroyed = false;   // sb200_destroy ran while handles were still alive: blocks go straight back to the driver
     void dev_free(void *p) {
         auto it = dev_block_size.find(p);
-        if (it != dev_block_size.end()) dev_free_blocks.insert({it->second, p});
+        if (it == dev_block_size.end()) return;
+        if (destroyed) {
+            cudaFree(p);
+            dev_bytes_total -= it->second;
+            dev_block_size.erase(it);
+            if (dev_block_size.empty()) {   // the last handle of a destroyed context: the record and its streams go too
+                cudaStreamDestroy(stream);
+                cudaStreamDestroy(copy_stream);
+                delete this;
+            }
+            return;
+        }
+        dev_free_blocks.insert({it->second, p});
     }
     void dev_trim() {   // release every cached (currently unused) block
         cudaStreamSynchronize(stream);

@@ -15,6 +15,7 @@
 #include "scan.cuh"
 #include "segsort.cuh"
 #include "grouphash.cuh"
+#include "partition.cuh"
 
 namespace sb200 {
 
@@ -239,100 +240,87 @@ template<int W>
 static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
                                    bool double_palindromes, bool drop_marker);
 
-template<int W, typename IdxT>
-static void launch_group_hash(sb200_ctx *ctx, int mode, uint32_t n_groups, const uint64_t *grouped, const ChunkRange *ranges, uint32_t *group_unique,
-                              uint32_t *ctrl, uint64_t *out, uint32_t *out_cnt, int shift2, uint64_t lw_keep, int pshift) {
+template<int W, int MODE, typename IdxT, bool SEG>
+static void launch_group_hash_inst(sb200_ctx *ctx, uint32_t n_groups, const uint64_t *grouped, const ChunkRange *ranges, uint32_t *group_unique,
+                                   uint32_t *ctrl, uint64_t *out, uint32_t *out_cnt, int shift2, uint64_t lw_keep, int pshift, const uint8_t *pay,
+                                   const GroupParts &parts) {
     const size_t smem = group_hash_smem<IdxT>();
-    if (mode == 1) {
-        auto seg_chunk_kernel_ = group_hash_kernel<W, 1, IdxT>;   // profile name kept: it is the same stage of the path
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
-    } else if (mode == 2) {
-        auto seg_chunk_kernel_ = group_hash_kernel<W, 2, IdxT>;
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
-    } else {
-        auto seg_chunk_kernel_ = group_hash_kernel<W, 0, IdxT>;
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift);
-    }
+    auto group_hash_kernel_ = group_hash_kernel<W, MODE, IdxT, SEG>;
+    CUDA_CHECK(cudaFuncSetAttribute(group_hash_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    LAUNCH(ctx, group_hash_kernel_, n_groups, HashCfg::THREADS, smem, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift, pay, parts);
 }
 
-// Sort + unique + counts + bucket table.  `inst` (n x W) is consumed.
-//   1. one or two stable counting passes group the instances by the composite key bucket << p | top p value bits, with p
-//      chosen so that a group is ~7 K records (radix_sort.cuh)
-//   2. one CTA per group finishes the order in shared memory (counting sort on the next 8 bits, warp-tile deduplication,
-//      ranking inside segments), counts, and packs the unique records; a scan + compaction closes the gaps (segsort.cuh)
-// pshift >= 0 (derived sets only, never together with counts): records carry a mask-bit payload (derive_kernel); the set then
-// comes with masks_file.
+// parts == nullptr: every group is a contiguous range of `grouped`; otherwise the groups lie in parts->n_src runs (sharded path)
+template<int W, typename IdxT>
+static void launch_group_hash(sb200_ctx *ctx, int mode, uint32_t n_groups, const uint64_t *grouped, const ChunkRange *ranges, uint32_t *group_unique,
+                              uint32_t *ctrl, uint64_t *out, uint32_t *out_cnt, int shift2, uint64_t lw_keep, int pshift, const uint8_t *pay,
+                              const GroupParts *parts = nullptr) {
+    const GroupParts none{nullptr, nullptr, 1u, n_groups};
+#define SB200_GH(MODE)                                                                                                                              \
+    do {                                                                                                                                           \
+        if (parts) launch_group_hash_inst<W, MODE, IdxT, true>(ctx, n_groups, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift, pay, *parts); \
+        else launch_group_hash_inst<W, MODE, IdxT, false>(ctx, n_groups, grouped, ranges, group_unique, ctrl, out, out_cnt, shift2, lw_keep, pshift, pay, none);    \
+    } while (0)
+    if (mode == 1) SB200_GH(1);
+    else if (mode == 2) SB200_GH(2);
+    else SB200_GH(0);
+#undef SB200_GH
+}
+
+// Deduplication, order, counts and tables of instances that are already GROUPED by the composite key (bucket - first_bucket) << p |
+// top p value bits: `a` holds the n grouped records, starts[g] the first record of group g (n_groups + 1 entries), `b` is a free buffer
+// of the same size that receives the unique records.  Both buffers are consumed.
+//   one CTA per group deduplicates by hashing, orders the distinct records and packs them (+ count / + OR-ed mask bits) at the front of
+//   the group's own range of `b` (grouphash.cuh); a scan of the per-group unique counts + seg_compact_kernel closes the gaps.
+// pshift >= 0 (derived sets only, never together with counts): records carry a mask-bit payload in their padding (derive kernels);
+// pay != nullptr: the payload lies in a byte array beside the records instead (k-mers that fill their last word).  The set then comes
+// with masks_file.
 template<int W>
-static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
-                               bool double_palindromes, bool drop_marker, int pshift = -1, uint32_t first_bucket = 0, uint32_t n_owned = 0) {
-    // [first_bucket, first_bucket + n_owned): the buckets the records can lie in (sharded path: this GPU's share; 0 = all B).  The group
-    // key counts buckets from first_bucket, so that its 16 bits (two counting passes) go to the value prefix instead of empty buckets.
-    if (n_owned == 0) { first_bucket = 0; n_owned = B; }
-    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
-    const uint64_t lw_keep = last_word_mask(K);
-    const bool masks_mode = pshift >= 0 && !want_counts;
-    if (2 * K < 24) {
-        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, inst.p, n, lw_keep);
-        return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
-    }
+static sb200_kmers *finish_grouped(sb200_ctx *ctx, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, uint64_t n, const uint32_t *starts, uint32_t n_groups, int p,
+                                   int K, uint32_t B, bool want_counts, bool double_palindromes, bool drop_marker, int pshift, const uint8_t *pay,
+                                   uint32_t first_bucket, uint32_t n_owned) {
     using Cfg = SegCfg<W>;
+    const uint64_t lw_keep = last_word_mask(K);
+    const bool masks_mode = (pshift >= 0 || pay != nullptr) && !want_counts;
     const int top = (W == 1) ? 2 * K : 64;
-    int bbits = 0;
-    while ((1ull << bbits) < n_owned) ++bbits;
-    const int pmax = std::min(24 - std::min(bbits, 24), top - 8);
-    int p = 0;
-    while (p < pmax && (double) n / (double) ((uint64_t) n_owned << p) > (double) Cfg::TARGET) ++p;
-    const uint32_t n_groups = (uint32_t) ((uint64_t) n_owned << p);
     const int dshift = top - p - 8;
-    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top, lw_keep, first_bucket};
-
-    DevBuf<uint64_t> scratch(ctx, n * W);
-    ctx->trace_point("  instances ready");
-    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker, lw_keep, first_bucket));
-    ctx->trace_point("  group passes");
-    uint64_t *other = (grouped == inst.p) ? scratch.p : inst.p;   // free ping-pong buffer: receives the unique records
-
-    DevBuf<uint32_t> starts(ctx, (uint64_t) n_groups + 1);
+    uint64_t *grouped = a.p, *other = b.p;
     DevBuf<ChunkRange> ranges(ctx, n_groups);
     DevBuf<uint32_t> ctrl(ctx, 4);   // [0] fail flag
     ctrl.zero();
-    LAUNCH(ctx, group_bounds_kernel<W>, div_up((uint64_t) n_groups + 1, 128), 128, 0, grouped, n, gk, n_groups, starts.p);
-    LAUNCH(ctx, group_ranges_kernel, div_up(n_groups, 256), 256, 0, starts.p, n_groups, ranges.p);
+    LAUNCH(ctx, group_ranges_kernel, div_up(n_groups, 256), 256, 0, starts, n_groups, ranges.p);
     ctx->trace_point("  group bounds");
 
     DevBuf<uint32_t> group_unique(ctx, (uint64_t) n_groups + 1);
     DevBuf<uint32_t> cnt_full;   // multiplicity (or OR-ed mask bits) of the unique record at the same position of `other`
     if (want_counts || masks_mode) cnt_full.alloc(ctx, n);
-    if (ctx->group_chunk) {   // A/B and cross-check: the sorting kernel
-    size_t smem = seg_chunk_smem<W>();
-    if (want_counts) {
-        auto seg_chunk_kernel_ = group_chunk_kernel<W, 1>;
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, 0);
-    } else if (masks_mode) {
-        auto seg_chunk_kernel_ = group_chunk_kernel<W, 2>;
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, pshift);
+    if (ctx->group_chunk && !pay) {   // A/B and cross-check: the sorting kernel
+        size_t smem = seg_chunk_smem<W>();
+        if (want_counts) {
+            auto group_chunk_kernel_ = group_chunk_kernel<W, 1>;
+            CUDA_CHECK(cudaFuncSetAttribute(group_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            LAUNCH(ctx, group_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, 0);
+        } else if (masks_mode) {
+            auto group_chunk_kernel_ = group_chunk_kernel<W, 2>;
+            CUDA_CHECK(cudaFuncSetAttribute(group_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            LAUNCH(ctx, group_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_full.p, dshift, lw_keep, pshift);
+        } else {
+            auto group_chunk_kernel_ = group_chunk_kernel<W, 0>;
+            CUDA_CHECK(cudaFuncSetAttribute(group_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            LAUNCH(ctx, group_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift,
+                   lw_keep, 0);
+        }
     } else {
-        auto seg_chunk_kernel_ = group_chunk_kernel<W, 0>;
-        CUDA_CHECK(cudaFuncSetAttribute(seg_chunk_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        LAUNCH(ctx, seg_chunk_kernel_, n_groups, Cfg::THREADS, smem, grouped, ranges.p, group_unique.p, ctrl.p, other, (uint32_t *) nullptr, dshift,
-               lw_keep, 0);
-    }
-    } else {
-        // hash deduplication of every group (grouphash.cuh); groups of 65535+ records go to the 32-bit-slot instance
+        // hash deduplication of every group (grouphash.cuh); groups of 65535+ records go to the 64-bit-slot instance
         const int shift2 = dshift + 8;
         const int mode = want_counts ? 1 : masks_mode ? 2 : 0;
         uint32_t *cnt_out = (mode == 0) ? nullptr : cnt_full.p;
         const int psh = (mode == 2) ? pshift : 0;
-        launch_group_hash<W, uint16_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh);
+        launch_group_hash<W, uint16_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh, pay);
         uint32_t flags[2] = {0, 0};
         ctx->fetch(flags, ctrl.p, 8);
         if (flags[1] && !flags[0])
-            launch_group_hash<W, uint32_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh);
+            launch_group_hash<W, uint32_t>(ctx, mode, n_groups, grouped, ranges.p, group_unique.p, ctrl.p, other, cnt_out, shift2, lw_keep, psh, pay);
     }
     // per-group unique counts -> offsets; the total sizes the result
     DevBuf<uint32_t> total32(ctx, 1);
@@ -340,14 +328,12 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     uint32_t u32 = 0, failed = 0;
     ctx->fetch(&u32, total32.p, 4);
     ctx->fetch(&failed, ctrl.p, 4);
-    ctx->trace_point("  chunk kernel");
-    if (failed) {   // a digit bin beyond the shared-memory capacity (massively repeated k-mer): redo with the generic path
-        uint64_t *src = grouped;
-        if (src != inst.p) CUDA_CHECK(cudaMemcpyAsync(inst.p, src, n * W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        scratch.release();
+    ctx->trace_point("  group kernel");
+    if (failed) {   // a group beyond what the group kernel orders in shared memory (massively repeated k-mer): redo with the generic path
+        b.release();
         cnt_full.release();
-        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, inst.p, n, lw_keep);   // masks then come from lookups (ext.cu)
-        return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, a.p, n, lw_keep);   // masks then come from lookups (ext.cu)
+        return finish_set_lsd<W>(ctx, a, n, K, B, want_counts, double_palindromes, drop_marker);
     }
     uint64_t u = u32;
 
@@ -379,9 +365,55 @@ static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t 
     }
     s->size = u;
     finish_tables<W>(ctx, s, B, group_unique.p, p, first_bucket, n_owned);   // group_unique holds the exclusive scan of the per-group unique counts
-    inst.release();
+    a.release();
+    b.release();
     ctx->trace_point("  shrink + tables");
     return s;
+}
+
+// composite-key width: p value bits below the bucket so that a group is ~ Cfg::TARGET records
+template<int W>
+static int choose_prefix_bits(uint64_t n, uint32_t n_owned, int K) {
+    using Cfg = SegCfg<W>;
+    const int top = (W == 1) ? 2 * K : 64;
+    int bbits = 0;
+    while ((1ull << bbits) < n_owned) ++bbits;
+    const int pmax = std::min(24 - std::min(bbits, 24), top - 8);
+    int p = 0;
+    while (p < pmax && (double) n / (double) ((uint64_t) n_owned << p) > (double) Cfg::TARGET) ++p;
+    return p;
+}
+
+// Sort + unique + counts + bucket table of UNGROUPED instances (records that came through an exchange, sb200_count_records): one or two
+// stable counting passes group them by the composite key (radix_sort.cuh), then finish_grouped.  `inst` (n x W) is consumed.
+template<int W>
+static sb200_kmers *finish_set(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint64_t n, int K, uint32_t B, bool want_counts,
+                               bool double_palindromes, bool drop_marker, int pshift = -1, uint32_t first_bucket = 0, uint32_t n_owned = 0) {
+    // [first_bucket, first_bucket + n_owned): the buckets the records can lie in (sharded path: this GPU's share; 0 = all B).  The group
+    // key counts buckets from first_bucket, so that its 16 bits (two counting passes) go to the value prefix instead of empty buckets.
+    if (n_owned == 0) { first_bucket = 0; n_owned = B; }
+    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    const uint64_t lw_keep = last_word_mask(K);
+    if (2 * K < 24) {
+        if (pshift >= 0) LAUNCH(ctx, strip_payload_kernel<W>, div_up(n, 256), 256, 0, inst.p, n, lw_keep);
+        return finish_set_lsd<W>(ctx, inst, n, K, B, want_counts, double_palindromes, drop_marker);
+    }
+    const int top = (W == 1) ? 2 * K : 64;
+    int bbits = 0;
+    while ((1ull << bbits) < n_owned) ++bbits;
+    const int p = choose_prefix_bits<W>(n, n_owned, K);
+    const uint32_t n_groups = (uint32_t) ((uint64_t) n_owned << p);
+    DigitSel gk{-3, 0, B, drop_marker ? 1 : 0, p, top, lw_keep, first_bucket};
+
+    DevBuf<uint64_t> scratch(ctx, n * W);
+    ctx->trace_point("  instances ready");
+    uint64_t *grouped = radix_sort_passes<W>(ctx, inst.p, scratch.p, n, composite_passes(bbits + p, p, top, B, drop_marker, lw_keep, first_bucket));
+    ctx->trace_point("  group passes");
+    if (grouped != inst.p) std::swap(inst, scratch);   // `inst` holds the grouped records, `scratch` is the free ping-pong buffer
+    DevBuf<uint32_t> starts(ctx, (uint64_t) n_groups + 1);
+    LAUNCH(ctx, group_bounds_kernel<W>, div_up((uint64_t) n_groups + 1, 128), 128, 0, inst.p, n, gk, n_groups, starts.p);
+    return finish_grouped<W>(ctx, inst, scratch, n, starts.p, n_groups, p, K, B, want_counts, double_palindromes, drop_marker, pshift, nullptr,
+                             first_bucket, n_owned);
 }
 
 // First version of the path: full LSD sort of every significant byte.  Kept for very short k-mers (2K < 24 bits), as
@@ -437,8 +469,9 @@ static sb200_kmers *finish_set_lsd(sb200_ctx *ctx, DevBuf<uint64_t> &inst, uint6
     return s;
 }
 
+// Materialise every instance in read order, then group with counting passes.
 template<int W>
-static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc, uint32_t B) {
+static sb200_kmers *count_reads_legacy_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc, uint32_t B) {
     int mode = canonical_only ? (add_rc ? MODE_CANON_RC : MODE_CANON_FWD) : (add_rc ? MODE_ALL_RC : MODE_ALL_FWD);
     uint32_t mult = (mode == MODE_ALL_RC) ? 2 : 1;
     DevBuf<uint64_t> off(ctx, rd->n_reads + 1);
@@ -456,6 +489,43 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
     return finish_set<W>(ctx, inst, n, K, B, true, mode == MODE_CANON_RC, mode == MODE_CANON_FWD);
 }
 
+// SB200_ATOMIC_PARTITION=1: reads -> grouped instances in one trip through HBM (partition.cuh), then deduplication / order / counts per
+// group.  Measured on B200 (profiles/r2a_*): 291 M scattered 16-byte stores behind 291 M L2 atomics run at the L2's REQUEST rate
+// (~80-110 G requests/s: 7.0 ms count + 12.8 ms write for S2 + S4 against 11.6 ms of coalesced counting passes), so the path that
+// stages bin runs in shared memory stays the default; this one is kept as an independent implementation for the cross-checks.
+template<int W>
+static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc, uint32_t B) {
+    if (!ctx->atomic_partition || 2 * K < 24) return count_reads_legacy_w<W>(ctx, rd, K, canonical_only, add_rc, B);
+    const int mode = canonical_only ? (add_rc ? PART_CANON : PART_MINIMAL_ONLY) : PART_FWD;
+    const bool both = !canonical_only && add_rc;   // spades-kmercount: every k-mer of both strands
+    // upper bound of the instance count (positions are 32-bit) and the estimate that sizes the groups
+    const uint64_t bases = rd->n_bases ? rd->n_bases : rd->n_words * 32;
+    const uint64_t shorter = rd->n_reads * (uint64_t) (K - 1);
+    const uint64_t n_est = std::max<uint64_t>(bases > shorter ? bases - shorter : 1, 1) * (both ? 2 : 1);
+    SB200_REQUIRE(bases * (both ? 2 : 1) < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    const int p = choose_prefix_bits<W>(n_est, B, K);
+    const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
+    const GroupSel gs{B, 0u, p, (W == 1) ? 2 * K : 64};
+    DevBuf<uint32_t> hist(ctx, (uint64_t) n_groups + 1), cursor(ctx, (uint64_t) n_groups + 1), total_dev(ctx, 1);
+    hist.zero();
+    const unsigned grid = (unsigned) std::min<uint64_t>((rd->n_reads + 7) / 8, (uint64_t) ctx->num_sms * 32);
+    auto count_pass = partition_reads_kernel<W, false>;
+    auto write_pass = partition_reads_kernel<W, true>;
+    LAUNCH(ctx, count_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, hist.p, (uint64_t *) nullptr);
+    if (both) LAUNCH(ctx, count_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, hist.p, (uint64_t *) nullptr);
+    exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) n_groups + 1, total_dev.p);   // hist[g] = first record of group g, hist[n_groups] = n
+    CUDA_CHECK(cudaMemcpyAsync(cursor.p, hist.p, ((size_t) n_groups + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    uint32_t n32 = 0;
+    ctx->fetch(&n32, total_dev.p, 4);
+    const uint64_t n = n32;
+    SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    DevBuf<uint64_t> inst(ctx, n * W), other(ctx, n * W);
+    LAUNCH(ctx, write_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, cursor.p, inst.p);
+    if (both) LAUNCH(ctx, write_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, cursor.p, inst.p);
+    ctx->trace_point("  instances partitioned");
+    return finish_grouped<W>(ctx, inst, other, n, hist.p, n_groups, p, K, B, true, mode == PART_CANON, false, -1, nullptr, 0, B);
+}
+
 sb200_kmers *count_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B) {
     SB200_REQUIRE(K >= 1 && K <= 128, "K out of range [1,128]");
     SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
@@ -471,13 +541,36 @@ template<int WS, int W>
 static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) {
     int k = (int) kp->k - 1;
     uint64_t n = kp->size * 2;
-    DevBuf<uint64_t> inst(ctx, n * W);
-    auto derive_kernel_ = derive_kernel<WS, W>;
-    // three padding bits above the k-mer in its last word carry the mask bit when they exist (every odd k except k = 31 mod 32)
+    // three padding bits above the k-mer in its last word carry the mask bit when they exist (every odd k except k = 31 mod 32);
+    // otherwise the fused path keeps the bit in a byte beside the record
     const int used = 2 * (k - 32 * (W - 1));
     const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
-    LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, pshift, inst.p);
-    sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false, pshift);
+    if (!ctx->atomic_partition || 2 * k < 24) {
+        DevBuf<uint64_t> inst(ctx, n * W);
+        auto derive_kernel_ = derive_kernel<WS, W>;
+        LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, pshift, inst.p);
+        sb200_kmers *s = finish_set<W>(ctx, inst, n, k, B, false, false, false, pshift);
+        s->instances = 0;
+        return s;
+    }
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    const int p = choose_prefix_bits<W>(n, B, k);
+    const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
+    const GroupSel gs{B, 0u, p, (W == 1) ? 2 * k : 64};
+    DevBuf<uint32_t> hist(ctx, (uint64_t) n_groups + 1), cursor(ctx, (uint64_t) n_groups + 1);
+    hist.zero();
+    auto count_pass = partition_derive_kernel<WS, W, false>;
+    auto write_pass = partition_derive_kernel<WS, W, true>;
+    const unsigned grid = div_up(kp->size, 256);
+    LAUNCH(ctx, count_pass, grid, 256, 0, kp->data.p, kp->size, k, pshift, gs, hist.p, (uint64_t *) nullptr, (uint8_t *) nullptr);
+    exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) n_groups + 1, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(cursor.p, hist.p, ((size_t) n_groups + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DevBuf<uint64_t> inst(ctx, n * W), other(ctx, n * W);
+    DevBuf<uint8_t> pay;
+    if (pshift < 0 && !ctx->no_mask_payload) pay.alloc(ctx, n);
+    LAUNCH(ctx, write_pass, grid, 256, 0, kp->data.p, kp->size, k, pshift, gs, cursor.p, inst.p, pay.p);
+    ctx->trace_point("  candidates partitioned");
+    sb200_kmers *s = finish_grouped<W>(ctx, inst, other, n, hist.p, n_groups, p, k, B, false, false, false, pshift, pay.p, 0, B);
     s->instances = 0;
     return s;
 }
@@ -520,6 +613,7 @@ static sb200_records *extract_records_w(sb200_ctx *ctx, const sb200_reads *rd, i
         unsigned grid = (unsigned) std::min<uint64_t>((rd->n_reads + 7) / 8, (uint64_t) ctx->num_sms * 32);
         LAUNCH(ctx, extract_reads_kernel<W>, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, off.p, r->data.p);
     }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // blocking like every entry point: the caller hands the records to a collective on another stream
     return r;
 }
 
@@ -616,6 +710,7 @@ static sb200_records *extract_partitioned_w(sb200_ctx *ctx, const sb200_reads *r
     r->n = n;
     r->data.alloc(ctx, n * W);
     if (n) LAUNCH(ctx, write_pass, grid, 256, 0, rd->words.p, rd->word_off.p, rd->len.p, nr, K, mode, B, G, cnt.p, r->data.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // `cnt` goes back to the allocator and the caller exchanges the records on another stream
     return r;
 }
 
@@ -662,6 +757,7 @@ static sb200_records *derive_records_w(sb200_ctx *ctx, const sb200_kmers *kp) {
     const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
     r->mask_payload = pshift >= 0;
     if (kp->size) LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, (int) r->k, pshift, r->data.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // blocking like every entry point
     return r;
 }
 

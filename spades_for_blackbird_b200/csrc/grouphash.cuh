@@ -86,6 +86,25 @@ __device__ __forceinline__ uint32_t gh_slot(const uint64_t *k) {
     return (uint32_t) (h >> (64 - HashCfg::LOG_TS));
 }
 
+// Where record q of the group lives.  One GPU: the group is a contiguous range (recs points at its first record).  Hash-sharded
+// path: the group arrives in n_src runs, one per source GPU (the senders group by the same global key, shard.cu), and is never
+// made contiguous: q is a position in the logical concatenation of the parts, base[] their logical starts, off[] their physical ones.
+constexpr int GH_MAX_SRC = 32;
+template<bool SEG>
+struct GhAddr {
+    const uint64_t *recs;
+    const uint8_t *pay;      // mask-bit payload beside the records (same indexing), or nullptr
+    const uint32_t *base;    // SEG: shared memory, n_src + 1 logical starts
+    const uint32_t *off;     // SEG: shared memory, n_src physical starts (record index into recs)
+    uint32_t n_src;
+    __device__ __forceinline__ uint64_t phys(uint32_t q) const {
+        if (!SEG) return q;
+        uint32_t s = 0;
+        while (s + 1 < n_src && q >= base[s + 1]) ++s;
+        return (uint64_t) off[s] + (q - base[s]);
+    }
+};
+
 // The shared memory of one CTA (see group_hash_smem): every phase gets the same view.
 template<typename IdxT>
 struct GhSmem {
@@ -114,9 +133,11 @@ __device__ __forceinline__ GhSmem<IdxT> gh_views(unsigned char *raw) {
 
 // Phase 1+2: stream the records of the group whose tag falls into the round's range through the hash table, then compact the occupied
 // slots to the list (lq, lc).  Returns the number of distinct records, or ~0u when the table got crowded (more than UMAX distinct).
-template<int W, int MODE, typename IdxT>
-__device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__restrict__ g, uint32_t gcnt, int shift2, uint64_t lw_keep, int pshift,
-                                          int lgR, uint32_t round, uint32_t *s_U, uint32_t *s_overflow) {
+template<int W, int MODE, typename IdxT, bool SEG>
+__device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const GhAddr<SEG> ga, uint32_t gcnt, int shift2,
+                                          uint64_t lw_keep, int pshift, int lgR, uint32_t round, uint32_t *s_U, uint32_t *s_overflow) {
+    const uint64_t *__restrict__ g = ga.recs;
+    const uint8_t *__restrict__ gpay = ga.pay;
     using SlotT = typename GhSlot<IdxT>::type;
     constexpr int THREADS = HashCfg::THREADS, UMAX = HashCfg::UMAX, TS = HashCfg::TS, HB = GhSlot<IdxT>::HB;
     constexpr SlotT LOW = ((SlotT) 1 << HB) - 1;
@@ -133,7 +154,7 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
             const uint32_t q = q0 + i * THREADS + threadIdx.x;
 #pragma unroll
             for (int j = 0; j < W; ++j) in[i][j] = 0;
-            if (q < gcnt) gh_load<W>(g, q, in[i]);
+            if (q < gcnt) gh_load<W>(g, ga.phys(q), in[i]);
         }
         // Four records per thread move through the probe rounds together, so that their look-ups of the first occurrences (an L2 hit of
         // several hundred cycles each: the copy of a k-mer finds its slot taken and has to see the record that took it) overlap.  A
@@ -144,8 +165,12 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t q = q0 + i * THREADS + threadIdx.x;
-            val[i] = (MODE == 2) ? 1u << ((uint32_t) (in[i][W - 1] >> pshift) & 7u) : (MODE == 1) ? 1u : 0u;
-            if (MODE == 2) in[i][W - 1] &= lw_keep;
+            if (MODE == 2) {   // the mask bit this candidate carries: in its padding bits, or in the byte array beside the records
+                val[i] = gpay ? ((q < gcnt) ? 1u << (gpay[ga.phys(q)] & 7u) : 0u) : 1u << ((uint32_t) (in[i][W - 1] >> pshift) & 7u);
+                in[i][W - 1] &= lw_keep;
+            } else {
+                val[i] = (MODE == 1) ? 1u : 0u;
+            }
             todo[i] = q < gcnt;
             if (lgR) todo[i] = todo[i] && (seg_tag(in[i][0], shift2) >> (32 - lgR)) == round;
             h[i] = gh_slot<W>(in[i]);
@@ -168,7 +193,7 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
                 for (int j = 0; j < W; ++j) o[i][j] = 0;
-                if (todo[i]) gh_load<W>(g, (uint32_t) (v[i] >> HB) - 1u, o[i]);
+                if (todo[i]) gh_load<W>(g, ga.phys((uint32_t) (v[i] >> HB) - 1u), o[i]);
             }
             any = false;
 #pragma unroll
@@ -207,9 +232,10 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const uint64_t *__
 }
 
 // Phase 3+4: order the U distinct records (bins over the tag, rank inside the bin) and write them (+ counts) to out[obase ...).
-template<int W, int MODE, typename IdxT>
-__device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restrict__ g, uint32_t U, int shift2, uint64_t lw_keep, int lgR,
+template<int W, int MODE, typename IdxT, bool SEG>
+__device__ __noinline__ void gh_emit(unsigned char *raw, const GhAddr<SEG> ga, uint32_t U, int shift2, uint64_t lw_keep, int lgR,
                                      uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, unsigned long long obase, uint32_t *s_wtot) {
+    const uint64_t *__restrict__ g = ga.recs;
     constexpr int THREADS = HashCfg::THREADS, BINS = HashCfg::BINS;
     const GhSmem<IdxT> sm = gh_views<IdxT>(raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,7 +249,7 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
             const uint32_t e = e0 + i * THREADS + threadIdx.x;
 #pragma unroll
             for (int j = 0; j < W; ++j) k[i][j] = 0;
-            if (e < U) gh_load<W>(g, sm.lq[e], k[i]);
+            if (e < U) gh_load<W>(g, ga.phys(sm.lq[e]), k[i]);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -268,7 +294,7 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
             const uint32_t e = e0 + i * THREADS + threadIdx.x;
 #pragma unroll
             for (int j = 0; j < W; ++j) me[i][j] = 0;
-            if (e < U) gh_load<W>(g, sm.lq[e], me[i]);
+            if (e < U) gh_load<W>(g, ga.phys(sm.lq[e]), me[i]);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -286,7 +312,7 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
                     ++less;
                 } else if (to == t && o != e) {   // tag tie: two distinct records agree on the upper part of word 0
                     uint64_t other[W];
-                    gh_load<W>(g, sm.lq[o], other);
+                    gh_load<W>(g, ga.phys(sm.lq[o]), other);
                     if (MODE == 2) other[W - 1] &= lw_keep;
                     less += rec_less_bf<W>(other, me[i]);
                 }
@@ -299,16 +325,29 @@ __device__ __noinline__ void gh_emit(unsigned char *raw, const uint64_t *__restr
     __syncthreads();   // the next round reuses every array
 }
 
+// Parts of the groups of a hash-sharded set: part (s, g) = cnt[s * n_groups + g] records starting at record off[s * n_groups + g]
+struct GroupParts {
+    const uint32_t *cnt;
+    const uint32_t *off;
+    uint32_t n_src;
+    uint32_t n_groups;
+};
+
 // shift2: the group prefix ends at bit `shift2` of word 0; the tag is the 32 bits below it.
 // MODE 0 records only, 1 + multiplicities, 2 + OR of the 3-bit mask payload at bit pshift of the last word (count.cu derive_kernel).
-template<int W, int MODE, typename IdxT>
+// SEG: the group's records lie in parts.n_src runs (GhAddr); ranges[b] then only places the OUTPUT (unique records of group b go to
+// out[ranges[b].s ...), ranges[b].e - ranges[b].s = records of the group).
+template<int W, int MODE, typename IdxT, bool SEG>
 __global__ void __launch_bounds__(HashCfg::THREADS, GH_MIN_BLOCKS)
 group_hash_kernel(const uint64_t *__restrict__ recs, const ChunkRange *__restrict__ ranges, uint32_t *__restrict__ group_unique,
-                  uint32_t *__restrict__ ctrl, uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, int shift2, uint64_t lw_keep, int pshift) {
+                  uint32_t *__restrict__ ctrl, uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, int shift2, uint64_t lw_keep, int pshift,
+                  const uint8_t *__restrict__ pay /* MODE 2: payload bytes beside the records, or nullptr (payload in the padding bits) */,
+                  GroupParts parts) {
     constexpr bool SMALL = sizeof(IdxT) == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_U, s_overflow;
     __shared__ uint32_t s_wtot[HashCfg::THREADS / 32];
+    __shared__ uint32_t s_base[GH_MAX_SRC + 1], s_off[GH_MAX_SRC];
 
     const uint32_t b = blockIdx.x;
     const ChunkRange cr = ranges[b];
@@ -321,7 +360,22 @@ group_hash_kernel(const uint64_t *__restrict__ recs, const ChunkRange *__restric
         if (threadIdx.x == 0) group_unique[b] = 0;
         return;
     }
-    const uint64_t *__restrict__ g = recs + (uint64_t) s * W;
+    GhAddr<SEG> ga;
+    if (SEG) {
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (uint32_t q = 0; q < parts.n_src; ++q) {
+                s_base[q] = acc;
+                s_off[q] = parts.off[(uint64_t) q * parts.n_groups + b];
+                acc += parts.cnt[(uint64_t) q * parts.n_groups + b];
+            }
+            s_base[parts.n_src] = acc;
+        }
+        __syncthreads();
+        ga.recs = recs; ga.pay = (MODE == 2) ? pay : nullptr; ga.base = s_base; ga.off = s_off; ga.n_src = parts.n_src;
+    } else {
+        ga.recs = recs + (uint64_t) s * W; ga.pay = (MODE == 2 && pay) ? pay + s : nullptr; ga.base = nullptr; ga.off = nullptr; ga.n_src = 1;
+    }
 
     uint32_t emitted = 0;
     int lgR = 0;
@@ -330,9 +384,9 @@ group_hash_kernel(const uint64_t *__restrict__ recs, const ChunkRange *__restric
         bool bad = false;
         const uint32_t R = 1u << lgR;
         for (uint32_t round = 0; round < R; ++round) {
-            const uint32_t U = gh_dedup<W, MODE, IdxT>(smem_raw, g, gcnt, shift2, lw_keep, pshift, lgR, round, &s_U, &s_overflow);
+            const uint32_t U = gh_dedup<W, MODE, IdxT, SEG>(smem_raw, ga, gcnt, shift2, lw_keep, pshift, lgR, round, &s_U, &s_overflow);
             if (U == ~0u) { bad = true; break; }   // block-uniform
-            gh_emit<W, MODE, IdxT>(smem_raw, g, U, shift2, lw_keep, lgR, out, out_cnt, (unsigned long long) s + emitted, s_wtot);
+            gh_emit<W, MODE, IdxT, SEG>(smem_raw, ga, U, shift2, lw_keep, lgR, out, out_cnt, (unsigned long long) s + emitted, s_wtot);
             emitted += U;
         }
         if (!bad) break;

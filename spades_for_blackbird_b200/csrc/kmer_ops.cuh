@@ -211,12 +211,26 @@ DEVINL bool rec_less(const uint64_t *a, const uint64_t *b) {
     return false;
 }
 
-// canonical form; returns true if x itself is minimal (out = x), false if out = rc(x)
+// canonical form; returns true if x itself is minimal (out = x), false if out = rc(x).
+// RtSeq::IsMinimal (rtseq.hpp:407-415) compares x and rc(x) base by base from base 0, i.e. it orders the packed integers of the
+// REVERSED sequences.  reverse(rc(x)) is the complement of x and reverse(x) the complement of rc(x), and complementing (bitwise not
+// inside the K-mer's bits) reverses the integer order, so
+//     x <=lex rc(x)   <=>   ~rc(x) <= ~x   <=>   rc(x) >= x   as multi-word integers (word W-1 most significant):
+// one word-wise compare of values that are there anyway, instead of four more 2-bit-group reversals (kmer_le_lex above is kept as
+// the literal form; tests/test_host_primitives.py checks both against the oracle).
+template<int W>
+DEVINL bool kmer_ge_num(const uint64_t *a, const uint64_t *b) {
+    bool ge = true;   // equal so far, scanning from the least significant word: a more significant word overrides
+#pragma unroll
+    for (int j = 0; j < W; ++j) ge = (a[j] > b[j]) | ((a[j] == b[j]) & ge);
+    return ge;
+}
+
 template<int W>
 DEVINL bool kmer_canonical(const uint64_t *x, int K, uint64_t *out) {
     uint64_t r[W];
     kmer_rc<W>(x, K, r);
-    bool minimal = kmer_le_lex<W>(x, r);
+    bool minimal = kmer_ge_num<W>(r, x);
 #pragma unroll
     for (int j = 0; j < W; ++j) out[j] = minimal ? x[j] : r[j];
     return minimal;
@@ -271,6 +285,44 @@ DEVINL uint32_t kmer_base_w(const uint64_t *x, int i) {
     for (int j = 1; j < W; ++j)
         if ((i >> 5) == j) w = x[j];
     return (uint32_t) (w >> (2 * (i & 31))) & 3u;
+}
+
+// The window moves one base to the right and takes base c in: x <<= c (rtseq.hpp:450-467) and, for its reverse complement, 3 - c
+// enters at base 0 while the last base leaves.  Both in place; lw_mask = last_word_mask(K).
+template<int W>
+DEVINL void kmer_roll(uint64_t *x, uint64_t *r, int K, uint32_t c, uint64_t lw_mask) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) x[j] = (x[j] >> 2) | ((j + 1 < W) ? (x[j + 1] << 62) : 0ULL);
+    x[W - 1] |= (uint64_t) c << (2 * ((K - 1) & 31));
+#pragma unroll
+    for (int j = W - 1; j > 0; --j) r[j] = (r[j] << 2) | (r[j - 1] >> 62);
+    r[0] = (r[0] << 2) | (uint64_t) (3u - c);
+    r[W - 1] &= lw_mask;
+}
+
+// The two canonical k-mer candidates of a (k+1)-mer x (DeBruijnKMerKMerSplitter::FillBufferFromKMers, kmer_splitters.hpp:159-176)
+// and the InOutMask bit x contributes to each (kmer_extension_index_builder.hpp:44-59, kmer_extension_index.hpp:92-106:
+// AddOutgoing(next nucleotide) for the prefix k-mer, AddIncoming(previous nucleotide) for the suffix k-mer, mirrored when the k-mer
+// is stored as its reverse complement).  rc(x[0..k)) is the suffix of rc(x) and rc(x[1..k]) its prefix, so ONE reverse complement of
+// the (k+1)-mer serves both candidates.
+template<int WS, int W>
+DEVINL void derive_candidates(const uint64_t *x, int k, uint64_t a[2][W], uint32_t bit[2]) {
+    uint64_t rx[WS];
+    kmer_rc<WS>(x, k + 1, rx);
+    const uint32_t pnucl = kmer_base(x, 0), nnucl = kmer_base_w<WS>(x, k);
+    uint64_t f[W], b[W];
+    kmer_subwindow<WS, W>(x, 0, k, f);
+    kmer_subwindow<WS, W>(rx, 1, k, b);
+    bool minimal = kmer_ge_num<W>(b, f);
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[0][j] = minimal ? f[j] : b[j];
+    bit[0] = minimal ? nnucl : 7u - nnucl;
+    kmer_subwindow<WS, W>(x, 1, k, f);
+    kmer_subwindow<WS, W>(rx, 0, k, b);
+    minimal = kmer_ge_num<W>(b, f);
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[1][j] = minimal ? f[j] : b[j];
+    bit[1] = minimal ? pnucl + 4u : 3u - pnucl;
 }
 
 // InOutMask::conjugate: bit-reverse the byte (kmer_extension_index.hpp:87)

@@ -283,11 +283,24 @@ __global__ void mphf_popc_kernel(const uint64_t *__restrict__ bits, uint64_t nwo
 // let a lookup rank with one read (mphf_lookup) can be built for it too.
 void mphf_complete(sb200_ctx *ctx, sb200_mphf *m) {
     const uint64_t words = m->total_words;
-    if ((words + 1) * 64 >= (1ull << 32) || m->total == 0) return;
-    m->pc_scan.alloc(ctx, words + 1);
-    LAUNCH(ctx, mphf_popc_kernel, div_up(words + 1, 256), 256, 0, m->bits.p, words + 1, m->pc_scan.p);
-    exclusive_scan<uint32_t>(ctx, m->pc_scan.p, words + 1, nullptr);
+    if (m->total == 0) return;
+    // per-word prefix popcounts of the summed bit-vectors: kept for one-read ranks when bit positions fit 32 bits, and in any case
+    // the source of every bucket's _lastbitsetrank (a sharded build only saw its own buckets' bits: the serialised index of a
+    // completed shard must carry the totals of ALL buckets, BooPHF.h:514-532)
+    const bool keep = (words + 1) * 64 < (1ull << 32);
+    DevBuf<uint32_t> tmp;
+    uint32_t *pcp;
+    if (keep) { m->pc_scan.alloc(ctx, words + 1); pcp = m->pc_scan.p; }
+    else { tmp.alloc(ctx, words + 1); pcp = tmp.p; }
+    LAUNCH(ctx, mphf_popc_kernel, div_up(words + 1, 256), 256, 0, m->bits.p, words + 1, pcp);
+    exclusive_scan<uint32_t>(ctx, pcp, words + 1, nullptr);
+    const uint32_t B = m->num_buckets;
+    std::vector<uint32_t> ends((size_t) B + 1, 0);
+    DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
+    LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pcp, m->word_off.p, B, words, ends_dev.p);
+    ctx->fetch(ends.data(), ends_dev.p, ((size_t) B + 1) * 4);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];
 }
 
 MphfDev mphf_dev(const sb200_mphf *m) {

@@ -8,7 +8,7 @@
 // start edges at once.  The first walk measures (length, end k-mer -> `!(s < !s)`); after two scans a second walk over the
 // kept edges re-traces the path and emits the 2-bit packed sequence directly, 32 bases per stored word.  Only the masks,
 // the MPHF and the junction's own k-mer are needed: nothing indexed by "all vertices" is built, which is also what lets
-// several GPUs extract disjoint file ranges of junctions independently (tests/test_multi_gpu.py).  A chain longer than
+// several GPUs extract disjoint file ranges of junctions independently (tests/test_gpu_sharded.py).  A chain longer than
 // WALK_LIMIT, or vertices no walk reached (perfect loops), send the whole extraction to the pointer-jumping path.
 #pragma once
 
@@ -441,7 +441,10 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     int k = (int) kmers->k;
     MphfDev m = mphf_dev(mphf);
     uint64_t n_range = last - first;
-    SB200_REQUIRE(2 * n_range < (1ull << 30), "more than 2^29 k-mers in one extraction range: shard the input");
+    if (2 * n_range >= (1ull << 30)) {   // the start-edge codes (t << 2 | nucleotide) are 32-bit
+        if (!stats_out) return nullptr;   // whole set: the caller falls through to the pointer-jumping path
+        SB200_REQUIRE(false, "more than 2^29 k-mers in one extraction range: shard the input");
+    }
     WalkStats st;
     uint64_t nt = 2 * n_range;
     const uint32_t n_tiles = (uint32_t) div_up(std::max<uint64_t>(nt, 1), EL_TILE);

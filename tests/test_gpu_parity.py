@@ -315,6 +315,31 @@ def test_low_complexity_reads_overflow_a_segment(ctx):
     assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
 
 
+def test_atomic_partition_path(monkeypatch):
+    """SB200_ATOMIC_PARTITION=1: reads / (k+1)-mers go straight into their groups through L2 atomics (partition.cuh: rolling windows,
+    one reverse complement per (k+1)-mer, mask bits beside the records when the k-mer fills its last word) instead of extract /
+    derive + counting passes — the same tables, masks and unitigs for one- to four-word records, the kmercount modes and the tip clipper."""
+    monkeypatch.setenv("SB200_ATOMIC_PARTITION", "1")
+    ctx2 = B.Context(0)
+    try:
+        from conftest import load_golden
+        for name in ("ecoli1k_k21", "ecoli1k_k55", "multiword_k77", "multiword_k127", "tipclip_k33", "loops_k21"):
+            g = load_golden(name)
+            streams, index, kpomers = build_index(ctx2, g["reads"], g["k"], g["buckets"])
+            assert np.array_equal(kpomers.final_kmers().reshape(-1), g["kpomers"]), name
+            assert np.array_equal(kpomers.counts(), g["coverage"]), name
+            assert np.array_equal(index.kmers.final_kmers().reshape(-1), g["kmers"]), name
+            if g["tip_bound"] >= 0:
+                assert B.EarlyTipClipperProcessor(index, g["tip_bound"]).ClipTips() == int(g["clipped"])
+            assert np.array_equal(index.data(), g["masks_idx"]), name
+            assert B.UnbranchingPathExtractor(index, g["k"]).ExtractUnbranchingPathsAndLoops() == g["unitigs"], name
+            kc = B.KMerDiskCounter(ctx2, streams, g["k"], canonical_only=False, add_rc=True).CountAll(16)
+            assert np.array_equal(kc.final_kmers().reshape(-1), g["kc_final"]), name
+            index.free(); kpomers.free(); streams.free(); kc.free()
+    finally:
+        ctx2.close()
+
+
 def test_baseline_config2_full_size(monkeypatch):
     """BASELINE configs[1] at full size (4.6 Mbp genome, 2x150 at 100x, k = 55, 80 buckets: 291 M (k+1)-mer instances) — far
     beyond what the oracle does in seconds, so: size-independent properties of the tables, and the two independent
@@ -362,6 +387,7 @@ def test_baseline_config2_full_size(monkeypatch):
     monkeypatch.setenv("SB200_NO_LINKS", "1")
     monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
     monkeypatch.setenv("SB200_NO_PLACE", "1")            # and k-mer indices by MPHF lookups instead of the build's placement record
+    monkeypatch.setenv("SB200_ATOMIC_PARTITION", "1")    # and the one-pass partition through L2 atomics instead of extract / derive + counting passes
     ctx2 = B.Context(0)
     try:
         streams, index, kp, (w, off, ln) = run(ctx2)

@@ -48,6 +48,14 @@ def test_kmer_ops_match_oracle(hp, K):
             x[:] = 0
             for i, c in enumerate(full):
                 x[i // 32] |= np.uint64(c) << np.uint64(2 * (i % 32))
+        if trial % 10 in (1, 2, 3) and K >= 2:   # near-palindrome: x and rc(x) agree up to one base, anywhere (every word decides IsMinimal once)
+            half = [int((int(x[i // 32]) >> (2 * (i % 32))) & 3) for i in range((K + 1) // 2)]
+            full = (half + [3 - c for c in reversed(half[:K // 2])])[:K]
+            j = int(rng.integers(0, K))
+            full[j] = (full[j] + 1 + int(rng.integers(0, 3))) % 4
+            x[:] = 0
+            for i, c in enumerate(full):
+                x[i // 32] |= np.uint64(c) << np.uint64(2 * (i % 32))
         rc = np.zeros(4, dtype=np.uint64); shl = np.zeros(4, dtype=np.uint64); h128 = np.zeros(2, dtype=np.uint64)
         minimal = C.c_int(); h64 = C.c_uint64(); bucket = C.c_uint32()
         c = int(rng.integers(0, 4)); B = int(rng.integers(1, 2000))
@@ -115,3 +123,63 @@ def test_subwindow(hp, K1):
 def test_mask_conj(hp):
     for m in range(256):
         assert hp.hp_mask_conj(m) == int("{:08b}".format(m)[::-1], 2)
+
+
+def _pack(codes):
+    w = np.zeros(max((len(codes) + 31) // 32, 1) + 1, dtype=np.uint64)
+    for i, c in enumerate(codes):
+        w[i // 32] |= np.uint64(int(c)) << np.uint64(2 * (i % 32))
+    return w
+
+
+def _unpack(w, K):
+    return [int((int(w[i // 32]) >> (2 * (i % 32))) & 3) for i in range(K)]
+
+
+@pytest.mark.parametrize("K", [5, 22, 32, 33, 56, 64, 65, 78, 96, 97, 127, 128])
+def test_rolling_window_and_rc(hp, K):
+    """partition.cuh: a lane extracts one window + its reverse complement and ROLLS both through the next bases"""
+    rng = np.random.default_rng(3000 + K)
+    W = (K + 31) // 32
+    for L_ in (K + 3, K + 40, 150 if K < 140 else K + 9, 250):
+        codes = [int(c) for c in rng.integers(0, 4, size=L_)]
+        seq = _pack(codes)
+        nw = (L_ + 31) // 32
+        for pos in range(0, L_ - K + 1, 7):
+            for steps in range(0, min(4, L_ - K - pos + 1)):
+                xo = np.zeros(4, dtype=np.uint64); ro = np.zeros(4, dtype=np.uint64)
+                hp.hp_roll(W, p64(seq), nw, pos, K, steps, p64(xo), p64(ro))
+                want = codes[pos + steps:pos + steps + K]
+                assert _unpack(xo, K) == want
+                assert _unpack(ro, K) == [3 - c for c in reversed(want)]
+                for j in range(W):   # padding bits stay zero
+                    if 2 * K < 64 * (j + 1):
+                        assert int(xo[j]) >> max(2 * K - 64 * j, 0) == 0 and int(ro[j]) >> max(2 * K - 64 * j, 0) == 0
+
+
+@pytest.mark.parametrize("K1", [6, 22, 32, 33, 34, 56, 64, 65, 78, 96, 97, 128])
+def test_derive_candidates(hp, K1):
+    """the two canonical k-mer candidates of a (k+1)-mer and their InOutMask bits, from ONE reverse complement"""
+    rng = np.random.default_rng(4000 + K1)
+    k = K1 - 1
+    WS, W = (K1 + 31) // 32, (k + 31) // 32
+    for trial in range(150):
+        x, _w = rand_kmer(rng, K1)
+        codes = _unpack(x, K1)
+        if trial % 5 == 0:   # k-mer candidates that are (near-)palindromes
+            half = codes[:(k + 1) // 2]
+            pal = (half + [3 - c for c in reversed(half[:k // 2])])[:k]
+            codes = pal + [codes[-1]] if trial % 10 == 0 else [codes[0]] + pal
+            x = np.zeros(4, dtype=np.uint64)
+            x[:len(_pack(codes)) - 1] = _pack(codes)[:-1]
+        out = np.zeros(8, dtype=np.uint64); bit = np.zeros(2, dtype=np.uint32)
+        hp.hp_candidates(WS, W, p64(x), k, p64(out), bit.ctypes.data_as(C.POINTER(C.c_uint32)))
+        for which, sub in ((0, codes[:k]), (1, codes[1:])):
+            rc = [3 - c for c in reversed(sub)]
+            minimal = sub <= rc
+            assert _unpack(out[4 * which:4 * which + 4], k) == (sub if minimal else rc)
+            if which == 0:
+                want_bit = codes[k] if minimal else 7 - codes[k]
+            else:
+                want_bit = codes[0] + 4 if minimal else 3 - codes[0]
+            assert int(bit[which]) == want_bit
