@@ -158,11 +158,49 @@ int  sb200_unitigs_extract_local(sb200_ctx *ctx, const sb200_kmers *local_kmers,
                                  sb200_unitigs **out /* NULL if a chain exceeded the walk limit */);
 int  sb200_unitigs_device(const sb200_unitigs *u, uint64_t **words, uint64_t **word_off, uint32_t **len);               /* device */
 
+/* ---- the hash-sharded path as ONE call per rank: host code in C++ over the NCCL C API (csrc/shard.cu, csrc/comm.cu).
+ *      A communicator is either NCCL (one rank per GPU; rank 0 makes the id, the launcher hands its 128 bytes to the others) or
+ *      "local" (G virtual ranks = G threads of one process, any placement of contexts on GPUs — the same orchestration on a one-GPU
+ *      box).  Every rank calls sb200_construct_sharded with ITS slice of the reads; the result holds this rank's shards of both k-mer
+ *      tables, the whole KMerIndex and mask array, and its slice of the unitigs (rank order = the reference's order); gather_to >= 0
+ *      also moves the packed unitigs to that rank.  Perfect loops and chains beyond the direct-walk limit are extracted by rank 0 for
+ *      everybody (info.whole_set_fallback).  No reference counterpart: SPAdes shuffles through kmers_raw<i> files
+ *      (kmer_mph/kmer_splitter.hpp:140-161). -------------------------------------------------------------------------------------- */
+typedef struct sb200_comm sb200_comm;
+typedef struct sb200_shard sb200_shard;
+int  sb200_comm_unique_id(uint8_t *id128);                       /* ncclGetUniqueId; nonzero when libnccl.so.2 cannot be loaded        */
+const char *sb200_comm_last_error(void);
+int  sb200_comm_create_nccl(sb200_ctx *ctx, int rank, int world, const uint8_t *id128, sb200_comm **out);
+int  sb200_comm_create_local(int world, sb200_comm **out /* world handles, rank r = out[r] */);
+int  sb200_comm_rank(const sb200_comm *c);
+int  sb200_comm_size(const sb200_comm *c);
+void sb200_comm_free(sb200_comm *c);
+typedef struct {
+    int rank, size;
+    int whole_set_fallback;      /* rank 0 extracted all unitigs (long chains / perfect loops): the other ranks' slices are empty      */
+    int gathered;                /* this rank's unitig handle holds the slices of all ranks                                           */
+    uint64_t total_kpomers, total_kmers, total_instances, total_unitigs, total_unitig_bases, n_loops, clipped;
+    uint64_t bytes_sent;         /* bytes this rank handed to other ranks (NVLink roofline)                                           */
+    double exchange_ms;          /* device time of the two record all-to-alls                                                        */
+    double stage_ms[8];          /* count_kpomers, count_kmers, mphf, masks, tipclip, unitigs, gather, total (host wall, stages block) */
+} sb200_shard_info_t;
+struct sb200_construct_params_s;
+int  sb200_construct_sharded(sb200_ctx *ctx, sb200_comm *comm, const sb200_reads *my_reads, const struct sb200_construct_params_s *params,
+                             int gather_to /* rank, or -1: leave the unitigs sharded */, sb200_shard **out);
+const sb200_kmers   *sb200_shard_kpomers(const sb200_shard *s);   /* borrowed handles: valid until sb200_shard_free               */
+const sb200_kmers   *sb200_shard_kmers(const sb200_shard *s);
+const sb200_mphf    *sb200_shard_mphf(const sb200_shard *s);
+const sb200_ext     *sb200_shard_ext(const sb200_shard *s);
+const sb200_unitigs *sb200_shard_unitigs(const sb200_shard *s);
+int  sb200_shard_info(const sb200_shard *s, sb200_shard_info_t *info);
+int  sb200_shard_walk_stats(const sb200_shard *s, uint64_t *out /* size x 6, see sb200_unitigs_extract_local */);
+void sb200_shard_free(sb200_shard *s);
+
 /* ---- whole path, host buffers in / host buffers out: what spades-gbuilder does between read conversion and output
  *      (projects/gbuilder/main.cpp:165-181) and spades-core's Construction stage (stages/construction.cpp:469-483).
  *      Result buffers are pinned host memory owned by the graph handle. ---------------------------------------------- */
 typedef struct sb200_graph sb200_graph;
-typedef struct {
+typedef struct sb200_construct_params_s {
     unsigned k;                 /* odd, 1 <= k < 128                                                                   */
     unsigned num_buckets;       /* 10 * nthreads in the reference                                                      */
     int      tip_clip;          /* run EarlyTipClipper (spades-core, !gap_closer)                                      */

@@ -816,9 +816,20 @@ void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_
 sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned) {
     SB200_REQUIRE(B >= 1 && B <= 65536, "num_buckets out of range [1,65536]");
     SB200_REQUIRE((uint64_t) first_bucket + n_owned <= B, "owned bucket range exceeds num_buckets");
-    SB200_REQUIRE(r->n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     sb200_kmers *s;
     SB200_REQUIRE(!(r->mask_payload && want_counts), "records with a mask payload cannot be counted");
+    if (r->n == 0) {   // an owner that received nothing (small input, many GPUs): an empty shard, not an error — the caller decides on the global total
+        s = new sb200_kmers();
+        s->ctx = ctx; s->k = r->k; s->words = r->words; s->num_buckets = B; s->size = 0;
+        s->data.alloc(ctx, 0);
+        if (want_counts) s->counts.alloc(ctx, 0);
+        if (r->mask_payload) s->masks_file.alloc(ctx, 4);
+        s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
+        s->bucket_starts.zero();
+        s->bucket_starts_host.assign((size_t) B + 1, 0);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        return s;
+    }
     const int pshift = r->mask_payload ? 2 * ((int) r->k - 32 * ((int) r->words - 1)) : -1;
     switch (r->words) {
         case 1: s = finish_set<1>(ctx, r->data, r->n, (int) r->k, B, want_counts != 0, r->double_palindromes, r->marker, pshift, first_bucket, n_owned); break;

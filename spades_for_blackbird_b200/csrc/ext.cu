@@ -101,19 +101,52 @@ static sb200_ext *build_ext_w(sb200_ctx *ctx, const sb200_kmers *kpomers, const 
     // (a shard's masks are complete too — every candidate of a k-mer met at its owner — and land in this GPU's slice of the
     // zeroed full-size array; the caller's sum over the GPUs assembles the rest)
     const bool have_masks = kmers->masks_file.p != nullptr;
-    if (mphf->place.p && mphf->place.n == kmers->size && !ctx->no_place)   // the index was built over exactly this table on this GPU
+    if (kmers->size == 0) {
+        // nothing of the table lives here (a rank that owns no k-mer)
+    } else if (mphf->place.p && mphf->pc_scan.p && mphf->place.n == kmers->size && !ctx->no_place)   // the index was built over exactly this table on this GPU
         LAUNCH(ctx, index_from_place_kernel, div_up(kmers->size, 256), 256, 0, mphf->place.p, mphf->pc_scan.p, mphf->bits.p, kmers->size, e->idx.p,
                e->inv.p, have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
     else
         LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
                have_masks ? kmers->masks_file.p : (const uint8_t *) nullptr, e->masks.p);
-    if (!have_masks) {
+    if (!have_masks && kpomers->size) {
         auto fill_masks_kernel_ = fill_masks_kernel<WS, W>;
         LAUNCH(ctx, fill_masks_kernel_, div_up(kpomers->size, 256), 256, 0, m, kpomers->data.p, kpomers->size, (int) kmers->k, e->masks.p,
                e->succ.p);
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // blocking like every entry point: callers all-reduce the masks next
     return e;
+}
+
+// Extension index of a WHOLE k-mer table whose masks (MPHF-index order) already exist on the device: idx / inverse permutation by
+// lookups, masks copied.  Used by the sharded path when rank 0 takes over the whole-set unitig extraction (shard.cu).
+template<int W>
+static sb200_ext *build_ext_from_masks_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const uint8_t *masks_dev) {
+    sb200_ext *e = new sb200_ext();
+    e->ctx = ctx; e->k = kmers->k; e->size = mphf->total; e->n_local = kmers->size;
+    const uint64_t padded = (e->size + 3) & ~3ULL;
+    e->masks.alloc(ctx, padded + 4);
+    e->masks.zero();
+    CUDA_CHECK(cudaMemcpyAsync(e->masks.p, masks_dev, e->size, cudaMemcpyDeviceToDevice, ctx->stream));
+    e->idx.alloc(ctx, kmers->size);
+    e->inv.alloc(ctx, kmers->size);
+    e->masks_edited = true;   // no file-order copy of the masks exists for this table
+    MphfDev m = mphf_dev(mphf);
+    if (kmers->size)
+        LAUNCH(ctx, index_of_kmers_kernel<W>, div_up(kmers->size, 256), 256, 0, m, kmers->data.p, kmers->size, e->idx.p, e->inv.p,
+               (const uint8_t *) nullptr, e->masks.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return e;
+}
+
+sb200_ext *build_ext_from_masks(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const uint8_t *masks_dev) {
+    SB200_REQUIRE(mphf->total == kmers->size && mphf->words == kmers->words, "MPHF was not built over this k-mer set");
+    switch (kmers->words) {
+        case 1: return build_ext_from_masks_w<1>(ctx, kmers, mphf, masks_dev);
+        case 2: return build_ext_from_masks_w<2>(ctx, kmers, mphf, masks_dev);
+        case 3: return build_ext_from_masks_w<3>(ctx, kmers, mphf, masks_dev);
+        default: return build_ext_from_masks_w<4>(ctx, kmers, mphf, masks_dev);
+    }
 }
 
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf) {
@@ -252,31 +285,59 @@ __global__ void __launch_bounds__(128) tipclip_links_kernel(MphfDev m, const uin
     if (del) mask_and_not(masks, id0, del);
 }
 
+// The clipper in three steps, so that the hash-sharded path (shard.cu) can run step 1 and 3 over every GPU's own k-mers and combine the
+// kill lists / mask slices in between: the masks and the kill list span the WHOLE index (ext->size), `kmers` may be one GPU's shard.
 template<int W>
-static uint64_t tipclip_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound) {
+static void tipclip_find_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound, TipClipState &st) {
     uint64_t n = kmers->size;
     MphfDev m = mphf_dev(mphf);
-    DevBuf<uint8_t> kill(ctx, n + 4), tipped(ctx, 2 * n + 4);
-    DevBuf<unsigned long long> removed(ctx, 1);
-    kill.zero(); tipped.zero(); removed.zero();
+    st.kill.alloc(ctx, ext->size + 4); st.tipped.alloc(ctx, 2 * n + 4); st.removed.alloc(ctx, 1);
+    st.kill.zero(); st.tipped.zero(); st.removed.zero();
     uint32_t b32 = bound > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t) bound;
-    LAUNCH(ctx, tipclip_find_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, b32, kill.p, tipped.p, removed.p);
-    LAUNCH(ctx, tipclip_apply_kernel, div_up(n, 256), 256, 0, ext->masks.p, kill.p, n);
-    LAUNCH(ctx, tipclip_links_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, tipped.p);
+    if (n) LAUNCH(ctx, tipclip_find_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, b32, st.kill.p, st.tipped.p, st.removed.p);
+}
+
+void tipclip_find(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound, TipClipState &st) {
+    switch (kmers->words) {
+        case 1: tipclip_find_w<1>(ctx, kmers, mphf, ext, bound, st); break;
+        case 2: tipclip_find_w<2>(ctx, kmers, mphf, ext, bound, st); break;
+        case 3: tipclip_find_w<3>(ctx, kmers, mphf, ext, bound, st); break;
+        default: tipclip_find_w<4>(ctx, kmers, mphf, ext, bound, st); break;
+    }
+}
+
+void tipclip_apply(sb200_ctx *ctx, sb200_ext *ext, TipClipState &st) {
+    if (ext->size) LAUNCH(ctx, tipclip_apply_kernel, div_up(ext->size, 256), 256, 0, ext->masks.p, st.kill.p, ext->size);
+}
+
+template<int W>
+static void tipclip_links_w(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, TipClipState &st) {
+    uint64_t n = kmers->size;
+    MphfDev m = mphf_dev(mphf);
+    if (n) LAUNCH(ctx, tipclip_links_kernel<W>, div_up(2 * n, 128), 128, 0, m, kmers->data.p, n, (int) kmers->k, ext->masks.p, st.tipped.p);
+}
+
+// returns the number of k-mers this GPU's junctions removed
+uint64_t tipclip_links(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, TipClipState &st) {
+    switch (kmers->words) {
+        case 1: tipclip_links_w<1>(ctx, kmers, mphf, ext, st); break;
+        case 2: tipclip_links_w<2>(ctx, kmers, mphf, ext, st); break;
+        case 3: tipclip_links_w<3>(ctx, kmers, mphf, ext, st); break;
+        default: tipclip_links_w<4>(ctx, kmers, mphf, ext, st); break;
+    }
     unsigned long long r = 0;
-    ctx->fetch(&r, removed.p, 8);
+    ctx->fetch(&r, st.removed.p, 8);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (r) { ext->succ_valid = false; ext->masks_edited = true; }   // a junction that lost a tip may now have a single successor the racing writes did not keep
     return r;
 }
 
 uint64_t tipclip(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound) {
-    switch (kmers->words) {
-        case 1: return tipclip_w<1>(ctx, kmers, mphf, ext, bound);
-        case 2: return tipclip_w<2>(ctx, kmers, mphf, ext, bound);
-        case 3: return tipclip_w<3>(ctx, kmers, mphf, ext, bound);
-        default: return tipclip_w<4>(ctx, kmers, mphf, ext, bound);
-    }
+    TipClipState st;
+    tipclip_find(ctx, kmers, mphf, ext, bound, st);
+    tipclip_apply(ctx, ext, st);
+    const uint64_t r = tipclip_links(ctx, kmers, mphf, ext, st);
+    if (r) { ext->succ_valid = false; ext->masks_edited = true; }   // a junction that lost a tip may now have a single successor the racing writes did not keep
+    return r;
 }
 
 }  // namespace sb200

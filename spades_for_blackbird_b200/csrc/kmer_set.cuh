@@ -77,3 +77,12 @@ struct sb200_unitigs {
     DevBuf<uint32_t> len;        // count
     DevBuf<uint64_t> words;      // packed 2-bit, same layout as reads
 };
+
+namespace sb200 {
+// EarlyTipClipper in three steps (ext.cu): the kill list and the masks span the WHOLE index, the k-mers may be one GPU's shard
+struct TipClipState {
+    DevBuf<uint8_t> kill;      // ext->size + 4: k-mers (MPHF index) to isolate
+    DevBuf<uint8_t> tipped;    // 2 * kmers->size + 4: oriented local junctions that lost a tip
+    DevBuf<unsigned long long> removed;
+};
+}  // namespace sb200

@@ -224,17 +224,18 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
 
     uint64_t n = ks->size;
     // whole-table build with 32-bit bit positions: remember where every key lands (see sb200_mphf::place)
-    const bool keep_place = global_sizes == nullptr && (words + 1) * 64 < (1ull << 32) && n > 0;
+    // (a shard records them too: the bit positions are global, and sb200_mphf_complete builds pc_scan once the index is whole)
+    const bool keep_place = (words + 1) * 64 < (1ull << 32) && n > 0;
     if (keep_place) m->place.alloc(ctx, n);
     DevBuf<ActiveKey> act_a(ctx, n), act_b(ctx, n);
     DevBuf<uint32_t> counters(ctx, MPHF_LEVELS + 1); counters.zero();
     uint32_t n32 = (uint32_t) n;
     CUDA_CHECK(cudaMemcpyAsync(counters.p, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
-           (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
+    if (n) LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
+                  (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
     ActiveKey *src = act_a.p, *dst = act_b.p;
     unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256 * MPHF_LEVEL_ITEMS), (uint64_t) ctx->num_sms * 16);
-    for (int l = 1; l < MPHF_LEVELS; ++l) {
+    for (int l = 1; l < MPHF_LEVELS && n; ++l) {   // (a rank that owns no k-mer at all only contributes zeroed arrays)
         LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
                (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
         std::swap(src, dst);
@@ -249,6 +250,7 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     LAUNCH(ctx, mphf_clear_popc_kernel, div_up(words + 1, 256), 256, 0, (unsigned long long *) m->bits.p,
            (const unsigned long long *) coll.p, words + 1, pcp);
     exclusive_scan<uint32_t>(ctx, pcp, words + 1, nullptr);
+    CUDA_CHECK(cudaMemsetAsync(m->ranks.p, 0, (ranks + 1) * 8, ctx->stream));   // buckets without keys here (other GPUs' shards) leave no garbage
     LAUNCH(ctx, mphf_ranks_kernel, (unsigned) NL, 128, 0, pcp, m->word_off.p, m->rank_off.p, nchar_dev.p, (uint64_t) NL, m->ranks.p);
     // _lastbitsetrank per bucket = set bits of the whole bucket
     std::vector<uint32_t> ends(B + 1, 0);

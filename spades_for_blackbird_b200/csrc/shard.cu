@@ -1,0 +1,385 @@
+// shard.cu — the hash-sharded path: one rank per GPU, the k-mer space split by the reference's own bucket function.
+//
+// Rank g of G owns the buckets [g*B/G, (g+1)*B/G) of KMerSegmentPolicy (C/utils/kmer_mph/kmer_buckets.hpp:28-41) — a contiguous
+// range of the reference's file order — so the shards concatenated in rank order ARE the single-GPU (= reference) result.  The
+// reference does the same shuffle through kmers_raw<i> files (kmer_splitter.hpp:140-161); here it is two all-to-alls over NVLink:
+//   1. reads are split by index; every rank extracts canonical (k+1)-mer instances straight into the owner groups (count.cu)
+//   2. all-to-all #1 (instances)             -> owners group / deduplicate / count: their shard of the (k+1)-mer KMerDiskStorage
+//   3. owners derive k-mer candidates (mask bit in the padding), group them by the owner of the K-MER
+//   4. all-to-all #2 (candidates)            -> owners deduplicate + OR the mask bits: their shard of final_kmers
+//   5. all-gather of bucket sizes (tiny)     -> segment starts / level geometry of the whole KMerIndex on every rank
+//   6. every rank builds the BooPHF levels of its own buckets inside the global layout; an owner's bit-vectors, rank samples and MPHF
+//      indices are CONTIGUOUS ranges, so the index is completed by an all-gather of slices (no zero-padded all-reduce)
+//   7. masks: the same all-gather of slices (mask bits rode through the k-mer sort); only a k-mer set without the payload falls
+//      back to lookups + an all-reduce
+//   8. [EarlyTipClipper: find over the own junctions, kill lists OR-ed over the ranks, forward links of the own junctions, slices again]
+//   9. every rank walks the start edges of the junctions in its own shard against the global index + masks: its slice of the unitig
+//      list, already in the reference's global order.  Chains beyond the direct-walk limit or perfect loops (no junction to start from)
+//      send the extraction to rank 0, which gathers the k-mer shards and runs the whole-set path (pointer jumping + CollectLoops,
+//      debruijn_graph_constructor.hpp:248-265,308-344) — complete for every input, at one GPU's speed for that stage;
+//  10. optional gather of the packed unitig slices to rank 0 in rank order (= reference order).
+// Host code is C++ (NCCL C API behind comm.cuh); Python only launches ranks and hands the NCCL id around.
+#include <string.h>
+
+#include <memory>
+#include <thread>
+
+#include "../../include/sb200.h"
+#include "comm.cuh"
+#include "common.cuh"
+#include "graph.cuh"
+#include "kmer_set.cuh"
+
+namespace sb200 {
+sb200_records *extract_records_partitioned(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, int canonical_only, int add_rc, unsigned B, unsigned G,
+                                           uint64_t *counts_out);
+sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp);
+void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
+sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
+sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
+void mphf_complete(sb200_ctx *ctx, sb200_mphf *m);
+sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf);
+sb200_ext *build_ext_from_masks(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const uint8_t *masks_dev);
+void tipclip_find(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound, TipClipState &st);
+void tipclip_apply(sb200_ctx *ctx, sb200_ext *ext, TipClipState &st);
+uint64_t tipclip_links(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, TipClipState &st);
+sb200_unitigs *extract_unitigs_local(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, uint64_t *stats);
+sb200_unitigs *extract_unitigs(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int with_loops);
+}  // namespace sb200
+
+struct sb200_shard {
+    sb200_ctx *ctx = nullptr;
+    int rank = 0, size = 1;
+    sb200_kmers *kpomers = nullptr, *kmers = nullptr;   // this rank's shards
+    sb200_mphf *mphf = nullptr;                         // the whole index
+    sb200_ext *ext = nullptr;                           // masks of the whole index, idx of the own k-mers
+    sb200_unitigs *unitigs = nullptr;                   // own slice (or everything on rank 0, see whole_set_fallback / gathered)
+    std::vector<uint64_t> walk_stats;                   // size x 6 (sb200_unitigs_extract_local's stats of every rank)
+    std::vector<uint64_t> unitig_counts;                // sequences per rank before any gather
+    uint64_t clipped = 0, total_kpomers = 0, total_kmers = 0, total_instances = 0, total_unitigs = 0, total_unitig_bases = 0, n_loops = 0;
+    bool whole_set_fallback = false, gathered = false;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // count_kpomers, count_kmers, mphf, masks, tipclip, unitigs, gather, total
+    uint64_t bytes_sent = 0;
+    double exchange_ms = 0;
+    ~sb200_shard() {
+        delete unitigs; delete ext; delete mphf; delete kmers; delete kpomers;
+    }
+};
+
+namespace sb200 {
+
+static sb200_records *alloc_records(sb200_ctx *ctx, uint64_t n, const sb200_records *like) {
+    sb200_records *r = new sb200_records();
+    r->ctx = ctx; r->k = like->k; r->words = like->words; r->n = n;
+    r->double_palindromes = like->double_palindromes; r->marker = like->marker; r->mask_payload = like->mask_payload;
+    r->data.alloc(ctx, n * r->words);
+    return r;
+}
+
+// records grouped by owner (counts[g] of them for owner g) -> exchange -> this rank's shard, grouped / deduplicated / counted
+static sb200_kmers *exchange_and_count(sb200_ctx *ctx, sb200_comm *cm, std::unique_ptr<sb200_records> rec, const uint64_t *counts, unsigned B,
+                                       bool want_counts) {
+    const int G = cm->size;
+    std::vector<uint64_t> all((size_t) G * G);
+    cm->all_gather_host(ctx, counts, (size_t) G, all.data());
+    const uint64_t rb = (uint64_t) rec->words * 8;
+    std::vector<uint64_t> send_off((size_t) G + 1, 0), recv_off((size_t) G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        send_off[(size_t) g + 1] = send_off[(size_t) g] + counts[g] * rb;
+        recv_off[(size_t) g + 1] = recv_off[(size_t) g] + all[(size_t) g * G + cm->rank] * rb;
+    }
+    const uint64_t n_recv = recv_off[(size_t) G] / rb;
+    SB200_REQUIRE(n_recv < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: use more GPUs");
+    std::unique_ptr<sb200_records> got(alloc_records(ctx, n_recv, rec.get()));
+    cm->all_to_all_v(ctx, rec->data.p, send_off.data(), got->data.p, recv_off.data());
+    rec.reset();   // the exchange has completed (all_to_all_v is blocking)
+    const unsigned n_owned = B / (unsigned) G;
+    return count_records(ctx, got.get(), B, want_counts ? 1 : 0, (unsigned) cm->rank * n_owned, n_owned);
+}
+
+static double now_ms() { return sb200_ctx::now_s() * 1e3; }
+
+static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb200_reads *reads, const sb200_construct_params *p, int gather_to) {
+    const int G = cm->size, me = cm->rank;
+    const unsigned B = p->num_buckets, k = p->k;
+    SB200_REQUIRE((k & 1) && k >= 1 && k < 128, "k must be odd and in [1,128)");
+    SB200_REQUIRE(B >= 1 && B <= 65536 && B % (unsigned) G == 0, "num_buckets must be a multiple of the number of GPUs");
+    SB200_REQUIRE(G <= 64, "at most 64 ranks");
+    std::unique_ptr<sb200_shard> res(new sb200_shard());
+    res->ctx = ctx; res->rank = me; res->size = G;
+    cm->bytes_sent = 0; cm->exchange_ms = 0;
+    const unsigned n_owned = B / (unsigned) G, first_bucket = (unsigned) me * n_owned;
+    double t0 = now_ms(), t_start = t0;
+    auto lap = [&](int stage) {
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const double t = now_ms();
+        res->stage_ms[stage] += t - t0;
+        t0 = t;
+    };
+
+    // ---- 1-2: (k+1)-mers ------------------------------------------------------------------------------------------------------
+    {
+        std::vector<uint64_t> counts((size_t) G, 0);
+        std::unique_ptr<sb200_records> rec(extract_records_partitioned(ctx, reads, k + 1, 1, 1, B, (unsigned) G, counts.data()));
+        res->kpomers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, true);
+    }
+    lap(0);
+    // ---- 3-4: k-mers --------------------------------------------------------------------------------------------------------------
+    {
+        std::vector<uint64_t> counts((size_t) G, 0);
+        std::unique_ptr<sb200_records> rec(derive_records(ctx, res->kpomers));
+        partition_records(ctx, rec.get(), B, (unsigned) G, counts.data());
+        res->kmers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, false);
+    }
+    lap(1);
+    // ---- 5: global sizes -------------------------------------------------------------------------------------------------------------
+    std::vector<uint64_t> sizes((size_t) B, 0);   // k-mers per bucket, all buckets
+    {
+        std::vector<uint64_t> mine((size_t) n_owned + 3, 0), all(((size_t) n_owned + 3) * G);
+        for (unsigned b = 0; b < n_owned; ++b)
+            mine[b] = res->kmers->bucket_starts_host[(size_t) first_bucket + b + 1] - res->kmers->bucket_starts_host[(size_t) first_bucket + b];
+        mine[n_owned] = res->kpomers->size; mine[(size_t) n_owned + 1] = res->kpomers->instances; mine[(size_t) n_owned + 2] = res->kmers->size;
+        cm->all_gather_host(ctx, mine.data(), mine.size(), all.data());
+        for (int g = 0; g < G; ++g) {
+            const uint64_t *row = all.data() + (size_t) g * mine.size();
+            for (unsigned b = 0; b < n_owned; ++b) sizes[(size_t) g * n_owned + b] = row[b];
+            res->total_kpomers += row[n_owned]; res->total_instances += row[(size_t) n_owned + 1]; res->total_kmers += row[(size_t) n_owned + 2];
+        }
+        SB200_REQUIRE(res->total_kmers > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+    }
+    // ---- 6: index ----------------------------------------------------------------------------------------------------------------------
+    res->mphf = mphf_build(ctx, res->kmers, sizes.data());
+    sb200_mphf *m = res->mphf;
+    if (G > 1) {
+        std::vector<uint64_t> woff((size_t) G + 1), roff((size_t) G + 1);
+        for (int g = 0; g <= G; ++g) {
+            const size_t t = (size_t) g * n_owned * 25;   // first (bucket, level) entry of rank g's buckets (mphf.cuh MPHF_LEVELS)
+            woff[(size_t) g] = 8 * (g < G ? m->word_off_host[t] : m->total_words);
+            roff[(size_t) g] = 8 * (g < G ? m->rank_off_host[t] : m->total_ranks);
+        }
+        cm->all_gather_v_inplace(ctx, m->bits.p, woff.data());
+        cm->all_gather_v_inplace(ctx, m->ranks.p, roff.data());
+    }
+    mphf_complete(ctx, m);
+    lap(2);
+    // ---- 7: masks ------------------------------------------------------------------------------------------------------------------------
+    // The masks a rank's k-mer sort OR-ed together are complete for its own k-mers; if ANY rank's set came without them (no padding bits
+    // for this k, or its groups overflowed into the LSD path), every rank fills by lookups instead — a mix would leave holes.
+    bool all_payload = true;
+    {
+        uint64_t have = res->kmers->masks_file.p ? 1 : 0, all[64];
+        cm->all_gather_host(ctx, &have, 1, all);
+        for (int g = 0; g < G; ++g) all_payload = all_payload && all[g];
+        if (!all_payload) res->kmers->masks_file.release();
+    }
+    res->ext = build_ext(ctx, res->kpomers, res->kmers, m);
+    std::vector<uint64_t> idx_off((size_t) G + 1, 0);   // rank g's k-mers hold the MPHF indices [idx_off[g], idx_off[g + 1])
+    for (int g = 0; g < G; ++g) {
+        uint64_t s = 0;
+        for (unsigned b = 0; b < n_owned; ++b) s += sizes[(size_t) g * n_owned + b];
+        idx_off[(size_t) g + 1] = idx_off[(size_t) g] + s;
+    }
+    if (G > 1) {
+        if (all_payload) cm->all_gather_v_inplace(ctx, res->ext->masks.p, idx_off.data());
+        else cm->all_reduce_or_bytes(ctx, res->ext->masks.p, res->ext->size, false);
+    }
+    lap(3);
+    // ---- 8: tip clipper --------------------------------------------------------------------------------------------------------------------
+    if (p->tip_clip) {
+        TipClipState st;
+        tipclip_find(ctx, res->kmers, m, res->ext, p->tip_length_bound, st);
+        if (G > 1) cm->all_reduce_or_bytes(ctx, st.kill.p, res->ext->size, true);
+        tipclip_apply(ctx, res->ext, st);
+        uint64_t removed = tipclip_links(ctx, res->kmers, m, res->ext, st), all[64];
+        if (G > 1) cm->all_gather_v_inplace(ctx, res->ext->masks.p, idx_off.data());   // a junction's mask lies in its owner's slice
+        cm->all_gather_host(ctx, &removed, 1, all);
+        for (int g = 0; g < G; ++g) res->clipped += all[g];
+        if (res->clipped) { res->ext->succ_valid = false; res->ext->masks_edited = true; }
+        lap(4);
+    }
+    // ---- 9: unitigs -------------------------------------------------------------------------------------------------------------------------
+    uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
+    res->unitigs = extract_unitigs_local(ctx, res->kmers, m, res->ext, stats);
+    res->walk_stats.assign((size_t) G * 6, 0);
+    cm->all_gather_host(ctx, stats, 6, res->walk_stats.data());
+    uint64_t chain_seen = 0, long_chains = 0;
+    for (int g = 0; g < G; ++g) { chain_seen += res->walk_stats[(size_t) g * 6]; long_chains += res->walk_stats[(size_t) g * 6 + 1]; }
+    const bool loops = p->with_loops && chain_seen != 2 * res->walk_stats[5];   // chain vertices no walk reached: perfect loops
+    if (long_chains || loops) {
+        // The direct walks cannot finish this input: rank 0 gathers the k-mer shards (rank order = file order) and runs the whole-set
+        // extraction (pointer jumping for the long chains, CollectLoops for the loops); the other ranks contribute an empty slice.
+        res->whole_set_fallback = true;
+        delete res->unitigs;
+        res->unitigs = nullptr;
+        const uint64_t rb = (uint64_t) res->kmers->words * 8;
+        std::vector<uint64_t> roff((size_t) G + 1, 0);
+        for (int g = 0; g < G; ++g) roff[(size_t) g + 1] = idx_off[(size_t) g + 1] * rb;
+        std::unique_ptr<sb200_kmers> full;
+        if (me == 0) {
+            full.reset(new sb200_kmers());
+            full->ctx = ctx; full->k = k; full->words = res->kmers->words; full->num_buckets = B; full->size = res->total_kmers;
+            full->data.alloc(ctx, full->size * full->words);
+            full->bucket_starts_host.assign((size_t) B + 1, 0);
+            for (unsigned b = 0; b < B; ++b) full->bucket_starts_host[(size_t) b + 1] = full->bucket_starts_host[b] + sizes[b];
+            full->bucket_starts.alloc(ctx, (size_t) B + 1);
+            CUDA_CHECK(cudaMemcpyAsync(full->bucket_starts.p, full->bucket_starts_host.data(), ((size_t) B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        cm->gather_v(ctx, res->kmers->data.p, res->kmers->size * rb, me == 0 ? full->data.p : nullptr, roff.data(), 0);
+        if (me == 0) {
+            std::unique_ptr<sb200_ext> fext(build_ext_from_masks(ctx, full.get(), m, res->ext->masks.p));
+            res->unitigs = extract_unitigs(ctx, full.get(), m, fext.get(), p->with_loops);
+        } else {
+            res->unitigs = new sb200_unitigs();
+            res->unitigs->ctx = ctx; res->unitigs->k = k;
+            res->unitigs->word_off.alloc(ctx, 1); res->unitigs->word_off.zero();
+            res->unitigs->len.alloc(ctx, 1); res->unitigs->words.alloc(ctx, 1);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        uint64_t mine[3] = {res->unitigs->count, res->unitigs->total_bases, res->unitigs->n_loops}, all[3 * 64];
+        cm->all_gather_host(ctx, mine, 3, all);
+        res->unitig_counts.assign((size_t) G, 0);
+        for (int g = 0; g < G; ++g) {
+            res->unitig_counts[(size_t) g] = all[3 * g];
+            res->total_unitigs += all[3 * g]; res->total_unitig_bases += all[3 * g + 1]; res->n_loops += all[3 * g + 2];
+        }
+    }
+    lap(5);
+    // ---- 10: gather ---------------------------------------------------------------------------------------------------------------------------
+    if (gather_to >= 0 && G > 1 && !res->whole_set_fallback) {
+        sb200_unitigs *u = res->unitigs;
+        uint64_t mine[2] = {u->count, u->total_words}, all[2 * 64];
+        cm->all_gather_host(ctx, mine, 2, all);
+        std::vector<uint64_t> woff((size_t) G + 1, 0), loff((size_t) G + 1, 0), ooff((size_t) G + 1, 0);
+        for (int g = 0; g < G; ++g) {
+            woff[(size_t) g + 1] = woff[(size_t) g] + all[2 * g + 1] * 8;
+            loff[(size_t) g + 1] = loff[(size_t) g] + all[2 * g] * 4;
+            ooff[(size_t) g + 1] = ooff[(size_t) g] + all[2 * g] * 8;
+        }
+        std::unique_ptr<sb200_unitigs> tot;
+        if (me == gather_to) {
+            tot.reset(new sb200_unitigs());
+            tot->ctx = ctx; tot->k = k; tot->count = loff[(size_t) G] / 4; tot->total_words = woff[(size_t) G] / 8;
+            tot->total_bases = res->total_unitig_bases; tot->n_loops = res->n_loops;
+            tot->words.alloc(ctx, tot->total_words + 1); tot->len.alloc(ctx, tot->count + 1); tot->word_off.alloc(ctx, tot->count + 1);
+        }
+        cm->gather_v(ctx, u->words.p, u->total_words * 8, tot ? tot->words.p : nullptr, woff.data(), gather_to);
+        cm->gather_v(ctx, u->len.p, u->count * 4, tot ? tot->len.p : nullptr, loff.data(), gather_to);
+        cm->gather_v(ctx, u->word_off.p, u->count * 8, tot ? tot->word_off.p : nullptr, ooff.data(), gather_to);
+        if (tot) {   // the slices' word offsets start at 0: shift every slice by the words before it
+            void shift_word_offsets(sb200_ctx *, uint64_t *, const uint64_t *, const uint64_t *, int, uint64_t);
+            shift_word_offsets(ctx, tot->word_off.p, ooff.data(), woff.data(), G, tot->total_words);
+            delete res->unitigs;
+            res->unitigs = tot.release();
+            res->gathered = true;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        lap(6);
+    }
+    res->stage_ms[7] = now_ms() - t_start;
+    res->bytes_sent = cm->bytes_sent;
+    res->exchange_ms = cm->exchange_ms;
+    return res.release();
+}
+
+__global__ void shift_offsets_kernel(uint64_t *__restrict__ off, uint64_t first, uint64_t count, uint64_t add) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) off[first + i] += add;
+}
+
+void shift_word_offsets(sb200_ctx *ctx, uint64_t *word_off, const uint64_t *ooff, const uint64_t *woff, int G, uint64_t total_words) {
+    for (int g = 0; g < G; ++g) {
+        const uint64_t first = ooff[g] / 8, count = (ooff[g + 1] - ooff[g]) / 8;
+        if (count && woff[g]) LAUNCH(ctx, shift_offsets_kernel, div_up(count, 256), 256, 0, word_off, first, count, woff[g] / 8);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(word_off + ooff[G] / 8, &total_words, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace sb200
+
+template<class F>
+static int guarded(sb200_ctx *ctx, sb200_comm *cm, F &&f) {
+    try {
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        f();
+        return 0;
+    } catch (const sb200_error &e) {
+        ctx->last_error = e.what();
+        cudaGetLastError();
+        if (cm) cm->fail();
+        return e.code;
+    } catch (const std::exception &e) {
+        ctx->last_error = e.what();
+        if (cm) cm->fail();
+        return 3;
+    }
+}
+
+static std::string g_comm_error;
+
+extern "C" {
+
+int sb200_comm_unique_id(uint8_t *id128) {
+    try {
+        sb200::nccl_unique_id(id128);
+        return 0;
+    } catch (const std::exception &e) {
+        g_comm_error = e.what();
+        return 5;
+    }
+}
+const char *sb200_comm_last_error(void) { return g_comm_error.c_str(); }
+
+int sb200_comm_create_nccl(sb200_ctx *ctx, int rank, int world, const uint8_t *id128, sb200_comm **out) {
+    *out = nullptr;
+    return guarded(ctx, nullptr, [&] { *out = sb200::comm_create_nccl(ctx, rank, world, id128); });
+}
+int sb200_comm_create_local(int world, sb200_comm **out) {
+    try {
+        sb200::comm_create_local(world, out);
+        return 0;
+    } catch (const std::exception &e) {
+        g_comm_error = e.what();
+        return 1;
+    }
+}
+int sb200_comm_rank(const sb200_comm *c) { return c->rank; }
+int sb200_comm_size(const sb200_comm *c) { return c->size; }
+void sb200_comm_free(sb200_comm *c) { delete c; }
+
+int sb200_construct_sharded(sb200_ctx *ctx, sb200_comm *comm, const sb200_reads *reads, const sb200_construct_params *params, int gather_to,
+                            sb200_shard **out) {
+    *out = nullptr;
+    return guarded(ctx, comm, [&] {
+        SB200_REQUIRE(reads && reads->ctx == ctx, "reads belong to another context");
+        *out = sb200::construct_sharded(ctx, comm, reads, params, gather_to);
+    });
+}
+const sb200_kmers *sb200_shard_kpomers(const sb200_shard *s) { return s->kpomers; }
+const sb200_kmers *sb200_shard_kmers(const sb200_shard *s) { return s->kmers; }
+const sb200_mphf *sb200_shard_mphf(const sb200_shard *s) { return s->mphf; }
+const sb200_ext *sb200_shard_ext(const sb200_shard *s) { return s->ext; }
+const sb200_unitigs *sb200_shard_unitigs(const sb200_shard *s) { return s->unitigs; }
+int sb200_shard_info(const sb200_shard *s, sb200_shard_info_t *info) {
+    memset(info, 0, sizeof *info);
+    info->rank = s->rank; info->size = s->size;
+    info->total_kpomers = s->total_kpomers; info->total_kmers = s->total_kmers; info->total_instances = s->total_instances;
+    info->total_unitigs = s->total_unitigs; info->total_unitig_bases = s->total_unitig_bases; info->n_loops = s->n_loops; info->clipped = s->clipped;
+    info->whole_set_fallback = s->whole_set_fallback ? 1 : 0; info->gathered = s->gathered ? 1 : 0;
+    info->bytes_sent = s->bytes_sent; info->exchange_ms = s->exchange_ms;
+    for (int i = 0; i < 8; ++i) info->stage_ms[i] = s->stage_ms[i];
+    return 0;
+}
+int sb200_shard_walk_stats(const sb200_shard *s, uint64_t *out /* size x 6 */) {
+    memcpy(out, s->walk_stats.data(), s->walk_stats.size() * 8);
+    return 0;
+}
+void sb200_shard_free(sb200_shard *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    delete s;
+}
+
+}  // extern "C"

@@ -48,6 +48,15 @@ class GraphView(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("whole_set_fallback", C.c_int), ("gathered", C.c_int),
+                ("total_kpomers", C.c_uint64), ("total_kmers", C.c_uint64), ("total_instances", C.c_uint64), ("total_unitigs", C.c_uint64),
+                ("total_unitig_bases", C.c_uint64), ("n_loops", C.c_uint64), ("clipped", C.c_uint64), ("bytes_sent", C.c_uint64),
+                ("exchange_ms", C.c_double), ("stage_ms", C.c_double * 8)]
+
+
+STAGE_NAMES = ("count_kpomers", "count_kmers", "mphf", "masks", "tipclip", "unitigs", "gather", "total")
+
 EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library exports every one of them
     "sb200_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "sb200_destroy": (None, [vp]),
@@ -110,6 +119,22 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_ext_masks_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
     "sb200_unitigs_extract_local": (C.c_int, [vp, vp, vp, vp, u64p, C.POINTER(vp)]),
     "sb200_unitigs_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "sb200_comm_unique_id": (C.c_int, [u8p]),
+    "sb200_comm_last_error": (C.c_char_p, []),
+    "sb200_comm_create_nccl": (C.c_int, [vp, C.c_int, C.c_int, u8p, C.POINTER(vp)]),
+    "sb200_comm_create_local": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "sb200_comm_rank": (C.c_int, [vp]),
+    "sb200_comm_size": (C.c_int, [vp]),
+    "sb200_comm_free": (None, [vp]),
+    "sb200_construct_sharded": (C.c_int, [vp, vp, vp, C.POINTER(ConstructParams), C.c_int, C.POINTER(vp)]),
+    "sb200_shard_kpomers": (vp, [vp]),
+    "sb200_shard_kmers": (vp, [vp]),
+    "sb200_shard_mphf": (vp, [vp]),
+    "sb200_shard_ext": (vp, [vp]),
+    "sb200_shard_unitigs": (vp, [vp]),
+    "sb200_shard_info": (C.c_int, [vp, C.POINTER(ShardInfo)]),
+    "sb200_shard_walk_stats": (C.c_int, [vp, u64p]),
+    "sb200_shard_free": (None, [vp]),
     "sb200_construct": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, C.POINTER(ConstructParams), C.POINTER(vp)]),
     "sb200_graph_get": (C.c_int, [vp, C.POINTER(GraphView)]),
     "sb200_graph_free": (None, [vp]),
@@ -275,9 +300,9 @@ class KMerDiskStorage:
         return out[:self._size]
 
     def free(self):
-        if self.h:
+        if self.h and getattr(self, "owned", True):
             self.ctx.lib.sb200_kmers_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -336,9 +361,9 @@ class KMerIndex:
         return buf
 
     def free(self):
-        if self.h:
+        if self.h and getattr(self, "owned", True):
             self.ctx.lib.sb200_mphf_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -512,3 +537,113 @@ def construct(ctx, words, word_off, lens, k, num_buckets, tip_clip=False, tip_le
     n = len(word_off) - 1
     ctx.check(ctx.lib.sb200_construct(ctx.h, _p(words, u64p), _p(word_off, u64p), _p(lens, u32p), n, C.byref(p), C.byref(h)))
     return Graph(ctx, h)
+
+
+# ---- hash-sharded path: one call per rank (csrc/shard.cu) -----------------------------------------------------------------------
+def download_unitigs(ctx, h):
+    """(words, word_off, len) of a sb200_unitigs handle"""
+    lib = ctx.lib
+    n, nw = lib.sb200_unitigs_count(h), lib.sb200_unitigs_total_words(h)
+    words = np.zeros(max(nw, 1), dtype=np.uint64)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    lens = np.zeros(max(n, 1), dtype=np.uint32)
+    ctx.check(lib.sb200_unitigs_download(h, _p(words, u64p), _p(off, u64p), _p(lens, u32p)))
+    return words[:nw], off, lens[:n]
+
+
+class Comm:
+    """sb200_comm: NCCL (one rank per GPU) or local (virtual ranks = threads of this process)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+        self.rank, self.size = lib.sb200_comm_rank(handle), lib.sb200_comm_size(handle)
+
+    @staticmethod
+    def unique_id():
+        lib = load_library()
+        buf = np.zeros(128, dtype=np.uint8)
+        if lib.sb200_comm_unique_id(_p(buf, u8p)) != 0:
+            raise Sb200Error(lib.sb200_comm_last_error().decode())
+        return buf
+
+    @classmethod
+    def nccl(cls, ctx, rank, world, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        h = vp()
+        ctx.check(ctx.lib.sb200_comm_create_nccl(ctx.h, rank, world, _p(uid, u8p), C.byref(h)))
+        return cls(ctx.lib, h)
+
+    @classmethod
+    def local(cls, world):
+        lib = load_library()
+        arr = (vp * world)()
+        if lib.sb200_comm_create_local(world, arr) != 0:
+            raise Sb200Error(lib.sb200_comm_last_error().decode())
+        return [cls(lib, vp(arr[r])) for r in range(world)]
+
+    def free(self):
+        if self.h:
+            self.lib.sb200_comm_free(self.h)
+            self.h = None
+
+
+class Shard:
+    """One rank's result of sb200_construct_sharded: its shards of both k-mer tables, the whole index + masks, its unitig slice."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        lib = ctx.lib
+        info = ShardInfo()
+        lib.sb200_shard_info(handle, C.byref(info))
+        self.info = info
+        self.stage_ms = {STAGE_NAMES[i]: float(info.stage_ms[i]) for i in range(8)}
+        self.kpomers = KMerDiskStorage(ctx, vp(lib.sb200_shard_kpomers(handle)))
+        self.kpomers.owned = False
+        self.kmers = KMerDiskStorage(ctx, vp(lib.sb200_shard_kmers(handle)))
+        self.kmers.owned = False
+        self.index = KMerIndex.__new__(KMerIndex)
+        self.index.ctx, self.index.storage, self.index.h, self.index.owned = ctx, self.kmers, vp(lib.sb200_shard_mphf(handle)), False
+        self.ext = vp(lib.sb200_shard_ext(handle))
+        self.unitigs_h = vp(lib.sb200_shard_unitigs(handle))
+
+    def masks(self):
+        """PerfectHashMap::data_ of the WHOLE index (every rank holds all of it)"""
+        out = np.zeros(max(self.info.total_kmers, 1), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.sb200_ext_masks_download(self.ext, _p(out, u8p)))
+        return out[:self.info.total_kmers]
+
+    def idx(self):
+        n = self.kmers.total_kmers()
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.sb200_ext_idx_download(self.ext, _p(out, u32p)))
+        return out[:n].astype(np.uint64)
+
+    def walk_stats(self):
+        out = np.zeros(6 * self.info.size, dtype=np.uint64)
+        self.ctx.lib.sb200_shard_walk_stats(self.h, _p(out, u64p))
+        return out.reshape(self.info.size, 6)
+
+    def unitigs_packed(self):
+        return download_unitigs(self.ctx, self.unitigs_h)
+
+    def unitigs(self):
+        return unpack_sequences(*self.unitigs_packed())
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sb200_shard_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def construct_sharded(ctx, comm, reads, k, num_buckets, tip_clip=False, tip_length_bound=0, with_loops=True, gather_to=-1):
+    """This rank's part of the hash-sharded path (every rank of `comm` must call it, each with its own slice of the reads)."""
+    p = ConstructParams(k, num_buckets, int(tip_clip), tip_length_bound, int(with_loops), 0)
+    h = vp()
+    ctx.check(ctx.lib.sb200_construct_sharded(ctx.h, comm.h, reads.h, C.byref(p), int(gather_to), C.byref(h)))
+    return Shard(ctx, h)

@@ -1,7 +1,8 @@
-"""world_size-2 gloo test of the exchange logic of the sharded path (spades_for_blackbird_b200/host/distributed.py):
-ownership by bucket range, all-to-all of variable-sized record groups, shard-wise sort/dedup/count — with a small CPU
-stand-in for the per-rank compute (pure Python on the oracle's primitives; the CUDA backend is tested on the GPU in
-tests/test_gpu_sharded.py).  Shards concatenated in rank order must equal the oracle's single-process k-mer sets."""
+"""world_size-2 gloo test of the exchange protocol of the sharded path (the model in spades_for_blackbird_b200/host/distributed.py of
+what csrc/shard.cu does over NCCL): ownership by bucket range, all-to-all of variable-sized record groups, shard-wise sort / dedup /
+count — with a small CPU stand-in for the per-rank compute (pure Python on the oracle's primitives; the CUDA path is tested on the
+GPU in tests/test_gpu_sharded.py and, on real NCCL, tests/test_gpu_nccl.py).  Shards concatenated in rank order must equal the oracle's
+single-process k-mer sets."""
 import os
 import socket
 import sys
@@ -112,21 +113,20 @@ def _worker(rank, world, port, k, B, reads, out_dir):
         be = CpuShardBackend(O)
         n = len(reads)
         mine = reads[n * rank // world: n * (rank + 1) // world]
-        kp = D.count_shard(be, comm, lambda: be.extract_partition(mine, k + 1, B, world), k + 1, B, True, True)
-        km = D.count_shard(be, comm, lambda: be.derive_partition(kp, B, world), k, B, False, False)
+        kp = D.count_shard(be, comm, lambda: be.extract_partition(mine, k + 1, B, world), k + 1, B, True)
+        km = D.count_shard(be, comm, lambda: be.derive_partition(kp, B, world), k, B, False)
         # ownership: only my bucket range
         lo, hi = rank * B // world, (rank + 1) * B // world
         assert all(lo <= b < hi for b in kp.buckets) and all(lo <= b < hi for b in km.buckets)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), kp=kp.records, kc=kp.counts, km=km.records)
-        # gather_v / all_reduce plumbing
+        # launcher plumbing: every rank's slice of a packed read set, re-based; the union is the whole set
+        words, word_off, lens = O.pack_reads(reads)
+        w, o, ln = D.slice_reads(words, word_off, lens, rank, world)
+        assert int(o[0]) == 0 and len(o) == len(ln) + 1 and int(o[-1]) == len(w)
         import torch
-        t = torch.arange(rank + 2, dtype=torch.int64)
-        g = comm.gather_v(t, 0)
-        if rank == 0:
-            assert [int(x.numel()) for x in g] == [r + 2 for r in range(world)]
-        s = torch.ones(4, dtype=torch.int64) * (rank + 1)
-        comm.all_reduce_sum_(s)
-        assert int(s[0]) == world * (world + 1) // 2
+        tot = torch.tensor([len(ln), len(w)], dtype=torch.int64)
+        comm.all_reduce_sum_(tot)
+        assert tot.tolist() == [len(lens), len(words)]
     finally:
         dist.destroy_process_group()
 
