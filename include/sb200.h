@@ -117,6 +117,22 @@ int  sb200_unitigs_download(const sb200_unitigs *u, uint64_t *words_out, uint64_
                             uint32_t *len_out);
 void sb200_unitigs_free(sb200_unitigs *u);
 
+/* ---- coverage: CoverageHashMapBuilder::BuildIndex (ph_map/coverage_hash_map_builder.hpp:15-54) — PerfectHashMap<RtSeq, uint32_t> over
+ *      the (k+1)-mers = a KMerIndex of the (k+1)-mer storage + one multiplicity per (k+1)-mer in ITS index order (no second pass over
+ *      the reads: the multiplicities are the run lengths of sb200_count) — and GraphCoverageFiller / FillCoverageAndFlankingFromPHM
+ *      (assembly_graph/graph_support/coverage_filling.hpp:16-95) over the unitigs: kc[i] = sum of the multiplicities of the (k+1)-mers
+ *      of sequence i (CoverageIndex raw coverage, GFA KC:i; DP:f = kc / (length - k)); flank[2i], flank[2i+1] = the same over its first /
+ *      last `averaging_range` (k+1)-mers (FlankingCoverage raw coverage of the edge / of its conjugate; spades-gbuilder -c uses 50,
+ *      projects/gbuilder/main.cpp:200-211). --------------------------------------------------------------------------------------- */
+typedef struct sb200_covmap sb200_covmap;
+int  sb200_coverage_map_build(sb200_ctx *ctx, const sb200_kmers *kpomers, sb200_covmap **out);
+const sb200_mphf *sb200_coverage_map_index(const sb200_covmap *c);          /* borrowed: KMerIndex over the (k+1)-mers            */
+uint64_t sb200_coverage_map_size(const sb200_covmap *c);
+int  sb200_coverage_map_values_download(const sb200_covmap *c, uint32_t *values_out /* size, index order = data_ */);
+void sb200_coverage_map_free(sb200_covmap *c);
+int  sb200_unitigs_coverage(sb200_ctx *ctx, const sb200_covmap *c, const sb200_unitigs *u, uint32_t averaging_range,
+                            uint64_t *kc_out /* count */, uint64_t *flank_out /* 2 * count, or NULL */);
+
 /* ---- hash-sharded path (several GPUs, one process each): the same stages with the shuffle points exposed.
  *      GPU g of G owns the buckets [g*B/G, (g+1)*B/G) of KMerSegmentPolicy — a contiguous range of the reference's file
  *      order — so the shards concatenated in rank order are the single-GPU (= reference) result.  The reference has no

@@ -447,6 +447,7 @@ private:
         const Context &c = index_.ctx();
         c.check(sb200_unitigs_extract(c.get(), index_.kmers().get(), index_.index().get(), index_.ext(), with_loops, &u));
         std::shared_ptr<sb200_unitigs> guard(u, sb200_unitigs_free);
+        last_ = guard;   // stays resident for the coverage filler (CoverageHashMap::FillCoverageAndFlanking)
         uint64_t n = sb200_unitigs_count(u);
         std::vector<uint64_t> words(sb200_unitigs_total_words(u) + 1), off(n + 1);
         std::vector<uint32_t> len(n + 1);
@@ -458,13 +459,47 @@ private:
     }
     DeBruijnExtensionIndex &index_;
     size_t k_;
+    mutable std::shared_ptr<sb200_unitigs> last_;
+public:
+    const sb200_unitigs *device_sequences() const { return last_.get(); }   // the last result, still in HBM
 };
 
-// CoverageHashMapBuilder::BuildIndex + FillCoverageFromStream: the reference builds a second MPHF over the (k+1)-mers
-// and re-streams the reads; on the GPU the multiplicities are the run lengths of the counting sort (self-reverse-
-// complement (k+1)-mers count twice, coverage_hash_map_builder.hpp:31-36).  Values come in (k+1)-mer FILE order.
+// utils::PerfectHashMap<RtSeq, uint32_t> of CoverageHashMapBuilder::BuildIndex (ph_map/coverage_hash_map_builder.hpp:39-54): the
+// reference builds a second MPHF over the (k+1)-mers and re-streams the reads; on the GPU the multiplicities are the run lengths of
+// the counting sort (self-reverse-complement (k+1)-mers count twice, :31-36), moved into the index order of the same BooPHF.
+class CoverageHashMap {
+public:
+    CoverageHashMap(const Context &ctx, const KMerDiskStorage &kpomers) : ctx_(ctx) {
+        sb200_covmap *h = nullptr;
+        ctx.check(sb200_coverage_map_build(ctx.get(), kpomers.get(), &h));
+        h_.reset(h, sb200_coverage_map_free);
+    }
+    size_t size() const { return (size_t) sb200_coverage_map_size(h_.get()); }
+    std::vector<uint32_t> data() const {   // data_: one count per (k+1)-mer in index order
+        std::vector<uint32_t> v(size());
+        if (!v.empty()) ctx_.check(sb200_coverage_map_values_download(h_.get(), v.data()));
+        return v;
+    }
+    // FillCoverageAndFlankingFromPHM (assembly_graph/graph_support/coverage_filling.hpp:89-95) over the sequences the extractor left in
+    // HBM: kc[i] = raw coverage of edge i (GFA KC:i), flank[2i] / flank[2i + 1] = raw flanking coverage of edge i / of its conjugate
+    void FillCoverageAndFlanking(const UnbranchingPathExtractor &ex, std::vector<uint64_t> &kc, std::vector<uint64_t> &flank,
+                                 unsigned averaging_range = 50) const {
+        const sb200_unitigs *u = ex.device_sequences();
+        if (!u) throw Error(1, "run the extractor first");
+        const size_t n = (size_t) sb200_unitigs_count(u);
+        kc.assign(n, 0);
+        flank.assign(2 * n, 0);
+        if (n) ctx_.check(sb200_unitigs_coverage(ctx_.get(), h_.get(), u, averaging_range, kc.data(), flank.data()));
+    }
+private:
+    const Context &ctx_;
+    std::shared_ptr<sb200_covmap> h_;
+};
+
 struct CoverageHashMapBuilder {
+    // values in (k+1)-mer FILE order (what coverage.u32 of the reference driver lists)
     std::vector<uint32_t> FillCoverage(const KMerDiskStorage &kpomers) const { return kpomers.counts(); }
+    CoverageHashMap BuildIndex(const Context &ctx, const KMerDiskStorage &kpomers) const { return CoverageHashMap(ctx, kpomers); }
 };
 
 // ---- the step right after the path: graph from the unitigs, GFA out ------------------------------------------------------------
@@ -472,8 +507,8 @@ struct CoverageHashMapBuilder {
 // the sequence is its own reverse complement); every sequence leaves a start and an end LinkRecord keyed by the MPHF index of
 // its canonical first / last k-mer (one batched KMerIndex::seq_idx on the GPU instead of one lookup per record); records are
 // sorted and every distinct index becomes a vertex pair (v, conjugate v) with ids min_id + 2j, min_id + 2j + 1.  WriteGFA
-// emits what gfa::GFAWriter::WriteSegmentsAndLinks emits for that graph (no coverage: DP:f:0 KC:i:0, as spades-gbuilder
-// without -c).  Lines come in id order; the reference's order of L lines depends on its adjacency containers, so files are
+// emits what gfa::GFAWriter::WriteSegmentsAndLinks emits for that graph (DP:f:0 KC:i:0 as spades-gbuilder without -c; with
+// SetCoverage the values FillCoverageAndFlankingFromPHM leaves, as with -c).  Lines come in id order; the reference's order of L lines depends on its adjacency containers, so files are
 // compared after sorting the lines.
 class CondensedGraph {
 public:
@@ -528,9 +563,15 @@ public:
     const std::vector<Vertex> &vertices() const { return vertices_; }
     uint64_t conjugate(uint64_t e) const { return self_conj_[(e - ID_BIAS) >> 1] ? e : (((e - ID_BIAS) ^ 1u) + ID_BIAS); }
 
+    // per-edge raw coverage (CoverageHashMap::FillCoverageAndFlanking): spades-gbuilder -c
+    void SetCoverage(const std::vector<uint64_t> &kc) { kc_ = kc; }
+    double coverage(size_t i) const {   // CoverageIndex::coverage: raw coverage / length in (k+1)-mers (assembly_graph/core/coverage.hpp:58-60)
+        return kc_.empty() ? 0.0 : (double) kc_[i] / (double) (edges_[i].size() - k_);
+    }
+
     void WriteGFA(std::ostream &os) const {
-        for (size_t i = 0; i < edges_.size(); ++i)
-            os << "S\t" << (ID_BIAS + 2 * i) << '\t' << edges_[i].str() << "\tDP:f:0\tKC:i:0\n";
+        for (size_t i = 0; i < edges_.size(); ++i)   // gfa_writer.cpp:18-26: DP:f:<float(coverage)> KC:i:<raw coverage>
+            os << "S\t" << (ID_BIAS + 2 * i) << '\t' << edges_[i].str() << "\tDP:f:" << float(coverage(i)) << "\tKC:i:" << (kc_.empty() ? 0 : kc_[i]) << '\n';
         for (const Vertex &v : vertices_)
             for (uint64_t inc : v.incoming)
                 for (uint64_t out : v.outgoing)
@@ -564,7 +605,7 @@ private:
     struct End { size_t vertex; bool conj; };
     std::string fastg_name(uint64_t e) const {
         const uint64_t c = name(e);
-        return "EDGE_" + std::to_string(c) + "_length_" + std::to_string(edges_[(c - ID_BIAS) >> 1].size()) + "_cov_" + std::to_string(0.0) +
+        return "EDGE_" + std::to_string(c) + "_length_" + std::to_string(edges_[(c - ID_BIAS) >> 1].size()) + "_cov_" + std::to_string(coverage((c - ID_BIAS) >> 1)) +
                (e == c ? "" : "'");
     }
     uint64_t name(uint64_t e) const { return std::min(e, conjugate(e)); }          // io::CanonicalEdgeHelper (io/utils/edge_namer.hpp:71-86)
@@ -574,6 +615,7 @@ private:
     std::vector<uint8_t> self_conj_;
     std::vector<Vertex> vertices_;
     std::vector<End> end_of_;   // by oriented edge (id - ID_BIAS)
+    std::vector<uint64_t> kc_;  // raw coverage per edge (empty: no coverage, DP:f:0 KC:i:0 as spades-gbuilder without -c)
 };
 
 }  // namespace sb200

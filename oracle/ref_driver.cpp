@@ -36,6 +36,7 @@
 //   masks_idx.u8       the data_ array itself, i.e. masks in MPHF-index order
 //   unitigs.txt        one sequence per line, in the reference's output order (paths, then loops)
 //   coverage.u32       per (k+1)-mer multiplicity in kpomer file order (if --coverage)
+//   graph_cov.gfa      graph.gfa after FillCoverageAndFlankingFromPHM (spades-gbuilder -c); flanking.txt: raw flanking coverage per edge / conjugate
 //   timing.txt         phase wall times in seconds
 #include "utils/extension_index/kmer_extension_index_builder.hpp"
 #include "utils/ph_map/coverage_hash_map_builder.hpp"
@@ -48,6 +49,7 @@
 #include "io/reads/converting_reader_wrapper.hpp"
 #include "io/reads/binary_converter.hpp"
 #include "assembly_graph/core/graph.hpp"
+#include "assembly_graph/graph_support/coverage_filling.hpp"
 #include "io/graph/gfa_writer.hpp"
 #include "io/graph/fastg_writer.hpp"
 #include "utils/logger/log_writers.hpp"
@@ -252,11 +254,11 @@ int main(int argc, char **argv) {
 
         // Coverage needs the streams again and must run before extraction only because extraction
         // does not touch the (k+1)-mer storage; order is irrelevant to the result.
+        using CoverageMap = utils::PerfectHashMap<RtSeq, uint32_t, utils::slim_kmer_index_traits<RtSeq>,
+                                                  utils::DefaultStoring>;
+        CoverageMap cov(k + 1);
         if (a.coverage) {
             double tc = now();
-            using CoverageMap = utils::PerfectHashMap<RtSeq, uint32_t, utils::slim_kmer_index_traits<RtSeq>,
-                                                      utils::DefaultStoring>;
-            CoverageMap cov(k + 1);
             utils::CoverageHashMapBuilder().BuildIndex(cov, kpomers, streams);
             timing << "coverage " << now() - tc << "\n";
             const double t_dump3 = now();
@@ -292,6 +294,19 @@ int main(int argc, char **argv) {
             const std::string fastg_name = a.out + "/graph.fastg";
             io::FastgWriter fastg_writer(g, fastg_name);
             fastg_writer.WriteSegmentsAndLinks();
+            if (a.coverage) {
+                // spades-gbuilder -c (main.cpp:200-211): per-edge coverage from the (k+1)-mer multiplicities
+                // (GraphCoverageFiller, assembly_graph/graph_support/coverage_filling.hpp:16-95), then the same GFA with DP:f / KC:i
+                omnigraph::FlankingCoverage<debruijn_graph::DeBruijnGraph> flanking_cov(g, 50);
+                debruijn_graph::FillCoverageAndFlankingFromPHM(cov, g, flanking_cov);
+                std::ofstream gc(a.out + "/graph_cov.gfa");
+                gfa::GFAWriter cov_writer(g, gc);
+                cov_writer.WriteSegmentsAndLinks();
+                // FlankingCoverage::GetInCov / GetOutCov of every canonical edge (detail_coverage.hpp), one line per edge in id order
+                std::ofstream fl(a.out + "/flanking.txt");
+                for (debruijn_graph::EdgeId e : g.canonical_edges())
+                    fl << g.int_id(e) << '\t' << flanking_cov.RawCoverage(e) << '\t' << flanking_cov.RawCoverage(g.conjugate(e)) << '\n';
+            }
         }
     } else {
         std::cerr << "bad mode\n";

@@ -70,10 +70,37 @@ def _graph(unitigs, k, seq_idx):
     return conj, vertices, end
 
 
-def gfa_lines(unitigs, k, seq_idx):
-    """unitigs: list[str] in extractor order; seq_idx(str canonical k-mer) -> MPHF index.  Returns the GFA lines in id order."""
+def edge_coverage(unitigs, k, count_of, averaging_range=50):
+    """GraphCoverageFiller::FillCoverageFromEdges (A/assembly_graph/graph_support/coverage_filling.hpp:45-63): per sequence the sum of
+    the multiplicities of its (k+1)-mers (count_of(canonical (k+1)-mer string) -> CoverageHashMap value) and the same over its first /
+    last `averaging_range` (k+1)-mers (FlankingCoverage of the edge / of its conjugate).  Returns (kc, [(start, end)])."""
+    kc, flank = [], []
+    for u in unitigs:
+        vals = []
+        for p in range(len(u) - k):
+            x = u[p:p + k + 1]
+            r = _rc(x)
+            vals.append(count_of(x if x <= r else r))
+        rng = min(averaging_range, len(vals))
+        kc.append(sum(vals))
+        flank.append((sum(vals[:rng]), sum(vals[len(vals) - rng:])))
+    return kc, flank
+
+
+def cxx_float(x):
+    """what `os << float(x)` prints (io/graph/gfa_writer.cpp:18-26: DP:f): the value rounded to binary32, then %g with 6 significant digits"""
+    import struct
+    return "%g" % struct.unpack("f", struct.pack("f", x))[0]
+
+
+def gfa_lines(unitigs, k, seq_idx, kc=None):
+    """unitigs: list[str] in extractor order; seq_idx(str canonical k-mer) -> MPHF index; kc: per-sequence raw coverage (spades-gbuilder
+    -c) or None.  Returns the GFA lines in id order."""
     conj, vertices, _ = _graph(unitigs, k, seq_idx)
-    lines = ["S\t%d\t%s\tDP:f:0\tKC:i:0" % (ID_BIAS + 2 * i, u) for i, u in enumerate(unitigs)]
+    if kc is None:
+        lines = ["S\t%d\t%s\tDP:f:0\tKC:i:0" % (ID_BIAS + 2 * i, u) for i, u in enumerate(unitigs)]
+    else:   # coverage(e) = raw coverage / length(e), length = number of (k+1)-mers (A/assembly_graph/core/coverage.hpp:58-60)
+        lines = ["S\t%d\t%s\tDP:f:%s\tKC:i:%d" % (ID_BIAS + 2 * i, u, cxx_float(float(kc[i]) / float(len(u) - k)), kc[i]) for i, u in enumerate(unitigs)]
     for inc, out in vertices:
         for a in inc:
             for b in out:

@@ -380,11 +380,22 @@ uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, con
         for (int l = 0; l < MPHF_LEVELS; ++l) {
             size_t t = (size_t) b * MPHF_LEVELS + l;
             uint64_t size = m->domain_host[t];
-            uint64_t nchar = size ? 1 + size / 64 : 0;   // empty bucket: default-constructed bit-vectors
+            if (size == 0) {
+                // Empty bucket: the reference leaves default-constructed bit-vectors (size 0, _nchar never set: what ITS save() writes for
+                // them is undefined, BooPHF.h:137-140,316-323).  We write what its load() expects to read back for size 0 — resize(0)
+                // makes one word (BooPHF.h:204-208,325-335) — so that KMerIndex::deserialize of these bytes is well-defined.
+                uint64_t one = 1, zero = 0;
+                put(&size, 8);
+                put(&one, 8);
+                put(&zero, 8);
+                put(&zero, 8);   // no rank samples
+                continue;
+            }
+            uint64_t nchar = 1 + size / 64;
             uint64_t nr = (nchar + 7) / 8;
             put(&size, 8);
             put(&nchar, 8);
-            if (nchar) put_bulk(bits_host, m->word_off_host[t], nchar * 8);
+            put_bulk(bits_host, m->word_off_host[t], nchar * 8);
             put(&nr, 8);
             if (nr) put_bulk(ranks_host, m->rank_off_host[t], nr * 8);
         }
@@ -418,9 +429,10 @@ void mphf_serialize_device(sb200_ctx *ctx, const sb200_mphf *m, uint8_t *out_dev
         for (int l = 0; l < MPHF_LEVELS; ++l) {
             size_t t = (size_t) b * MPHF_LEVELS + l;
             uint64_t size = m->domain_host[t];
-            uint64_t nchar = size ? 1 + size / 64 : 0, nr = (nchar + 7) / 8;
+            if (size == 0) { off += 32; continue; }   // empty bucket: size, nchar = 1, one zero word, no rank samples (host-written)
+            uint64_t nchar = 1 + size / 64, nr = (nchar + 7) / 8;
             off += 16;
-            if (nchar) segs.push_back(SerSeg{off, m->word_off_host[t], nchar, 0u, 0u});
+            segs.push_back(SerSeg{off, m->word_off_host[t], nchar, 0u, 0u});
             off += nchar * 8 + 8;
             if (nr) segs.push_back(SerSeg{off, m->rank_off_host[t], nr, 1u, 0u});
             off += nr * 8;

@@ -119,6 +119,12 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_ext_masks_device": (C.c_int, [vp, C.POINTER(vp), u64p]),
     "sb200_unitigs_extract_local": (C.c_int, [vp, vp, vp, vp, u64p, C.POINTER(vp)]),
     "sb200_unitigs_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "sb200_coverage_map_build": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "sb200_coverage_map_index": (vp, [vp]),
+    "sb200_coverage_map_size": (C.c_uint64, [vp]),
+    "sb200_coverage_map_values_download": (C.c_int, [vp, u32p]),
+    "sb200_coverage_map_free": (None, [vp]),
+    "sb200_unitigs_coverage": (C.c_int, [vp, vp, vp, C.c_uint32, u64p, u64p]),
     "sb200_comm_unique_id": (C.c_int, [u8p]),
     "sb200_comm_last_error": (C.c_char_p, []),
     "sb200_comm_create_nccl": (C.c_int, [vp, C.c_int, C.c_int, u8p, C.POINTER(vp)]),
@@ -463,23 +469,28 @@ class UnbranchingPathExtractor:
     def __init__(self, index, k):
         self.index, self.k = index, k
         self.n_loops = 0
+        self.h = None   # the last result stays in HBM (CoverageHashMap.edge_coverage reads it there) until free()
 
     def _run(self, with_loops):
         ix = self.index
         lib, ctx = ix.ctx.lib, ix.ctx
+        self.free()
         h = vp()
         ctx.check(lib.sb200_unitigs_extract(ctx.h, ix.kmers.h, ix.index.h, ix.h, int(with_loops), C.byref(h)))
+        self.h = h
+        self.n_loops = lib.sb200_unitigs_loops(h)
+        return download_unitigs(ctx, h)
+
+    def free(self):
+        if self.h:
+            self.index.ctx.lib.sb200_unitigs_free(self.h)
+            self.h = None
+
+    def __del__(self):
         try:
-            n = lib.sb200_unitigs_count(h)
-            self.n_loops = lib.sb200_unitigs_loops(h)
-            nw = lib.sb200_unitigs_total_words(h)
-            words = np.zeros(max(nw, 1), dtype=np.uint64)
-            off = np.zeros(n + 1, dtype=np.uint64)
-            lens = np.zeros(max(n, 1), dtype=np.uint32)
-            ctx.check(lib.sb200_unitigs_download(h, _p(words, u64p), _p(off, u64p), _p(lens, u32p)))
-        finally:
-            lib.sb200_unitigs_free(h)
-        return words[:nw], off, lens[:n]
+            self.free()
+        except Exception:
+            pass
 
     def ExtractUnbranchingPaths(self, nchunks=1, packed=False):
         r = self._run(False)
@@ -488,6 +499,45 @@ class UnbranchingPathExtractor:
     def ExtractUnbranchingPathsAndLoops(self, nchunks=1, packed=False):
         r = self._run(True)
         return r if packed else unpack_sequences(*r)
+
+
+class CoverageHashMap:
+    """utils::PerfectHashMap<RtSeq, uint32_t> of CoverageHashMapBuilder::BuildIndex (ph_map/coverage_hash_map_builder.hpp:39-54): a KMerIndex
+    over the (k+1)-mer storage + the multiplicity of every (k+1)-mer in index order; edge_coverage() is GraphCoverageFiller
+    (assembly_graph/graph_support/coverage_filling.hpp:45-95) over a unitig set."""
+
+    def __init__(self, ctx, kpomers):
+        self.ctx, self.kpomers = ctx, kpomers
+        h = vp()
+        ctx.check(ctx.lib.sb200_coverage_map_build(ctx.h, kpomers.h, C.byref(h)))
+        self.h = h
+        self.index = KMerIndex.__new__(KMerIndex)
+        self.index.ctx, self.index.storage, self.index.h, self.index.owned = ctx, kpomers, vp(ctx.lib.sb200_coverage_map_index(h)), False
+
+    def data(self):
+        n = self.ctx.lib.sb200_coverage_map_size(self.h)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.sb200_coverage_map_values_download(self.h, _p(out, u32p)))
+        return out[:n]
+
+    def edge_coverage(self, unitigs_handle, averaging_range=50):
+        """(kc, flank) for the sequences of a sb200_unitigs handle: kc[i] = KC:i of GFA, flank[i] = (start, end) raw flanking coverage"""
+        n = self.ctx.lib.sb200_unitigs_count(unitigs_handle)
+        kc = np.zeros(max(n, 1), dtype=np.uint64)
+        fl = np.zeros(max(2 * n, 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.sb200_unitigs_coverage(self.ctx.h, self.h, unitigs_handle, averaging_range, _p(kc, u64p), _p(fl, u64p)))
+        return kc[:n], fl[:2 * n].reshape(-1, 2)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sb200_coverage_map_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Graph:

@@ -29,6 +29,7 @@ def load_golden(name):
     d["unitigs"] = [str(u) for u in d["unitigs"]]
     d["gfa"] = [str(l) for l in d["gfa"]]
     d["fastg"] = [str(l) for l in d["fastg"]]
+    d["gfa_cov"] = [str(l) for l in d["gfa_cov"]]
     d["name"] = name
     return d
 

@@ -9,6 +9,7 @@ Each fixture holds the input reads and every artefact the reference produced for
   kmers / idx / masks_idx / index_bin     final_kmers, MPHF index of each, InOutMask array in index order, KMerIndex::serialize
   unitigs / clipped                       UnbranchingPathExtractor output (reference order) / tip-clipper count
   gfa / fastg                             FastGraphFromSequencesConstructor + gfa::GFAWriter / io::FastgWriter on those unitigs, lines / records sorted
+  gfa_cov / flanking                      the same GFA after FillCoverageAndFlankingFromPHM (spades-gbuilder -c), raw flanking coverage per edge
   kc_final                                spades-kmercount style final_kmers (non-canonical, 16 buckets)
 """
 import os
@@ -63,6 +64,13 @@ def run_ref(reads, k, buckets, mode="gbuilder", tip_bound=None, coverage=True, t
         # spades-gbuilder --fastg: one FASTA record per oriented edge; compared record by record after sorting
         with open(os.path.join(out, "graph.fastg")) as f:
             res["fastg"] = np.array(sorted(">" + r.rstrip("\n") for r in f.read().split(">") if r.strip()))
+        if coverage:
+            # spades-gbuilder -c: the same graph after FillCoverageAndFlankingFromPHM (DP:f / KC:i filled), and the raw flanking
+            # coverage of every canonical edge / its conjugate (id order)
+            with open(os.path.join(out, "graph_cov.gfa")) as f:
+                res["gfa_cov"] = np.array(sorted(l.rstrip("\n") for l in f if l.strip()))
+            res["flanking"] = np.array([[int(x) for x in l.split()] for l in open(os.path.join(out, "flanking.txt")) if l.strip()],
+                                       dtype=np.int64).reshape(-1, 3)
         clipped = 0
         for line in open(os.path.join(out, "timing.txt")):
             if line.startswith("clipped "):

@@ -83,6 +83,10 @@ def test_gbuilder_files_equal_reference(tool, tmp_path, golden):
     # follows its adjacency containers)
     assert sorted(open(tmp_path / "graph.gfa").read().splitlines()) == list(g["gfa"])
     assert sorted(">" + r.rstrip("\n") for r in open(tmp_path / "graph.fastg").read().split(">") if r.strip()) == list(g["fastg"])
+    # spades-gbuilder -c — per-edge coverage from the (k+1)-mer multiplicities (DP:f / KC:i), flanking coverage
+    assert sorted(open(tmp_path / "graph_cov.gfa").read().splitlines()) == list(g["gfa_cov"])
+    fl = np.array([[int(x) for x in l.split()] for l in open(tmp_path / "flanking.txt")], dtype=np.int64).reshape(-1, 3)
+    assert np.array_equal(fl[np.argsort(fl[:, 0])], g["flanking"][np.argsort(g["flanking"][:, 0])])
     # second run from the binary read files it wrote (io::BinaryFileStream path): same graph
     out2 = tmp_path / "o2"
     out2.mkdir()

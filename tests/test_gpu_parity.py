@@ -45,7 +45,23 @@ def test_golden_whole_path(ctx, golden):
     if g["tip_bound"] >= 0:
         assert B.EarlyTipClipperProcessor(index, g["tip_bound"]).ClipTips() == int(g["clipped"])
     assert np.array_equal(index.data(), g["masks_idx"])
-    assert B.UnbranchingPathExtractor(index, g["k"]).ExtractUnbranchingPathsAndLoops() == g["unitigs"]
+    ex = B.UnbranchingPathExtractor(index, g["k"])
+    assert ex.ExtractUnbranchingPathsAndLoops() == g["unitigs"]
+    # the coverage map (a KMerIndex over the (k+1)-mers + counts in ITS index order) and the per-edge coverage
+    cov = B.CoverageHashMap(ctx, kpomers)
+    kp_idx = cov.index.seq_idx(kpomers.final_kmers())
+    assert np.array_equal(np.sort(kp_idx), np.arange(kpomers.total_kmers(), dtype=np.uint64))       # minimal perfect over the (k+1)-mers
+    assert np.array_equal(cov.data()[kp_idx.astype(np.int64)], g["coverage"])                         # PerfectHashMap<RtSeq, uint32_t>::data_
+    kc, flank = cov.edge_coverage(ex.h, 50)
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sb200_gfa
+    idx_of = {tuple(int(v) for v in rec): int(i) for rec, i in zip(index.kmers.final_kmers(), g["idx"])}
+    lines = sb200_gfa.gfa_lines(g["unitigs"], g["k"], lambda s: idx_of[tuple(int(v) for v in O.pack_reads([s])[0])], kc=[int(x) for x in kc])
+    assert sorted(lines) == g["gfa_cov"]                                                             # spades-gbuilder -c: DP:f / KC:i
+    fl = g["flanking"][np.argsort(g["flanking"][:, 0])]
+    assert np.array_equal(flank.astype(np.int64), fl[:, 1:])                                          # FlankingCoverage raw values
+    cov.free(); ex.free()
 
 
 def test_golden_kmercount(ctx, golden):

@@ -83,7 +83,8 @@ int main(int argc, char **argv) {
             std::ofstream ib(out + "/index.bin", std::ios::binary);
             index.index().serialize(ib);
         }
-        std::vector<sb200::Sequence> edges = sb200::UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops(threads * 16);
+        sb200::UnbranchingPathExtractor extractor(index, k);
+        std::vector<sb200::Sequence> edges = extractor.ExtractUnbranchingPathsAndLoops(threads * 16);
         double t1 = now();
         kpomers.write_final_kmers(out + "/kpomers");
         index.kmers().write_final_kmers(out + "/final_kmers");
@@ -100,6 +101,17 @@ int main(int argc, char **argv) {
             graph.WriteGFA(gf);
             std::ofstream fg(out + "/graph.fastg");   // spades-gbuilder --fastg
             graph.WriteFASTG(fg);
+            if (coverage) {   // spades-gbuilder -c (main.cpp:200-211): coverage map over the (k+1)-mers, per-edge coverage, the same GFA with DP:f / KC:i
+                sb200::CoverageHashMap cov = sb200::CoverageHashMapBuilder().BuildIndex(ctx, kpomers);
+                std::vector<uint64_t> kc, flank;
+                cov.FillCoverageAndFlanking(extractor, kc, flank, 50);
+                graph.SetCoverage(kc);
+                std::ofstream gc(out + "/graph_cov.gfa");
+                graph.WriteGFA(gc);
+                std::ofstream fl(out + "/flanking.txt");
+                for (size_t i = 0; i < kc.size(); ++i)
+                    fl << (sb200::CondensedGraph::ID_BIAS + 2 * i) << '\t' << flank[2 * i] << '\t' << flank[2 * i + 1] << '\n';
+            }
         }
         printf("%zu (k+1)-mers, %zu k-mers, %zu unitigs, %.3f s on device incl. transfers, %llu kernel launches\n", kpomers.total_kmers(),
                index.size(), edges.size(), t1 - t0, (unsigned long long) ctx.kernel_launches());
