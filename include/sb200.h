@@ -86,6 +86,9 @@ uint64_t sb200_mphf_size(const sb200_mphf *m);                                  
 uint64_t sb200_mphf_mem_size(const sb200_mphf *m);                              /* KMerIndex::mem_size(), bytes        */
 /* KMerIndex::seq_idx for n host records (kmer_index.hpp:85-90); idx_out[i] = ~0 if the key falls through all levels */
 int  sb200_mphf_lookup(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *records, uint64_t n, uint64_t *idx_out);
+/* KMerIndex::seq_idx(const Seq &) for ONE key, evaluated on the HOST (the bit-vectors + rank samples are copied out once): for the
+ * reference's per-key consumers after the path (link records, edge index); thread-safe; *idx_out = ~0 if the key falls through */
+int  sb200_mphf_seq_idx(const sb200_mphf *m, const uint64_t *record, uint64_t *idx_out);
 /* KMerIndex::serialize bytes (kmer_index.hpp:99-105); out == NULL: size query */
 int  sb200_mphf_serialize(const sb200_mphf *m, uint8_t *out, uint64_t *size);
 void sb200_mphf_free(sb200_mphf *m);
@@ -237,6 +240,21 @@ int  sb200_construct(sb200_ctx *ctx, const uint64_t *words, const uint64_t *word
                      uint64_t n_reads, const sb200_construct_params *params, sb200_graph **out);
 int  sb200_graph_get(const sb200_graph *g, sb200_graph_view *view);
 void sb200_graph_free(sb200_graph *g);
+
+/* ---- several GPUs behind ONE host thread: what SURVEY.md 8(b) writes as sb200_create(n_gpus, device_ids).  The library drives one
+ *      rank per entry of device_ids from its own host threads (NCCL between distinct devices; a device id that repeats gives virtual
+ *      ranks with the local communicator, for one-GPU boxes), splits the host reads by index, runs sb200_construct_sharded on every rank
+ *      and returns ONE graph in the layout of sb200_construct: the shards concatenated in rank order = the single-GPU result (every GPU
+ *      copies its shard of the k-mer tables home over its own PCIe link; masks, index and unitigs come from rank 0).  The graph is
+ *      released with sb200_graph_free before sb200_multi_destroy. ---------------------------------------------------------------------- */
+typedef struct sb200_multi sb200_multi;
+int  sb200_multi_create(int n_gpus, const int *device_ids, sb200_multi **out);
+void sb200_multi_destroy(sb200_multi *m);
+const char *sb200_multi_last_error(const sb200_multi *m);     /* m may be NULL: error of the last failed sb200_multi_create         */
+int  sb200_multi_size(const sb200_multi *m);
+sb200_ctx *sb200_multi_context(sb200_multi *m, int rank);     /* borrowed: e.g. sb200_mphf_lookup on rank 0 for the link records      */
+int  sb200_multi_construct(sb200_multi *m, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                           const sb200_construct_params *params, sb200_graph **out);
 
 #ifdef __cplusplus
 }

@@ -245,8 +245,38 @@ public:
     uint64_t kmer_instances() const { return sb200_kmers_instances(h_.get()); }
     // records of bucket i = the contents of the reference's kmers<i> file (bucket_begin(i) .. bucket_end(i))
     std::vector<uint64_t> bucket(size_t i) const { return download(starts_[i], bucket_size(i)); }
-    // merge() + final_kmers(): all buckets concatenated
+    // bucket_begin(i) / bucket_end(i): input iterators over the records of kmers<i>, each yielding (const uint64_t *, bytes) like
+    // KMerDiskStorage::kmer_iterator (kmer_index_builder.hpp:57-92); the bucket is downloaded once and shared by the iterator copies
+    typedef std::pair<const uint64_t *, size_t> KMerRawData;
+    class kmer_iterator {
+    public:
+        typedef std::input_iterator_tag iterator_category;
+        typedef KMerRawData value_type;
+        typedef ptrdiff_t difference_type;
+        typedef const KMerRawData *pointer;
+        typedef KMerRawData reference;
+        kmer_iterator() {}
+        kmer_iterator(std::shared_ptr<std::vector<uint64_t>> data, unsigned words) : data_(std::move(data)), words_(words) {}
+        KMerRawData operator*() const { return KMerRawData(data_->data() + pos_ * words_, (size_t) words_ * 8); }
+        kmer_iterator &operator++() { ++pos_; return *this; }
+        void operator+=(size_t n) { pos_ += n; }
+        bool operator==(const kmer_iterator &o) const { return at_end() == o.at_end() && (at_end() || (data_ == o.data_ && pos_ == o.pos_)); }
+        bool operator!=(const kmer_iterator &o) const { return !(*this == o); }
+    private:
+        bool at_end() const { return !data_ || pos_ * words_ >= data_->size(); }
+        std::shared_ptr<std::vector<uint64_t>> data_;
+        unsigned words_ = 1;
+        size_t pos_ = 0;
+    };
+    kmer_iterator bucket_begin(size_t i) const { return kmer_iterator(std::make_shared<std::vector<uint64_t>>(bucket(i)), kmer_words()); }
+    kmer_iterator bucket_end(size_t) const { return kmer_iterator(); }
+    // merge() + final_kmers(): all buckets concatenated.  The reference merges the bucket FILES into <work_dir>/final_kmers and hands
+    // the path around (kmer_index_builder.hpp:168-181); here the buckets already are one device array: merge() only records that the
+    // caller asked for it, final_kmers(path) writes the file where a consumer wants one.
+    void merge() { merged_ = true; }
+    bool merged() const { return merged_; }
     std::vector<uint64_t> final_kmers() const { return download(0, total_kmers()); }
+    std::string final_kmers(const std::string &path) const { write_final_kmers(path); return path; }
     // multiplicities in file order (empty for derived sets): what CoverageHashMapBuilder::FillCoverageFromStream counts
     std::vector<uint32_t> counts() const {
         std::vector<uint32_t> c(total_kmers());
@@ -270,6 +300,7 @@ private:
     const Context *ctx_ = nullptr;
     std::shared_ptr<sb200_kmers> h_;
     std::vector<uint64_t> starts_;
+    bool merged_ = false;
 };
 
 // ---- splitters: on the GPU a splitter is only the description of what to count (the records never hit a disk) ---------
@@ -340,6 +371,12 @@ public:
         std::vector<uint64_t> idx(records.size() / words);
         if (!idx.empty()) ctx_->check(sb200_mphf_lookup(ctx_->get(), h_.get(), records.data(), idx.size(), idx.data()));
         return idx;
+    }
+    // seq_idx(const Seq &): one key from host code (kmer_index.hpp:85-90); the lookup runs on the host over a copy of the bit-vectors
+    size_t seq_idx(const Sequence &kmer) const {
+        uint64_t idx = 0;
+        ctx_->check(sb200_mphf_seq_idx(h_.get(), kmer.data(), &idx));
+        return (size_t) idx;
     }
     void serialize(std::ostream &os) const {
         uint64_t n = 0;

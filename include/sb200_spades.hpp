@@ -15,6 +15,10 @@
 //                                           (k+1)-mer storage like the reference.  The reference's UnbranchingPathExtractor,
 //                                           EarlyTipClipperProcessor, FastGraphFromSequencesConstructor and GFAWriter then run on it
 //                                           as they are (oracle/ref_dropin.cpp does exactly that and compares with the GPU's unitigs).
+//   sb200_spades::PackedReads::FromGraphEdges + GpuKMerCounter(..., canonical_only, add_rc = false)
+//                                           the counter behind the EDGE INDEX (assembly_graph/index/edge_index_builders.hpp:20-150:
+//                                           DeBruijnGraphKMerSplitter / DeBruijnEdgeKMerSplitter feed every edge of the graph — conjugates
+//                                           are edges of their own — through FillBufferFromSequence with the index's KmerFilter): SURVEY 8(f)4.
 //   sb200_spades::GpuUnbranchingPaths       std::vector<Sequence> of UnbranchingPathExtractor::ExtractUnbranchingPathsAndLoops
 //                                           (assembly_graph/construction/debruijn_graph_constructor.hpp:377-384) from the GPU.
 // Streams: pass the FORWARD streams (single_binary_readers_for_libs(..., followed_by_rc = false, ...)); the RC stream the reference
@@ -79,6 +83,19 @@ struct PackedReads {
         for (size_t i = 0; i < n; ++i) words[base + i / 32] |= (uint64_t) (unsigned char) s[i] << (2 * (i % 32));
         word_off.push_back(words.size());
         len.push_back((uint32_t) n);
+    }
+    // every edge of a graph in iteration order (conjugate edges included, as DeBruijnGraphKMerSplitter::Split walks them)
+    template<class Graph>
+    static PackedReads FromGraphEdges(const Graph &g) {
+        PackedReads p;
+        for (auto it = g.ConstEdgeBegin(); !it.IsEnd(); ++it) p.push_back(g.EdgeNucls(*it));
+        return p;
+    }
+    template<class Graph, class Edges>
+    static PackedReads FromEdges(const Graph &g, const Edges &edges) {   // DeBruijnEdgeKMerSplitter: an explicit edge list
+        PackedReads p;
+        for (auto e : edges) p.push_back(g.EdgeNucls(e));
+        return p;
     }
     template<class Streams>
     static PackedReads FromStreams(Streams &streams) {

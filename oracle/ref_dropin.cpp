@@ -11,6 +11,8 @@
 //      (sequence by sequence, order included)
 //   D  the REFERENCE's FastGraphFromSequencesConstructor + gfa::GFAWriter over the GPU-filled index and the GPU's unitigs writes
 //      the same GFA lines as over the reference's own
+//   E  the edge-index counter: KMerDiskCounter over the reference's DeBruijnGraphKMerSplitter on the condensed graph, with
+//      the keep-all and the keep-minimal filter, against the GPU counter fed with the same edges: bucket files byte for byte
 // Exit code 0 iff everything matches; one "name OK|FAIL" line per check on stdout.
 #include "utils/extension_index/kmer_extension_index_builder.hpp"
 #include "assembly_graph/construction/debruijn_graph_constructor.hpp"
@@ -20,6 +22,7 @@
 #include "io/reads/longest_valid_wrapper.hpp"
 #include "assembly_graph/core/graph.hpp"
 #include "io/graph/gfa_writer.hpp"
+#include "assembly_graph/index/edge_index_builders.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
 
@@ -199,6 +202,33 @@ int main(int argc, char **argv) {
 
     // ---- D: graph + GFA --------------------------------------------------------------------------------------------------------------------
     report("D_gfa_from_gpu_index_and_unitigs", gfa_lines(k, ext_gpu, gpu_seqs) == gfa_lines(k, ext_ref, ref_seqs));
+
+    // ---- E: the edge index's counter ------------------------------------------------------------------------------------------------------
+    {
+        debruijn_graph::DeBruijnGraph g(k);
+        debruijn_graph::FastGraphFromSequencesConstructor<debruijn_graph::DeBruijnGraph>(k, ext_ref).ConstructGraph(g, ref_seqs);
+        sb200_spades::PackedReads edges = sb200_spades::PackedReads::FromGraphEdges(g);
+        {
+            using EdgeSplitter = debruijn_graph::DeBruijnGraphKMerSplitter<debruijn_graph::DeBruijnGraph, utils::StoringTypeFilter<utils::SimpleStoring>>;
+            kmers::KMerDiskCounter<RtSeq> ref_counter(workdir, EdgeSplitter(workdir, k + 1, g));
+            auto ref_storage = ref_counter.Count(B, T);
+            sb200_spades::GpuKMerCounter gpu_counter(workdir, ctx, k + 1, edges, /*canonical_only=*/false, /*add_rc=*/false);
+            auto gpu_storage = gpu_counter.Count(B, T);
+            bool ok = ref_storage.total_kmers() == gpu_storage.total_kmers();
+            for (size_t b = 0; ok && b < ref_storage.num_buckets(); ++b) ok = bucket_bytes(ref_storage, b) == bucket_bytes(gpu_storage, b);
+            report("E_edge_index_counter_all_kmers", ok, std::to_string(gpu_storage.total_kmers()) + " (k+1)-mers of " + std::to_string(edges.len.size()) + " edges");
+        }
+        {
+            using EdgeSplitter = debruijn_graph::DeBruijnGraphKMerSplitter<debruijn_graph::DeBruijnGraph, utils::StoringTypeFilter<utils::InvertableStoring>>;
+            kmers::KMerDiskCounter<RtSeq> ref_counter(workdir, EdgeSplitter(workdir, k + 1, g));
+            auto ref_storage = ref_counter.Count(B, T);
+            sb200_spades::GpuKMerCounter gpu_counter(workdir, ctx, k + 1, edges, /*canonical_only=*/true, /*add_rc=*/false);
+            auto gpu_storage = gpu_counter.Count(B, T);
+            bool ok = ref_storage.total_kmers() == gpu_storage.total_kmers();
+            for (size_t b = 0; ok && b < ref_storage.num_buckets(); ++b) ok = bucket_bytes(ref_storage, b) == bucket_bytes(gpu_storage, b);
+            report("E_edge_index_counter_minimal_kmers", ok, std::to_string(gpu_storage.total_kmers()) + " (k+1)-mers");
+        }
+    }
 
     std::cout << (failures ? "DROPIN FAIL" : "DROPIN OK") << std::endl;
     return failures ? 1 : 0;

@@ -15,6 +15,7 @@ sb200_kmers *derive_kmers(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
 void mphf_lookup_device(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *recs_dev, uint64_t n, uint64_t *out_dev);
 uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out);
+uint64_t mphf_seq_idx_host(sb200_mphf *m, const uint64_t *rec);
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf);
 uint64_t tipclip(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, sb200_ext *ext, uint64_t bound);
 sb200_unitigs *extract_unitigs(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const sb200_ext *ext, int with_loops);
@@ -281,6 +282,9 @@ int sb200_mphf_lookup(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *recor
         CUDA_CHECK(cudaMemcpyAsync(idx_out, idx.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     });
+}
+int sb200_mphf_seq_idx(const sb200_mphf *m, const uint64_t *record, uint64_t *idx_out) {
+    return guarded(m->ctx, [&] { *idx_out = sb200::mphf_seq_idx_host(const_cast<sb200_mphf *>(m), record); });
 }
 int sb200_mphf_serialize(const sb200_mphf *m, uint8_t *out, uint64_t *size) {
     return guarded(m->ctx, [&] { *size = sb200::mphf_serialize(m, out); });

@@ -54,6 +54,9 @@ struct sb200_mphf {
     // no hashing, no level probing (ext.cu index_from_place_kernel).
     DevBuf<uint32_t> place, pc_scan;
     uint64_t final_level_keys = 0;
+    // host copy of bits / ranks for single-key lookups from host code (sb200_mphf_seq_idx), made on first use
+    std::vector<uint64_t> bits_host, ranks_host;
+    bool host_copy = false;
 };
 
 struct sb200_ext {   // DeBruijnExtensionIndex payload: masks in MPHF-index order (+ successor links for the walks)

@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kmer_ops.cuh"
 #include "kmer_set.cuh"
@@ -332,6 +334,55 @@ void mphf_lookup_device(sb200_ctx *ctx, const sb200_mphf *m, const uint64_t *rec
         case 2: LAUNCH(ctx, mphf_lookup_kernel<2>, g, 256, 0, d, recs_dev, n, out_dev); break;
         case 3: LAUNCH(ctx, mphf_lookup_kernel<3>, g, 256, 0, d, recs_dev, n, out_dev); break;
         default: LAUNCH(ctx, mphf_lookup_kernel<4>, g, 256, 0, d, recs_dev, n, out_dev); break;
+    }
+}
+
+// KMerIndex::seq_idx(const Seq &) for ONE key from host code (kmer_index.hpp:85-90, boomphf::mphf::lookup BooPHF.h:465-487, bitVector::rank
+// :303-314): the consumers of the index after the path (link records, edge index, read mapping) look keys up one at a time from CPU
+// threads.  The 5.8 bits per key of bit-vectors + rank samples are copied to the host once; the lookup itself is the reference's
+// arithmetic (same XXH3 specialisations as the kernels, kmer_ops.cuh compiled for the host).  Thread-safe after the first call.
+template<int W>
+static uint64_t mphf_lookup_host(const sb200_mphf *m, const uint64_t *rec) {
+    const uint32_t b = kmer_bucket<W>(rec, m->num_buckets);
+    uint64_t s0, s1;
+    xxh3_128<W>(rec, s0, s1);
+    for (int l = 0; l < MPHF_LEVELS - 1; ++l) {
+        const size_t t = (size_t) b * MPHF_LEVELS + l;
+        const uint64_t h = (l == 0) ? s0 : (l == 1) ? s1 : xs_next(s0, s1);
+        const uint64_t d = m->domain_host[t];
+        if (d == 0) return ~0ULL;
+        const uint64_t pos = mulhi64(h, d);
+        const uint64_t *bv = m->bits_host.data() + m->word_off_host[t];
+        const uint64_t word = bv[pos >> 6];
+        if ((word >> (pos & 63)) & 1ULL) {
+            uint64_t r = m->ranks_host[m->rank_off_host[t] + (pos >> 9)];
+            for (uint64_t w = (pos >> 9) << 3; w < (pos >> 6); ++w) r += (uint64_t) __builtin_popcountll(bv[w]);
+            r += (uint64_t) __builtin_popcountll(word & ((1ULL << (pos & 63)) - 1ULL));
+            return m->segment_starts_host[b] + r;
+        }
+    }
+    return ~0ULL;
+}
+
+uint64_t mphf_seq_idx_host(sb200_mphf *m, const uint64_t *rec) {
+    if (!m->host_copy) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!m->host_copy) {
+            sb200_ctx *ctx = m->ctx;
+            CUDA_CHECK(cudaSetDevice(ctx->device));
+            m->bits_host.resize(m->total_words + 1);
+            m->ranks_host.resize(m->total_ranks + 1);
+            CUDA_CHECK(cudaMemcpy(m->bits_host.data(), m->bits.p, m->total_words * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(m->ranks_host.data(), m->ranks.p, m->total_ranks * 8, cudaMemcpyDeviceToHost));
+            m->host_copy = true;
+        }
+    }
+    switch (m->words) {
+        case 1: return mphf_lookup_host<1>(m, rec);
+        case 2: return mphf_lookup_host<2>(m, rec);
+        case 3: return mphf_lookup_host<3>(m, rec);
+        default: return mphf_lookup_host<4>(m, rec);
     }
 }
 

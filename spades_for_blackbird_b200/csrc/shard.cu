@@ -21,7 +21,9 @@
 // Host code is C++ (NCCL C API behind comm.cuh); Python only launches ranks and hands the NCCL id around.
 #include <string.h>
 
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "../../include/sb200.h"
@@ -299,6 +301,197 @@ void shift_word_offsets(sb200_ctx *ctx, uint64_t *word_off, const uint64_t *ooff
 
 }  // namespace sb200
 
+// ---- one host process, several GPUs: sb200_multi --------------------------------------------------------------------------------------
+// SURVEY.md 8(b) sketches the boundary as sb200_create(n_gpus, device_ids): the caller of the reference's interfaces is ONE host thread
+// (pipeline/stage.cpp:143-204), so the multi-GPU form of sb200_construct takes host reads, splits them by index over its GPUs, drives one
+// rank per GPU from its own host threads (NCCL between distinct devices, the local communicator when a device id repeats — virtual
+// ranks, for one-GPU boxes) and hands back ONE graph in the layout of the single-GPU call: the shards concatenated in rank order.
+namespace sb200 {
+struct MultiBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, waiting = 0;
+    uint64_t gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const uint64_t g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return; }
+        cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+}  // namespace sb200
+
+struct sb200_multi {
+    int n = 0;
+    std::vector<int> devices;
+    std::vector<sb200_ctx *> ctx;
+    std::vector<sb200_comm *> comm;
+    std::string last_error;
+    ~sb200_multi() {
+        for (auto c : comm) delete c;
+        for (auto c : ctx) if (c) sb200_destroy(c);
+    }
+};
+
+namespace sb200 {
+
+static void multi_create(sb200_multi *mg) {
+    const int G = mg->n;
+    bool repeats = false;
+    for (int a = 0; a < G; ++a)
+        for (int b = a + 1; b < G; ++b) repeats = repeats || mg->devices[a] == mg->devices[b];
+    mg->ctx.assign((size_t) G, nullptr);
+    mg->comm.assign((size_t) G, nullptr);
+    for (int r = 0; r < G; ++r)
+        if (sb200_create(mg->devices[r], &mg->ctx[r]) != 0) throw sb200_error(4, sb200_last_error(nullptr));
+    if (repeats || G == 1) {
+        comm_create_local(G, mg->comm.data());
+        return;
+    }
+    uint8_t id[128];
+    nccl_unique_id(id);
+    std::vector<std::thread> th;
+    std::vector<std::string> err((size_t) G);
+    for (int r = 0; r < G; ++r)
+        th.emplace_back([&, r] {
+            try {
+                mg->comm[r] = comm_create_nccl(mg->ctx[r], r, G, id);
+            } catch (const std::exception &e) {
+                err[r] = e.what();
+            }
+        });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < G; ++r)
+        if (!err[r].empty()) throw sb200_error(5, err[r]);
+}
+
+static sb200_graph *multi_construct(sb200_multi *mg, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                                    const sb200_construct_params *p) {
+    const int G = mg->n;
+    std::vector<sb200_shard *> shard((size_t) G, nullptr);
+    std::vector<std::string> err((size_t) G);
+    MultiBarrier bar;
+    bar.n = G;
+    sb200_graph *g = nullptr;
+    std::vector<uint64_t> kp_off((size_t) G + 1, 0), km_off((size_t) G + 1, 0);
+    bool failed = false;
+    auto rank_main = [&](int r) {
+        sb200_ctx *ctx = mg->ctx[r];
+        sb200_reads *rd = nullptr;
+        bool ok = true;
+        try {
+            CUDA_CHECK(cudaSetDevice(ctx->device));
+            const uint64_t lo = n_reads * (uint64_t) r / G, hi = n_reads * (uint64_t) (r + 1) / G;
+            std::vector<uint64_t> off(hi - lo + 1);
+            for (uint64_t i = lo; i <= hi; ++i) off[i - lo] = word_off[i] - word_off[lo];
+            static const uint32_t zero32 = 0;
+            if (sb200_reads_upload(ctx, words + word_off[lo], off.data(), hi > lo ? len + lo : &zero32, hi - lo, &rd) != 0) throw sb200_error(2, ctx->last_error);
+            shard[r] = construct_sharded(ctx, mg->comm[r], rd, p, 0);
+        } catch (const std::exception &e) {
+            err[r] = e.what();
+            mg->comm[r]->fail();
+            ok = false;
+        }
+        if (rd) sb200_reads_free(rd);
+        {
+            std::lock_guard<std::mutex> lk(bar.m);
+            failed = failed || !ok;
+        }
+        bar.wait();   // every rank has its shard (or has failed)
+        if (failed) return;
+        if (r == 0) {   // sizes -> offsets, host buffers from rank 0's pinned pool
+            try {
+                for (int q = 0; q < G; ++q) {
+                    kp_off[(size_t) q + 1] = kp_off[(size_t) q] + shard[q]->kpomers->size;
+                    km_off[(size_t) q + 1] = km_off[(size_t) q] + shard[q]->kmers->size;
+                }
+                g = new sb200_graph();
+                g->ctx = ctx;
+                memset(&g->view, 0, sizeof g->view);
+                sb200_graph_view &v = g->view;
+                const sb200_shard *s0 = shard[0];
+                const unsigned W1 = s0->kpomers->words, W0 = s0->kmers->words, B = p->num_buckets;
+                v.n_kpomers = kp_off[(size_t) G]; v.n_kmers = km_off[(size_t) G]; v.kpomer_instances = s0->total_instances; v.clipped = s0->clipped;
+                if (p->fetch_kmers) {
+                    v.kpomers = g->pin<uint64_t>(v.n_kpomers * W1 + 1);
+                    v.kpomer_counts = g->pin<uint32_t>(v.n_kpomers + 1);
+                    v.kmers = g->pin<uint64_t>(v.n_kmers * W0 + 1);
+                    g->kp_starts.assign((size_t) B + 1, 0);
+                    g->km_starts.assign((size_t) B + 1, 0);
+                    const unsigned n_owned = B / (unsigned) G;
+                    for (int q = 0; q < G; ++q)
+                        for (unsigned b = 0; b < n_owned; ++b) {
+                            const size_t gb = (size_t) q * n_owned + b;
+                            g->kp_starts[gb] = kp_off[(size_t) q] + shard[q]->kpomers->bucket_starts_host[gb];
+                            g->km_starts[gb] = km_off[(size_t) q] + shard[q]->kmers->bucket_starts_host[gb];
+                        }
+                    g->kp_starts[B] = v.n_kpomers; g->km_starts[B] = v.n_kmers;
+                    v.kpomer_bucket_starts = g->kp_starts.data(); v.kmer_bucket_starts = g->km_starts.data();
+                    v.d2h_bytes += v.n_kpomers * (W1 * 8 + 4) + v.n_kmers * W0 * 8;
+                }
+            } catch (const std::exception &e) {
+                err[0] = e.what();
+                std::lock_guard<std::mutex> lk(bar.m);
+                failed = true;
+            }
+        }
+        bar.wait();   // the host buffers exist
+        if (failed) return;
+        try {
+            sb200_graph_view &v = g->view;
+            const sb200_shard *s = shard[r];
+            cudaStream_t st = ctx->stream;
+            if (p->fetch_kmers) {   // every GPU brings its shard home over its own PCIe link
+                const unsigned W1 = s->kpomers->words, W0 = s->kmers->words;
+                CUDA_CHECK(cudaMemcpyAsync(const_cast<uint64_t *>(v.kpomers) + kp_off[r] * W1, s->kpomers->data.p, s->kpomers->size * W1 * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(const_cast<uint32_t *>(v.kpomer_counts) + kp_off[r], s->kpomers->counts.p, s->kpomers->size * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(const_cast<uint64_t *>(v.kmers) + km_off[r] * W0, s->kmers->data.p, s->kmers->size * W0 * 8, cudaMemcpyDeviceToHost, st));
+            }
+            if (r == 0) {   // masks, index bytes and the gathered unitigs live on rank 0
+                uint8_t *masks = g->pin<uint8_t>(v.n_kmers + 1);
+                CUDA_CHECK(cudaMemcpyAsync(masks, s->ext->masks.p, v.n_kmers, cudaMemcpyDeviceToHost, st));
+                v.masks = masks;
+                uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out);
+                const uint64_t isz = mphf_serialize(s->mphf, nullptr);
+                uint8_t *ib = g->pin<uint8_t>(isz + 8);
+                mphf_serialize(s->mphf, ib);
+                v.index_bytes = ib; v.index_size = isz;
+                const sb200_unitigs *u = s->unitigs;
+                v.n_unitigs = u->count; v.n_loops = u->n_loops; v.unitig_bases = u->total_bases; v.n_unitig_words = u->total_words;
+                uint64_t *uw = g->pin<uint64_t>(u->total_words + 1), *uo = g->pin<uint64_t>(u->count + 1);
+                uint32_t *ul = g->pin<uint32_t>(u->count + 1);
+                CUDA_CHECK(cudaMemcpyAsync(uw, u->words.p, u->total_words * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(uo, u->word_off.p, (u->count + 1) * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(ul, u->len.p, u->count * 4, cudaMemcpyDeviceToHost, st));
+                v.unitig_words = uw; v.unitig_word_off = uo; v.unitig_len = ul;
+                v.d2h_bytes += v.n_kmers + isz + u->total_words * 8 + (u->count + 1) * 8 + u->count * 4;
+            }
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        } catch (const std::exception &e) {
+            err[r] = e.what();
+            std::lock_guard<std::mutex> lk(bar.m);
+            failed = true;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; ++r) th.emplace_back(rank_main, r);
+    for (auto &t : th) t.join();
+    for (auto s : shard) if (s) { cudaSetDevice(s->ctx->device); delete s; }
+    if (failed) {
+        if (g) { cudaSetDevice(g->ctx->device); delete g; }
+        std::string msg;
+        for (int r = 0; r < G; ++r)
+            if (!err[r].empty() && err[r].find("another rank of the local communicator failed") == std::string::npos) { msg = err[r]; break; }
+        if (msg.empty())
+            for (int r = 0; r < G; ++r) if (!err[r].empty()) { msg = err[r]; break; }
+        throw sb200_error(1, msg.empty() ? std::string("sb200: multi-GPU construction failed") : msg);
+    }
+    return g;
+}
+
+}  // namespace sb200
+
 template<class F>
 static int guarded(sb200_ctx *ctx, sb200_comm *cm, F &&f) {
     try {
@@ -380,6 +573,47 @@ void sb200_shard_free(sb200_shard *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     delete s;
+}
+
+static std::string g_multi_error;
+int sb200_multi_create(int n_gpus, const int *device_ids, sb200_multi **out) {
+    *out = nullptr;
+    sb200_multi *mg = new sb200_multi();
+    try {
+        SB200_REQUIRE(n_gpus >= 1 && n_gpus <= 64 && device_ids, "number of GPUs out of range [1,64]");
+        mg->n = n_gpus;
+        mg->devices.assign(device_ids, device_ids + n_gpus);
+        sb200::multi_create(mg);
+        *out = mg;
+        return 0;
+    } catch (const sb200_error &e) {
+        g_multi_error = e.what();
+        delete mg;
+        return e.code;
+    } catch (const std::exception &e) {
+        g_multi_error = e.what();
+        delete mg;
+        return 3;
+    }
+}
+void sb200_multi_destroy(sb200_multi *mg) { delete mg; }
+const char *sb200_multi_last_error(const sb200_multi *mg) { return mg ? mg->last_error.c_str() : g_multi_error.c_str(); }
+int sb200_multi_size(const sb200_multi *mg) { return mg->n; }
+sb200_ctx *sb200_multi_context(sb200_multi *mg, int rank) { return (rank >= 0 && rank < mg->n) ? mg->ctx[(size_t) rank] : nullptr; }
+int sb200_multi_construct(sb200_multi *mg, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                          const sb200_construct_params *params, sb200_graph **out) {
+    *out = nullptr;
+    try {
+        SB200_REQUIRE(params && word_off && len && (words || n_reads == 0), "null read buffers / parameters");
+        *out = sb200::multi_construct(mg, words, word_off, len, n_reads, params);
+        return 0;
+    } catch (const sb200_error &e) {
+        mg->last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        mg->last_error = e.what();
+        return 3;
+    }
 }
 
 }  // extern "C"

@@ -86,6 +86,7 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_mphf_size": (C.c_uint64, [vp]),
     "sb200_mphf_mem_size": (C.c_uint64, [vp]),
     "sb200_mphf_lookup": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p]),
+    "sb200_mphf_seq_idx": (C.c_int, [vp, u64p, u64p]),
     "sb200_mphf_serialize": (C.c_int, [vp, u8p, u64p]),
     "sb200_mphf_free": (None, [vp]),
     "sb200_ext_build": (C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
@@ -141,6 +142,12 @@ EXPORTS = {   # symbol -> (restype, argtypes); tests check that the library expo
     "sb200_shard_info": (C.c_int, [vp, C.POINTER(ShardInfo)]),
     "sb200_shard_walk_stats": (C.c_int, [vp, u64p]),
     "sb200_shard_free": (None, [vp]),
+    "sb200_multi_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
+    "sb200_multi_destroy": (None, [vp]),
+    "sb200_multi_last_error": (C.c_char_p, [vp]),
+    "sb200_multi_size": (C.c_int, [vp]),
+    "sb200_multi_context": (vp, [vp, C.c_int]),
+    "sb200_multi_construct": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, C.POINTER(ConstructParams), C.POINTER(vp)]),
     "sb200_construct": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, C.POINTER(ConstructParams), C.POINTER(vp)]),
     "sb200_graph_get": (C.c_int, [vp, C.POINTER(GraphView)]),
     "sb200_graph_free": (None, [vp]),
@@ -358,6 +365,13 @@ class KMerIndex:
         out = np.zeros(max(len(records), 1), dtype=np.uint64)
         self.ctx.check(self.ctx.lib.sb200_mphf_lookup(self.ctx.h, self.h, _p(records, u64p), len(records), _p(out, u64p)))
         return out[:len(records)]
+
+    def seq_idx_one(self, record):
+        """KMerIndex::seq_idx(const Seq &): one key, looked up on the host"""
+        rec = np.ascontiguousarray(record, dtype=np.uint64)
+        out = C.c_uint64()
+        self.ctx.check(self.ctx.lib.sb200_mphf_seq_idx(self.h, _p(rec, u64p), C.byref(out)))
+        return out.value
 
     def serialize(self):
         n = C.c_uint64()
@@ -697,3 +711,40 @@ def construct_sharded(ctx, comm, reads, k, num_buckets, tip_clip=False, tip_leng
     h = vp()
     ctx.check(ctx.lib.sb200_construct_sharded(ctx.h, comm.h, reads.h, C.byref(p), int(gather_to), C.byref(h)))
     return Shard(ctx, h)
+
+
+class MultiContext:
+    """sb200_multi: several GPUs (or virtual ranks on one GPU when a device id repeats) driven by the library from ONE host thread —
+    SURVEY.md 8(b)'s sb200_create(n_gpus, device_ids)."""
+
+    def __init__(self, device_ids):
+        self.lib = load_library()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = vp()
+        if self.lib.sb200_multi_create(len(device_ids), ids, C.byref(h)) != 0:
+            raise Sb200Error(self.lib.sb200_multi_last_error(None).decode())
+        self.h = h
+
+    def construct(self, words, word_off, lens, k, num_buckets, tip_clip=False, tip_length_bound=0, with_loops=True, fetch_kmers=True):
+        p = ConstructParams(k, num_buckets, int(tip_clip), tip_length_bound, int(with_loops), int(fetch_kmers))
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        word_off = np.ascontiguousarray(word_off, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        g = vp()
+        if self.lib.sb200_multi_construct(self.h, _p(words, u64p), _p(word_off, u64p), _p(lens, u32p), len(word_off) - 1, C.byref(p), C.byref(g)) != 0:
+            raise Sb200Error(self.lib.sb200_multi_last_error(self.h).decode())
+
+        class _Ctx:   # what Graph needs from a context
+            lib = self.lib
+        return Graph(_Ctx, g)
+
+    def close(self):
+        if self.h:
+            self.lib.sb200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

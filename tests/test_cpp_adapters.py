@@ -70,10 +70,12 @@ def test_gbuilder_files_equal_reference(tool, tmp_path, golden):
         pytest.skip("bucket count is not 10 x threads")
     write_reads(tmp_path / "r.txt", g["reads"])
     args = [tool, "--reads", str(tmp_path / "r.txt"), "--write-binary", str(tmp_path / "lib"), "--out", str(tmp_path), "-k", str(g["k"]),
-            "-t", str(g["buckets"] // 10), "--coverage"]
+            "-t", str(g["buckets"] // 10), "--coverage", "--self-check"]
     if g["tip_bound"] >= 0:
         args += ["--tip-clip", str(g["tip_bound"])]
-    subprocess.check_call(args)
+    out = subprocess.run(args, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "self-check OK" in out.stdout          # KMerDiskStorage bucket iterators + KMerIndex::seq_idx(const Seq &) on the host
     assert np.array_equal(np.fromfile(tmp_path / "kpomers", dtype=np.uint64), g["kpomers"])
     assert np.array_equal(np.fromfile(tmp_path / "final_kmers", dtype=np.uint64), g["kmers"])
     assert np.array_equal(np.fromfile(tmp_path / "coverage.u32", dtype=np.uint32), g["coverage"])

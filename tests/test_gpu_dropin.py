@@ -2,7 +2,8 @@
 container against the unmodified SPAdes headers + libspades_b200.so (oracle/Makefile `make dropin`).  It runs the reference's CPU
 path and the GPU path side by side and lets the REFERENCE's own code consume the GPU's results: KMerCounter::Count bucket files,
 ConstructKWH(kmer).idx() on the GPU-built KMerIndex, UnbranchingPathExtractor and FastGraphFromSequencesConstructor + GFAWriter on
-the GPU-filled DeBruijnExtensionIndex (see the header of oracle/ref_dropin.cpp for checks A-D)."""
+the GPU-filled DeBruijnExtensionIndex, and the edge index's KMerDiskCounter over DeBruijnGraphKMerSplitter against the GPU counter on the
+same edges (see the header of oracle/ref_dropin.cpp for checks A-E)."""
 import os
 import subprocess
 
@@ -26,5 +27,6 @@ def test_reference_types_filled_from_the_gpu(tmp_path, name, threads):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "DROPIN OK" in r.stdout
     for check in ("A_counter_bucket_files", "A_counter_final_kmers_after_merge", "B_kpomer_storage", "B_reference_lookup_on_gpu_index", "B_masks",
-                  "B_kmer_index_serialize", "C_reference_extractor_on_gpu_index", "C_gpu_unitigs", "D_gfa_from_gpu_index_and_unitigs"):
+                  "B_kmer_index_serialize", "C_reference_extractor_on_gpu_index", "C_gpu_unitigs", "D_gfa_from_gpu_index_and_unitigs", "E_edge_index_counter_all_kmers",
+                  "E_edge_index_counter_minimal_kmers"):
         assert check + " OK" in r.stdout, r.stdout

@@ -40,6 +40,9 @@ def test_golden_whole_path(ctx, golden):
     assert np.array_equal(index.kmers.final_kmers().reshape(-1), g["kmers"])
     assert np.array_equal(index.index.seq_idx(index.kmers.final_kmers()), g["idx"])
     assert np.array_equal(index.idx(), g["idx"])
+    km_recs = index.kmers.final_kmers()
+    for i in range(0, len(km_recs), max(len(km_recs) // 50, 1)):            # KMerIndex::seq_idx(const Seq &): one key at a time, on the host
+        assert index.index.seq_idx_one(km_recs[i]) == int(g["idx"][i])
     if (np.diff(index.kmers.bucket_starts) > 0).all():
         assert np.array_equal(index.index.serialize(), g["index_bin"])    # KMerIndex::serialize, byte for byte
     if g["tip_bound"] >= 0:

@@ -139,3 +139,43 @@ def test_sharded_alternative_paths_agree(monkeypatch, env):
     monkeypatch.setenv(env, "1")
     res = run_sharded(G, reads, k, nb)
     check(res, want, G, nb)
+
+
+@pytest.mark.parametrize("ids", [[0, 0], [0, 0, 0, 0]])
+def test_multi_context_one_host_thread(ids):
+    """sb200_multi (SURVEY 8(b)'s sb200_create(n_gpus, device_ids)): the library splits host reads over its ranks, runs the sharded path
+    from its own threads and returns ONE graph in the single-GPU layout.  A repeated device id = virtual ranks on this GPU."""
+    from conftest import load_golden
+    for name in ("ecoli1k_k55", "loops_k21", "tipclip_k33"):
+        g = load_golden(name)
+        nb = g["buckets"] if g["buckets"] % len(ids) == 0 else g["buckets"] * len(ids)
+        tip = int(g["tip_bound"]) if g["tip_bound"] >= 0 else None
+        if nb == g["buckets"]:
+            want = dict(kpomers=g["kpomers"], coverage=g["coverage"], kmers=g["kmers"], masks_idx=g["masks_idx"], unitigs=g["unitigs"],
+                        clipped=int(g["clipped"]))
+        else:
+            w = O.gbuilder(g["reads"], g["k"], nb, tip_bound=tip)
+            want = dict(kpomers=w["kpomers"].data.reshape(-1), coverage=w["kpomers"].counts, kmers=w["kmers"].data.reshape(-1),
+                        masks_idx=w["masks_idx"], unitigs=w["unitigs"], clipped=w.get("clipped", 0))
+        words, word_off, lens = O.pack_reads(g["reads"])
+        mc = B.MultiContext(ids)
+        try:
+            gr = mc.construct(words, word_off, lens, g["k"], nb, tip_clip=tip is not None, tip_length_bound=tip or 0, fetch_kmers=True)
+            v = gr.view
+            assert np.array_equal(np.ctypeslib.as_array(v.kpomers, shape=(len(want["kpomers"]),)), want["kpomers"]), name
+            assert np.array_equal(np.ctypeslib.as_array(v.kpomer_counts, shape=(v.n_kpomers,)), want["coverage"]), name
+            assert np.array_equal(np.ctypeslib.as_array(v.kmers, shape=(len(want["kmers"]),)), want["kmers"]), name
+            assert np.array_equal(gr.masks(), want["masks_idx"]), name
+            assert gr.unitigs() == list(want["unitigs"]), name
+            assert v.clipped == want["clipped"]
+            ks = np.ctypeslib.as_array(v.kmer_bucket_starts, shape=(nb + 1,))
+            assert ks[0] == 0 and ks[-1] == v.n_kmers and (np.diff(ks.astype(np.int64)) >= 0).all()
+            gr.free()
+        finally:
+            mc.close()
+    with pytest.raises(B.Sb200Error, match="No kmers were extracted"):
+        mc = B.MultiContext([0, 0])
+        try:
+            mc.construct(*O.pack_reads(["ACGT", "GGCA"]), 21, 4)
+        finally:
+            mc.close()

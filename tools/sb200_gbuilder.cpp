@@ -8,6 +8,7 @@
 // own PREFIX.seq/.off files.  Not a product CLI — spades-gbuilder itself stays the front end.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <chrono>
 #include <fstream>
@@ -25,7 +26,7 @@ int main(int argc, char **argv) {
     std::string mode = "gbuilder", reads_path, binary_prefix, out, write_binary;
     unsigned k = 21, threads = 8;
     long tip_bound = -1;
-    bool coverage = false;
+    bool coverage = false, self_check = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -38,6 +39,7 @@ int main(int argc, char **argv) {
         else if (a == "-t") threads = (unsigned) atoi(next().c_str());
         else if (a == "--tip-clip") tip_bound = atol(next().c_str());
         else if (a == "--coverage") coverage = true;
+        else if (a == "--self-check") self_check = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (out.empty() || (reads_path.empty() && binary_prefix.empty())) {
@@ -92,6 +94,26 @@ int main(int argc, char **argv) {
             auto c = sb200::CoverageHashMapBuilder().FillCoverage(kpomers);
             std::ofstream os(out + "/coverage.u32", std::ios::binary);
             os.write((const char *) c.data(), (std::streamsize) (c.size() * 4));
+        }
+        if (self_check) {
+            // the per-key and per-bucket faces of the reference's interfaces: KMerDiskStorage::bucket_begin/end iterate the records of
+            // kmers<i> (kmer_index_builder.hpp:149-159), KMerIndex::seq_idx(const Seq &) looks one key up from host code (kmer_index.hpp:85-90)
+            const sb200::KMerDiskStorage &km = index.kmers();
+            const unsigned W = km.kmer_words();
+            std::vector<uint64_t> all = km.final_kmers();
+            std::vector<uint32_t> idx = index.idx();
+            size_t pos = 0, bad = 0;
+            for (size_t b = 0; b < km.num_buckets(); ++b) {
+                size_t in_bucket = 0;
+                for (auto it = km.bucket_begin(b); it != km.bucket_end(b); ++it, ++pos, ++in_bucket) {
+                    auto rec = *it;
+                    if (rec.second != W * 8 || memcmp(rec.first, &all[pos * W], W * 8) != 0) ++bad;
+                    if (pos % 7 == 0 && index.index().seq_idx(sb200::Sequence(rec.first, k)) != idx[pos]) ++bad;
+                }
+                if (in_bucket != km.bucket_size(b)) ++bad;
+            }
+            printf("self-check %s: %zu records through the bucket iterators, single-key seq_idx on every 7th\n", (bad == 0 && pos == km.total_kmers()) ? "OK" : "FAIL", pos);
+            if (bad || pos != km.total_kmers()) return 1;
         }
         std::ofstream us(out + "/unitigs.txt");
         for (const auto &e : edges) us << e.str() << "\n";
