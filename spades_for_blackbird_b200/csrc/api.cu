@@ -70,6 +70,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->no_place = getenv("SB200_NO_PLACE") != nullptr;
         ctx->no_fused_partition = getenv("SB200_NO_FUSED_PARTITION") != nullptr;
         ctx->atomic_partition = getenv("SB200_ATOMIC_PARTITION") != nullptr;
+        ctx->counting_passes = getenv("SB200_COUNTING_PASSES") != nullptr;
         ctx->group_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");
         ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -69,6 +69,7 @@ struct sb200_ctx {
     bool trace = false;
     double trace_t0 = 0;
     bool group_chunk = false;       // SB200_GROUP_KERNEL=chunk: the sorting group kernel (segsort.cuh) instead of the hashing one (grouphash.cuh)
+    bool counting_passes = false;      // SB200_COUNTING_PASSES=1: round-1 grouping (extract / derive, then two histogram + scatter passes) instead of the staged producer-fused partition (A/B, cross-check)
     bool atomic_partition = false;     // SB200_ATOMIC_PARTITION=1: one-pass partition through L2 atomics (partition.cuh) instead of extract / derive + counting passes (A/B, cross-check)
     bool no_fused_partition = false;   // SB200_NO_FUSED_PARTITION=1: sharded path extracts first and partitions afterwards (cross-check)
     bool no_place = false;          // SB200_NO_PLACE=1: k-mer indices by MPHF lookups even when the build recorded the placements (cross-check)

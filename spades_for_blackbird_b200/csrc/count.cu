@@ -16,6 +16,7 @@
 #include "segsort.cuh"
 #include "grouphash.cuh"
 #include "partition.cuh"
+#include "staged_partition.cuh"
 
 namespace sb200 {
 
@@ -373,16 +374,78 @@ static sb200_kmers *finish_grouped(sb200_ctx *ctx, DevBuf<uint64_t> &a, DevBuf<u
 
 // composite-key width: p value bits below the bucket so that a group is ~ Cfg::TARGET records
 template<int W>
-static int choose_prefix_bits(uint64_t n, uint32_t n_owned, int K) {
+static int choose_prefix_bits(uint64_t n, uint32_t n_owned, int K, int target = 0) {
     using Cfg = SegCfg<W>;
+    if (target == 0) target = Cfg::TARGET;
     const int top = (W == 1) ? 2 * K : 64;
     int bbits = 0;
     while ((1ull << bbits) < n_owned) ++bbits;
     const int pmax = std::min(24 - std::min(bbits, 24), top - 8);
     int p = 0;
-    while (p < pmax && (double) n / (double) ((uint64_t) n_owned << p) > (double) Cfg::TARGET) ++p;
+    while (p < pmax && (double) n / (double) ((uint64_t) n_owned << p) > (double) target) ++p;
     return p;
 }
+
+// ---- producer-fused grouping in two staged passes (staged_partition.cuh) -----------------------------------------------------------
+struct StagedPlan {
+    int p = 0, s = 0;
+    uint32_t n_groups = 0, n_coarse = 0;
+};
+
+// false: the staged partition does not apply (the fine-group histogram would not fit the shared memory of a count CTA)
+template<int W>
+static bool staged_plan(sb200_ctx *ctx, uint64_t n_est, uint32_t B, int K, StagedPlan &pl) {
+    if (B > SP_MAX_GROUPS) return false;
+    // the hashing group kernel does not stage the group, so 3- and 4-word records take the same group size as 1- and 2-word ones
+    pl.p = choose_prefix_bits<W>(n_est, B, K, ctx->group_chunk ? 0 : 7168);
+    while (pl.p > 0 && ((uint64_t) B << pl.p) > SP_MAX_GROUPS) --pl.p;   // larger groups: the group kernel takes them in rounds
+    pl.n_groups = (uint32_t) ((uint64_t) B << pl.p);
+    const uint32_t max_coarse = std::min<uint32_t>(SP_MAX_BINS, SpCfg<W>::CAP / 8);   // >= 8 records per run of a full tile
+    pl.s = 0;
+    while ((((pl.n_groups - 1) >> pl.s) + 1) > max_coarse) ++pl.s;
+    if ((1u << pl.s) > (uint32_t) SP_MAX_BINS) return false;
+    pl.n_coarse = ((pl.n_groups - 1) >> pl.s) + 1;
+    return true;
+}
+
+// After the count pass: group starts, cursors of both passes, tile table.  hist (n_groups + 1 counts) becomes the fine starts.
+struct StagedTables {
+    DevBuf<uint32_t> cur1, cur2, tile_start;
+    uint64_t n = 0;
+};
+
+__global__ void sp_coarse_cursors_kernel(const uint32_t *__restrict__ fine_start, int s, uint32_t n_coarse, uint32_t *__restrict__ cur1) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_coarse) cur1[c] = fine_start[(uint64_t) c << s];
+}
+
+template<int W>
+static void staged_tables(sb200_ctx *ctx, const StagedPlan &pl, DevBuf<uint32_t> &hist, StagedTables &t) {
+    DevBuf<uint32_t> total_dev(ctx, 1);
+    exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) pl.n_groups + 1, total_dev.p);   // hist[g] = first record of group g, hist[n_groups] = n
+    t.cur1.alloc(ctx, pl.n_coarse);
+    t.cur2.alloc(ctx, (uint64_t) pl.n_groups + 1);
+    t.tile_start.alloc(ctx, (uint64_t) pl.n_coarse + 1);
+    LAUNCH(ctx, sp_coarse_cursors_kernel, div_up(pl.n_coarse, 256), 256, 0, hist.p, pl.s, pl.n_coarse, t.cur1.p);
+    CUDA_CHECK(cudaMemcpyAsync(t.cur2.p, hist.p, ((size_t) pl.n_groups + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, sp_tiles_kernel, 1, 1024, 0, hist.p, pl.s, pl.n_coarse, pl.n_groups, (uint32_t) SpCfg<W>::CAP2, t.tile_start.p);
+    uint32_t n32 = 0;
+    ctx->fetch(&n32, total_dev.p, 4);
+    t.n = n32;
+}
+
+// pass 2: mid (grouped by coarse bin) -> out (grouped by fine group)
+template<int W>
+static void staged_pass2(sb200_ctx *ctx, const StagedPlan &pl, const StagedTables &t, const uint32_t *fine_start, const GroupSel &gs, uint64_t lw_keep,
+                         const uint64_t *mid, const uint8_t *mid_pay, uint64_t *out, uint8_t *out_pay) {
+    constexpr int CAP2 = SpCfg<W>::CAP2;
+    const size_t smem = 2 * (size_t) CAP2 * W * 8 + (size_t) CAP2 * 4 + 2 * (size_t) CAP2 + (size_t) (3 * SP_MAX_BINS + 1) * 4 + 64;
+    auto sp_scatter_fine_kernel_ = sp_scatter_fine_kernel<W>;
+    CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_fine_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    LAUNCH(ctx, sp_scatter_fine_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem, mid, mid_pay, fine_start, t.tile_start.p, gs, lw_keep, pl.s,
+           pl.n_coarse, pl.n_groups, t.cur2.p, out, out_pay);
+}
+
 
 // Sort + unique + counts + bucket table of UNGROUPED instances (records that came through an exchange, sb200_count_records): one or two
 // stable counting passes group them by the composite key (radix_sort.cuh), then finish_grouped.  `inst` (n x W) is consumed.
@@ -495,7 +558,7 @@ static sb200_kmers *count_reads_legacy_w(sb200_ctx *ctx, const sb200_reads *rd, 
 // stages bin runs in shared memory stays the default; this one is kept as an independent implementation for the cross-checks.
 template<int W>
 static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, int canonical_only, int add_rc, uint32_t B) {
-    if (!ctx->atomic_partition || 2 * K < 24) return count_reads_legacy_w<W>(ctx, rd, K, canonical_only, add_rc, B);
+    if (ctx->counting_passes || 2 * K < 24) return count_reads_legacy_w<W>(ctx, rd, K, canonical_only, add_rc, B);
     const int mode = canonical_only ? (add_rc ? PART_CANON : PART_MINIMAL_ONLY) : PART_FWD;
     const bool both = !canonical_only && add_rc;   // spades-kmercount: every k-mer of both strands
     // upper bound of the instance count (positions are 32-bit) and the estimate that sizes the groups
@@ -503,6 +566,37 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
     const uint64_t shorter = rd->n_reads * (uint64_t) (K - 1);
     const uint64_t n_est = std::max<uint64_t>(bases > shorter ? bases - shorter : 1, 1) * (both ? 2 : 1);
     SB200_REQUIRE(bases * (both ? 2 : 1) < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    StagedPlan pl;
+    if (!ctx->atomic_partition) {
+        if (!staged_plan<W>(ctx, n_est, B, K, pl)) return count_reads_legacy_w<W>(ctx, rd, K, canonical_only, add_rc, B);
+        const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * K : 64};
+        DevBuf<uint32_t> hist(ctx, (uint64_t) pl.n_groups + 1);
+        hist.zero();
+        auto sp_count_reads_kernel_ = sp_count_reads_kernel<W>;
+        auto sp_scatter_reads_kernel_ = sp_scatter_reads_kernel<W>;
+        const size_t smem_c = (size_t) pl.n_groups * 4, smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, false);
+        CUDA_CHECK(cudaFuncSetAttribute(sp_count_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_c));
+        CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+        const unsigned grid_c = (unsigned) ctx->num_sms, grid_s = (unsigned) ctx->num_sms * 2;
+        LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, pl.n_groups, hist.p);
+        if (both) LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, pl.n_groups, hist.p);
+        StagedTables t;
+        staged_tables<W>(ctx, pl, hist, t);
+        const uint64_t n = t.n;
+        SB200_REQUIRE(n > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
+        DevBuf<uint64_t> inst(ctx, n * W), mid(ctx, n * W);
+        // a tile takes `rounds` chunks per warp: as many as fit its capacity when every chunk is full
+        const uint32_t max_nwin = rd->max_len >= (uint32_t) K ? rd->max_len - (uint32_t) K + 1 : 128u;
+        const uint32_t chunk_cap = 32u * std::min<uint32_t>(PART_RUN, (max_nwin + 31u) / 32u);
+        const int rounds = std::max<int>(1, SpCfg<W>::CAP / (int) (SP_WARPS * chunk_cap));
+        LAUNCH(ctx, sp_scatter_reads_kernel_, grid_s, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, pl.s, pl.n_coarse,
+               rounds, t.cur1.p, mid.p);
+        if (both) LAUNCH(ctx, sp_scatter_reads_kernel_, grid_s, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, pl.s,
+                         pl.n_coarse, rounds, t.cur1.p, mid.p);
+        staged_pass2<W>(ctx, pl, t, hist.p, gs, ~0ULL, mid.p, nullptr, inst.p, nullptr);
+        ctx->trace_point("  instances partitioned (staged)");
+        return finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, K, B, true, mode == PART_CANON, false, -1, nullptr, 0, B);
+    }
     const int p = choose_prefix_bits<W>(n_est, B, K);
     const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
     const GroupSel gs{B, 0u, p, (W == 1) ? 2 * K : 64};
@@ -545,7 +639,9 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
     // otherwise the fused path keeps the bit in a byte beside the record
     const int used = 2 * (k - 32 * (W - 1));
     const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
-    if (!ctx->atomic_partition || 2 * k < 24) {
+    StagedPlan pl;
+    const bool staged = !ctx->counting_passes && !ctx->atomic_partition && 2 * k >= 24 && staged_plan<W>(ctx, n, B, k, pl);
+    if (!staged && (!ctx->atomic_partition || 2 * k < 24)) {
         DevBuf<uint64_t> inst(ctx, n * W);
         auto derive_kernel_ = derive_kernel<WS, W>;
         LAUNCH(ctx, derive_kernel_, div_up(kp->size, 256), 256, 0, kp->data.p, kp->size, k, pshift, inst.p);
@@ -554,6 +650,30 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
         return s;
     }
     SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: shard the input");
+    if (staged) {
+        const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * k : 64};
+        DevBuf<uint32_t> hist(ctx, (uint64_t) pl.n_groups + 1);
+        hist.zero();
+        const bool side_pay = pshift < 0 && !ctx->no_mask_payload;
+        auto sp_count_derive_kernel_ = sp_count_derive_kernel<WS, W>;
+        auto sp_scatter_derive_kernel_ = sp_scatter_derive_kernel<WS, W>;
+        const size_t smem_c = (size_t) pl.n_groups * 4, smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, side_pay);
+        CUDA_CHECK(cudaFuncSetAttribute(sp_count_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_c));
+        CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+        LAUNCH(ctx, sp_count_derive_kernel_, (unsigned) ctx->num_sms, SPC_THREADS, smem_c, kp->data.p, kp->size, k, gs, pl.n_groups, hist.p);
+        StagedTables t;
+        staged_tables<W>(ctx, pl, hist, t);
+        DevBuf<uint64_t> inst(ctx, n * W), mid(ctx, n * W);
+        DevBuf<uint8_t> pay, mid_pay;
+        if (side_pay) { pay.alloc(ctx, n); mid_pay.alloc(ctx, n); }
+        LAUNCH(ctx, sp_scatter_derive_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, pshift, gs, pl.s, pl.n_coarse, t.cur1.p,
+               mid.p, mid_pay.p);
+        staged_pass2<W>(ctx, pl, t, hist.p, gs, last_word_mask(k), mid.p, mid_pay.p, inst.p, pay.p);
+        ctx->trace_point("  candidates partitioned (staged)");
+        sb200_kmers *s = finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, k, B, false, false, false, pshift, pay.p, 0, B);
+        s->instances = 0;
+        return s;
+    }
     const int p = choose_prefix_bits<W>(n, B, k);
     const uint32_t n_groups = (uint32_t) ((uint64_t) B << p);
     const GroupSel gs{B, 0u, p, (W == 1) ? 2 * k : 64};

@@ -1,0 +1,450 @@
+// staged_partition.cuh — producer-fused grouping of k-mer instances in two staged passes.
+//
+// Round 1 materialised every instance (extract / derive kernel: one write), then grouped the array with two counting passes, each a
+// histogram kernel (one read) and a scatter kernel (one read + one write): the instances crossed HBM eight times before the group
+// kernel saw them.  A one-pass scatter through L2 atomics (partition.cuh) moves them only twice but issues one L2 request per RECORD,
+// and the L2's request rate — not its bandwidth — bounds it (profiles/r2a_ubench.log: 291 M scattered 16-byte stores + atomics = 7.4 ms).
+// Here the producer is the first pass and every trip to L2 is a burst:
+//   count   the producer (windows of reads / candidates of (k+1)-mers) runs once without storing anything: every CTA keeps the histogram
+//           of the FINE group key  g = bucket << p | top p value bits  in shared memory (n_groups <= 49152 counters) and adds it to the
+//           global histogram at the end.  One scan gives the group starts — the table the group kernel needs — and, read at a stride of
+//           2^s groups, the starts of the COARSE bins  c = g >> s.
+//   pass 1  the producer runs again; a CTA collects a tile of records in shared memory, orders the tile by coarse bin (shared-memory
+//           histogram, scan, ranks), claims a run per non-empty bin with ONE global atomic and writes the run as a coalesced burst.
+//   pass 2  tiles of one coarse bin are loaded with bulk asynchronous copies (cp.async.bulk global -> shared, mbarrier completion,
+//           double buffered), ordered by the fine group inside the bin (2^s local bins) and written out the same way.
+// The instances cross HBM four times (written by pass 1, read + written by pass 2, read by the group kernel); no pass reads a histogram
+// matrix, and no pass makes a per-record request to L2.  Record order inside a group is arbitrary (the group kernel hashes).
+// Reference stages replaced: KMerSortingSplitter's per-thread x per-bucket cells and DumpBuffers (C/utils/kmer_mph/kmer_splitter.hpp:
+// 73-167), DeBruijnReadKMerSplitter / DeBruijnKMerKMerSplitter producers (kmer_splitters.hpp:25-59,159-204).
+#pragma once
+#include "common.cuh"
+#include "kmer_ops.cuh"
+#include "partition.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sb200 {
+
+constexpr int SP_THREADS = 512;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_MAX_BINS = 1024;             // local bins of a tile (coarse bins in pass 1, fine groups of one coarse bin in pass 2)
+constexpr uint32_t SP_MAX_GROUPS = 49152;     // fine groups the count kernels keep in shared memory (192 KB of counters)
+constexpr int SPC_THREADS = 1024;             // count kernels: one CTA per SM (the histogram fills the shared memory), 32 warps
+template<int W> struct SpCfg {
+    static constexpr int CAP = (W <= 2) ? 4608 : 2304;   // records of a pass-1 tile: 72 KB of records + ordering arrays, two CTAs per SM
+    static constexpr int CAP2 = (W <= 2) ? 2048 : 1024;  // records of a pass-2 tile (two bulk-copy buffers of 32 KB), two CTAs per SM
+};
+
+// ---- the shared-memory stage of one tile -----------------------------------------------------------------------------------------
+struct SpStage {
+    uint64_t *rec;       // CAP x W words, arrival order
+    uint16_t *bin;       // local bin of every record
+    uint16_t *src;       // src[d] = arrival slot of the record that leaves at position d of the bin-ordered tile
+    uint8_t *pay;        // mask-bit payload beside the record (or nullptr)
+    uint32_t *bstart;    // SP_MAX_BINS + 1: first position of every bin in the ordered tile
+    uint32_t *cursor;    // SP_MAX_BINS: records of the bin placed so far (= its size after placement)
+    uint32_t *gdelta;    // SP_MAX_BINS: global position of the bin's run minus its position in the tile
+};
+
+template<int W>
+constexpr size_t sp_stage_bytes(int cap, bool with_pay) {
+    return (size_t) cap * W * 8 + (size_t) cap * 2 * 2 + (with_pay ? (size_t) cap : 0) + (size_t) (3 * SP_MAX_BINS + 1) * 4 + 64;
+}
+
+template<int W>
+__device__ __forceinline__ SpStage sp_carve(unsigned char *raw, int cap, bool with_pay) {
+    SpStage s;
+    s.rec = reinterpret_cast<uint64_t *>(raw);
+    unsigned char *p = raw + (size_t) cap * W * 8;
+    s.bin = reinterpret_cast<uint16_t *>(p); p += (size_t) cap * 2;
+    s.src = reinterpret_cast<uint16_t *>(p); p += (size_t) cap * 2;
+    s.pay = with_pay ? p : nullptr;
+    if (with_pay) p += (size_t) cap;
+    p = reinterpret_cast<unsigned char *>(((uintptr_t) p + 15) & ~(uintptr_t) 15);
+    s.bstart = reinterpret_cast<uint32_t *>(p);
+    s.cursor = s.bstart + SP_MAX_BINS + 1;
+    s.gdelta = s.cursor + SP_MAX_BINS;
+    return s;
+}
+
+// Orders the n staged records by local bin and writes every bin's run to out[] at a position claimed from gcursor[first_bin + bin].
+// All threads of the CTA call it; the stage may be refilled when it returns.
+template<int W>
+__device__ __forceinline__ void sp_flush(const SpStage &st, uint32_t n, uint32_t n_bins, uint32_t *__restrict__ gcursor, uint32_t first_bin,
+                                         uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay, uint32_t *s_scan) {
+    for (uint32_t b = threadIdx.x; b <= n_bins; b += SP_THREADS) st.bstart[b] = 0;
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n; q += SP_THREADS) atomicAdd(&st.bstart[st.bin[q]], 1u);
+    __syncthreads();
+    {   // exclusive scan of up to 1024 bin counts: two per thread
+        const uint32_t b0 = 2u * threadIdx.x, b1 = b0 + 1u;
+        const uint32_t c0 = b0 < n_bins ? st.bstart[b0] : 0u, c1 = b1 < n_bins ? st.bstart[b1] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<uint32_t, SP_THREADS>(c0 + c1, &total, s_scan);
+        if (b0 < n_bins) { st.bstart[b0] = ex; st.cursor[b0] = 0; }
+        if (b1 < n_bins) { st.bstart[b1] = ex + c0; st.cursor[b1] = 0; }
+        if (threadIdx.x == 0) st.bstart[n_bins] = total;
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n; q += SP_THREADS) {
+        const uint32_t b = st.bin[q];
+        st.src[st.bstart[b] + atomicAdd(&st.cursor[b], 1u)] = (uint16_t) q;
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < n_bins; b += SP_THREADS) {   // one global atomic per non-empty bin of the tile
+        const uint32_t c = st.cursor[b];
+        if (c) st.gdelta[b] = atomicAdd(&gcursor[first_bin + b], c) - st.bstart[b];
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < n; d += SP_THREADS) {        // consecutive d of one bin -> consecutive records in HBM
+        const uint32_t q = st.src[d];
+        const uint32_t g = st.gdelta[st.bin[q]] + d;
+        uint64_t r[W];
+        if (W == 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(st.rec + (size_t) q * 2);
+            r[0] = v.x; r[1] = v.y;
+        } else if (W == 4) {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(st.rec + (size_t) q * 4);
+            const ulonglong2 a = p[0], c = p[1];
+            r[0] = a.x; r[1] = a.y; r[2] = c.x; r[3] = c.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) r[j] = st.rec[(size_t) q * W + j];
+        }
+        store_rec<W>(out, g, r);
+        if (out_pay) out_pay[g] = st.pay[q];
+    }
+    __syncthreads();
+}
+
+template<int W>
+__device__ __forceinline__ void sp_put(const SpStage &st, uint32_t slot, const uint64_t *r, uint32_t bin) {
+    if (W == 2) {
+        *reinterpret_cast<ulonglong2 *>(st.rec + (size_t) slot * 2) = make_ulonglong2(r[0], r[1]);
+    } else if (W == 4) {
+        ulonglong2 *p = reinterpret_cast<ulonglong2 *>(st.rec + (size_t) slot * 4);
+        p[0] = make_ulonglong2(r[0], r[1]);
+        p[1] = make_ulonglong2(r[2], r[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) st.rec[(size_t) slot * W + j] = r[j];
+    }
+    st.bin[slot] = (uint16_t) bin;
+}
+
+// ---- reads: one warp per chunk of <= 128 windows of a read, every lane rolls through a run of consecutive windows (partition.cuh) ----
+// State of a warp's walk over its reads: read index, first window of the next chunk.
+struct SpReadCursor {
+    uint64_t rd;
+    uint32_t c0;
+};
+
+// Forms the records of the warp's next chunk.  Returns the number of valid records of this LANE (<= PART_RUN); rec / gid hold them.
+template<int W>
+__device__ __forceinline__ uint32_t sp_read_chunk(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off, const uint32_t *__restrict__ len,
+                                                  uint64_t n_reads, uint64_t warps_total, int K, int mode, const GroupSel &gs, SpReadCursor &cur,
+                                                  uint64_t rec[PART_RUN][W], uint32_t gid[PART_RUN], bool &exhausted) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t lw_mask = last_word_mask(K);
+    uint32_t valid = 0;
+    // skip reads that are too short / finished
+    while (cur.rd < n_reads) {
+        const uint32_t l = len[cur.rd];
+        if (l >= (uint32_t) K && cur.c0 < l - (uint32_t) K + 1) break;
+        cur.rd += warps_total;
+        cur.c0 = 0;
+    }
+    if (cur.rd >= n_reads) { exhausted = true; return 0; }
+    const uint32_t l = len[cur.rd];
+    const uint32_t nwin = l - (uint32_t) K + 1, nw = (l + 31) >> 5;
+    const uint64_t *seq = words + word_off[cur.rd];
+    const uint32_t left = nwin - cur.c0;
+    const uint32_t run = left >= 32u * PART_RUN ? (uint32_t) PART_RUN : (left + 31u) >> 5;
+    const uint32_t p0 = cur.c0 + (uint32_t) lane * run;
+    if (p0 < nwin) {
+        uint64_t x[W], r[W];
+        kmer_window<W>(seq, nw, p0, K, x);
+        kmer_rc<W>(x, K, r);
+        uint64_t nxt = 0;
+        if (run > 1 && p0 + (uint32_t) K < l) kmer_window<1>(seq, nw, p0 + (uint32_t) K, 32, &nxt);
+#pragma unroll
+        for (int i = 0; i < PART_RUN; ++i) {
+            if ((uint32_t) i < run && p0 + (uint32_t) i < nwin) {
+                if (i > 0) kmer_roll<W>(x, r, K, (uint32_t) (nxt >> (2 * (i - 1))) & 3u, lw_mask);
+                const bool minimal = kmer_ge_num<W>(r, x);
+                const bool take_x = mode == PART_FWD || (mode != PART_REV && minimal);
+                if (mode != PART_MINIMAL_ONLY || minimal) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) rec[i][j] = take_x ? x[j] : r[j];
+                    gid[i] = group_of<W>(rec[i], gs);
+                    valid |= 1u << i;
+                }
+            }
+        }
+    }
+    cur.c0 += 32u * run;
+    return valid;
+}
+
+// count: fine-group histogram in shared memory, flushed to the global one at the end
+template<int W>
+__global__ void __launch_bounds__(SPC_THREADS) sp_count_reads_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
+                                                                   const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode, GroupSel gs,
+                                                                   uint32_t n_groups, uint32_t *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(sp_smem);
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) sh[i] = 0;
+    __syncthreads();
+    const uint64_t warps_total = (uint64_t) gridDim.x * (SPC_THREADS / 32);
+    SpReadCursor cur{(uint64_t) blockIdx.x * (SPC_THREADS / 32) + (threadIdx.x >> 5), 0u};
+    bool exhausted = false;
+    while (!exhausted) {
+        uint64_t rec[PART_RUN][W];
+        uint32_t gid[PART_RUN];
+        const uint32_t valid = sp_read_chunk<W>(words, word_off, len, n_reads, warps_total, K, mode, gs, cur, rec, gid, exhausted);
+#pragma unroll
+        for (int i = 0; i < PART_RUN; ++i)
+            if ((valid >> i) & 1u) atomicAdd(&sh[gid[i]], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// pass 1: tiles of <= rounds x 16 chunks, ordered by coarse bin c = g >> s, runs written at the bins' cursors
+template<int W>
+__global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
+                                                                     const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode, GroupSel gs,
+                                                                     int s, uint32_t n_coarse, int rounds, uint32_t *__restrict__ gcursor,
+                                                                     uint64_t *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ uint32_t s_fill, s_scan[SP_THREADS / 32 + 1];
+    const SpStage st = sp_carve<W>(sp_smem, SpCfg<W>::CAP, false);
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t) gridDim.x * SP_WARPS;
+    SpReadCursor cur{(uint64_t) blockIdx.x * SP_WARPS + (threadIdx.x >> 5), 0u};
+    bool exhausted = false;
+    while (true) {
+        if (threadIdx.x == 0) s_fill = 0;
+        __syncthreads();
+        for (int round = 0; round < rounds; ++round) {
+            if (exhausted) continue;
+            uint64_t rec[PART_RUN][W];
+            uint32_t gid[PART_RUN];
+            const uint32_t valid = sp_read_chunk<W>(words, word_off, len, n_reads, warps_total, K, mode, gs, cur, rec, gid, exhausted);
+            // the warp reserves room for its valid records with one shared-memory atomic
+            const uint32_t mine = (uint32_t) __popc(valid);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&s_fill, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t slot = base + incl - mine;
+#pragma unroll
+            for (int i = 0; i < PART_RUN; ++i)
+                if ((valid >> i) & 1u) sp_put<W>(st, slot++, rec[i], gid[i] >> s);
+        }
+        __syncthreads();
+        const uint32_t n = s_fill;
+        if (n) sp_flush<W>(st, n, n_coarse, gcursor, 0u, out, nullptr, s_scan);
+        if (__syncthreads_and(exhausted ? 1 : 0)) break;
+    }
+}
+
+// ---- k-mer candidates of (k+1)-mers (partition.cuh derive_candidates) -----------------------------------------------------------------
+template<int WS, int W>
+__global__ void __launch_bounds__(SPC_THREADS) sp_count_derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, GroupSel gs, uint32_t n_groups,
+                                                                    uint32_t *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(sp_smem);
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t) blockIdx.x * SPC_THREADS + threadIdx.x; i < n; i += (uint64_t) gridDim.x * SPC_THREADS) {
+        uint64_t x[WS], a[2][W];
+        uint32_t bit[2];
+        load_rec<WS>(kp, i, x);
+        derive_candidates<WS, W>(x, k, a, bit);
+        atomicAdd(&sh[group_of<W>(a[0], gs)], 1u);
+        atomicAdd(&sh[group_of<W>(a[1], gs)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+template<int WS, int W>
+__global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, int pshift, GroupSel gs, int s,
+                                                                      uint32_t n_coarse, uint32_t *__restrict__ gcursor, uint64_t *__restrict__ out,
+                                                                      uint8_t *__restrict__ out_pay) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ uint32_t s_scan[SP_THREADS / 32 + 1];
+    constexpr int CAP = SpCfg<W>::CAP;
+    constexpr uint64_t SRC_PER_TILE = CAP / 2;
+    const SpStage st = sp_carve<W>(sp_smem, CAP, out_pay != nullptr);
+    for (uint64_t t0 = (uint64_t) blockIdx.x * SRC_PER_TILE; t0 < n; t0 += (uint64_t) gridDim.x * SRC_PER_TILE) {
+        const uint32_t cnt = (uint32_t) ((n - t0) < SRC_PER_TILE ? (n - t0) : SRC_PER_TILE);
+        for (uint32_t j = threadIdx.x; j < cnt; j += SP_THREADS) {
+            uint64_t x[WS], a[2][W];
+            uint32_t bit[2];
+            load_rec<WS>(kp, t0 + j, x);
+            derive_candidates<WS, W>(x, k, a, bit);
+            const uint32_t g0 = group_of<W>(a[0], gs), g1 = group_of<W>(a[1], gs);
+            if (pshift >= 0) {
+                a[0][W - 1] |= (uint64_t) bit[0] << pshift;
+                a[1][W - 1] |= (uint64_t) bit[1] << pshift;
+            } else if (st.pay) {
+                st.pay[2 * j] = (uint8_t) bit[0];
+                st.pay[2 * j + 1] = (uint8_t) bit[1];
+            }
+            sp_put<W>(st, 2 * j, a[0], g0 >> s);
+            sp_put<W>(st, 2 * j + 1, a[1], g1 >> s);
+        }
+        __syncthreads();
+        sp_flush<W>(st, 2 * cnt, n_coarse, gcursor, 0u, out, out_pay, s_scan);
+    }
+}
+
+// ---- pass 2: tiles of ONE coarse bin, loaded with bulk asynchronous copies, ordered by the fine group ------------------------------------
+__device__ __forceinline__ uint32_t sp_smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sp_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(sp_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(sp_smem_addr(bar)), "r"(phase) : "memory");
+}
+
+// tile_start[c] = first tile of coarse bin c (tiles of CAP2 records), tile_start[n_coarse] = number of tiles
+__global__ void sp_tiles_kernel(const uint32_t *__restrict__ fine_start, int s, uint32_t n_coarse, uint32_t n_groups, uint32_t cap2,
+                                uint32_t *__restrict__ tile_start) {
+    // one CTA: n_coarse <= 1024
+    __shared__ uint32_t sm[1024 / 32 + 1];
+    const uint32_t c = threadIdx.x;
+    uint32_t t = 0;
+    if (c < n_coarse) {
+        const uint32_t lo = fine_start[(uint64_t) c << s];
+        const uint64_t hi_g = ((uint64_t) c + 1) << s;
+        const uint32_t hi = fine_start[hi_g < n_groups ? hi_g : n_groups];
+        t = (hi - lo + cap2 - 1) / cap2;
+    }
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan<uint32_t, 1024>(t, &total, sm);
+    if (c < n_coarse) tile_start[c] = ex;
+    if (c == 0) tile_start[n_coarse] = total;
+}
+
+template<int W>
+__global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const uint64_t *__restrict__ mid, const uint8_t *__restrict__ mid_pay,
+                                                                    const uint32_t *__restrict__ fine_start, const uint32_t *__restrict__ tile_start,
+                                                                    GroupSel gs, uint64_t lw_keep, int s, uint32_t n_coarse, uint32_t n_groups,
+                                                                    uint32_t *__restrict__ gcursor, uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay) {
+    extern __shared__ __align__(128) unsigned char sp_smem[];
+    __shared__ uint32_t s_scan[SP_THREADS / 32 + 1];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tile_c[2], s_tile_lo[2], s_tile_n[2];
+    __shared__ uint32_t s_tstart[SP_MAX_BINS + 1], s_cstart[SP_MAX_BINS + 1];   // first tile / first record of every coarse bin
+    constexpr int CAP2 = SpCfg<W>::CAP2;
+    const bool with_pay = mid_pay != nullptr;
+    // two record buffers (bulk-copy destinations), then ONE set of ordering arrays: a tile is ordered and written out before the next
+    unsigned char *buf[2] = {sp_smem, sp_smem + (size_t) CAP2 * W * 8};
+    unsigned char *aux = sp_smem + 2 * (size_t) CAP2 * W * 8;
+    SpStage st;
+    st.bin = reinterpret_cast<uint16_t *>(aux); aux += (size_t) CAP2 * 2;
+    st.src = reinterpret_cast<uint16_t *>(aux); aux += (size_t) CAP2 * 2;
+    uint8_t *paybuf[2] = {aux, aux + CAP2};
+    aux += 2 * (size_t) CAP2;
+    st.bstart = reinterpret_cast<uint32_t *>(((uintptr_t) aux + 15) & ~(uintptr_t) 15);
+    st.cursor = st.bstart + SP_MAX_BINS + 1;
+    st.gdelta = st.cursor + SP_MAX_BINS;
+    const uint32_t n_local = 1u << s;
+    for (uint32_t c = threadIdx.x; c <= n_coarse; c += SP_THREADS) {
+        s_tstart[c] = tile_start[c];
+        const uint64_t g = (uint64_t) c << s;
+        s_cstart[c] = fine_start[g < n_groups ? g : n_groups];
+    }
+    __syncthreads();
+    const uint32_t n_tiles = s_tstart[n_coarse];
+
+    auto issue = [&](uint32_t t, int b) {   // thread 0: locate tile t (coarse bin by binary search over the tile table) and start its copy into buffer b
+        uint32_t lo = 0, hi = n_coarse;     // last c with s_tstart[c] <= t
+        while (hi - lo > 1) {
+            const uint32_t mid_c = (lo + hi) >> 1;
+            if (s_tstart[mid_c] <= t) lo = mid_c; else hi = mid_c;
+        }
+        const uint32_t c = lo;
+        const uint32_t first = s_cstart[c], last = s_cstart[c + 1];
+        const uint32_t begin = first + (t - s_tstart[c]) * (uint32_t) CAP2;
+        const uint32_t cnt = (last - begin) < (uint32_t) CAP2 ? (last - begin) : (uint32_t) CAP2;
+        s_tile_c[b] = c; s_tile_lo[b] = begin; s_tile_n[b] = cnt;
+        // bulk copies need 16-byte aligned addresses and sizes: record arrays are 256-byte aligned and W * 8 = 16 or 32 (W = 2, 4) keeps
+        // every record boundary aligned; odd W and the payload bytes take plain loads (below)
+        if (W % 2 == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
+            sp_mbar_expect(&s_bar[b], cnt * (uint32_t) (W * 8));
+            sp_bulk_g2s(buf[b], mid + (uint64_t) begin * W, cnt * (uint32_t) (W * 8), &s_bar[b]);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        sp_mbar_init(&s_bar[0], 1);
+        sp_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t t = blockIdx.x;
+    if (t < n_tiles && threadIdx.x == 0) issue(t, 0);
+    uint32_t phase[2] = {0, 0};
+    int b = 0;
+    for (; t < n_tiles; t += gridDim.x, b ^= 1) {
+        __syncthreads();   // the previous iteration's flush is done with the ordering arrays; s_tile_*[b] is visible
+        const uint32_t tn = t + gridDim.x;
+        if (tn < n_tiles && threadIdx.x == 0) issue(tn, b ^ 1);   // prefetch the next tile while this one is ordered
+        const uint32_t c = s_tile_c[b], begin = s_tile_lo[b], cnt = s_tile_n[b];
+        st.rec = reinterpret_cast<uint64_t *>(buf[b]);
+        st.pay = with_pay ? paybuf[b] : nullptr;
+        if (W % 2 == 0) {
+            sp_mbar_wait(&s_bar[b], phase[b]);
+            phase[b] ^= 1;
+        } else {
+            for (uint32_t q = threadIdx.x; q < cnt * (uint32_t) W; q += SP_THREADS) st.rec[q] = mid[(uint64_t) begin * W + q];
+        }
+        if (with_pay)
+            for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) st.pay[q] = mid_pay[begin + q];
+        if (W % 2 != 0) __syncthreads();
+        const uint32_t gbase = c << s;
+        for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) {
+            uint64_t r[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) r[j] = st.rec[(size_t) q * W + j];
+            r[W - 1] &= lw_keep;   // the group key ignores a mask-bit payload in the padding
+            st.bin[q] = (uint16_t) (group_of<W>(r, gs) - gbase);
+        }
+        __syncthreads();
+        sp_flush<W>(st, cnt, n_local, gcursor, gbase, out, out_pay, s_scan);
+    }
+}
+
+}  // namespace sb200

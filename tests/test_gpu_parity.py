@@ -334,11 +334,12 @@ def test_low_complexity_reads_overflow_a_segment(ctx):
     assert B.UnbranchingPathExtractor(index, k).ExtractUnbranchingPathsAndLoops() == want["unitigs"]
 
 
-def test_atomic_partition_path(monkeypatch):
-    """SB200_ATOMIC_PARTITION=1: reads / (k+1)-mers go straight into their groups through L2 atomics (partition.cuh: rolling windows,
-    one reverse complement per (k+1)-mer, mask bits beside the records when the k-mer fills its last word) instead of extract /
-    derive + counting passes — the same tables, masks and unitigs for one- to four-word records, the kmercount modes and the tip clipper."""
-    monkeypatch.setenv("SB200_ATOMIC_PARTITION", "1")
+@pytest.mark.parametrize("env", ["SB200_ATOMIC_PARTITION", "SB200_COUNTING_PASSES"])
+def test_alternative_grouping_paths(monkeypatch, env):
+    """The default grouping is the staged producer-fused partition (staged_partition.cuh).  SB200_ATOMIC_PARTITION=1: reads / (k+1)-mers
+    go straight into their groups through L2 atomics (partition.cuh); SB200_COUNTING_PASSES=1: round 1's extract / derive + two
+    histogram + scatter passes — the same tables, masks and unitigs for one- to four-word records, the kmercount modes and the tip clipper."""
+    monkeypatch.setenv(env, "1")
     ctx2 = B.Context(0)
     try:
         from conftest import load_golden
@@ -406,7 +407,7 @@ def test_baseline_config2_full_size(monkeypatch):
     monkeypatch.setenv("SB200_NO_LINKS", "1")
     monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
     monkeypatch.setenv("SB200_NO_PLACE", "1")            # and k-mer indices by MPHF lookups instead of the build's placement record
-    monkeypatch.setenv("SB200_ATOMIC_PARTITION", "1")    # and the one-pass partition through L2 atomics instead of extract / derive + counting passes
+    monkeypatch.setenv("SB200_COUNTING_PASSES", "1")     # and extract / derive + counting passes instead of the staged producer-fused partition
     ctx2 = B.Context(0)
     try:
         streams, index, kp, (w, off, ln) = run(ctx2)
