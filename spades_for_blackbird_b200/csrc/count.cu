@@ -8,6 +8,8 @@
 // The reference streams every read and its reverse complement and keeps a window iff it IsMinimal(); here each
 // forward window emits min(x, rc(x)) once (a self-reverse-complement window counts twice, exactly as both of the
 // reference's streams would count it), so half of the work and none of the RC stream exists.
+#include <memory>
+
 #include "common.cuh"
 #include "kmer_ops.cuh"
 #include "kmer_set.cuh"
@@ -408,9 +410,29 @@ static bool staged_plan(sb200_ctx *ctx, uint64_t n_est, uint32_t B, int K, Stage
     return true;
 }
 
-// After the count pass: group starts, cursors of both passes, tile table.  hist (n_groups + 1 counts) becomes the fine starts.
+// Tiles of pass 2 from a segment list (begin / count / first fine group of every run of records that shares a coarse bin)
+struct StagedTiles {
+    DevBuf<SpTile> tiles;
+    DevBuf<uint32_t> tile_off;   // n_seg + 1: exclusive scan of the tiles per segment; the last entry is the number of tiles
+    uint32_t n_seg = 0;
+};
+
+template<int W>
+static void staged_tiles(sb200_ctx *ctx, const uint32_t *seg_begin, const uint32_t *seg_cnt, const uint32_t *seg_gbase, uint32_t n_seg, uint64_t n,
+                         StagedTiles &t) {
+    constexpr uint32_t CAP2 = SpCfg<W>::CAP2;
+    t.n_seg = n_seg;
+    t.tile_off.alloc(ctx, (uint64_t) n_seg + 1);
+    t.tiles.alloc(ctx, n / CAP2 + n_seg + 1);   // ceil(c_i / CAP2) summed over the segments is at most n / CAP2 + n_seg
+    LAUNCH(ctx, sp_seg_tiles_kernel, div_up((uint64_t) n_seg + 1, 256), 256, 0, seg_cnt, n_seg, CAP2, t.tile_off.p);
+    exclusive_scan<uint32_t>(ctx, t.tile_off.p, (uint64_t) n_seg + 1, nullptr);
+    LAUNCH(ctx, sp_tile_fill_kernel, div_up(n_seg, 256), 256, 0, seg_begin, seg_cnt, seg_gbase, t.tile_off.p, n_seg, CAP2, t.tiles.p);
+}
+
+// After the count pass: group starts, cursors of both passes, tiles of pass 2.  hist (n_groups + 1 counts) becomes the fine starts.
 struct StagedTables {
-    DevBuf<uint32_t> cur1, cur2, tile_start;
+    DevBuf<uint32_t> cur1, cur2, seg;
+    StagedTiles tiles;
     uint64_t n = 0;
 };
 
@@ -425,27 +447,28 @@ static void staged_tables(sb200_ctx *ctx, const StagedPlan &pl, DevBuf<uint32_t>
     exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) pl.n_groups + 1, total_dev.p);   // hist[g] = first record of group g, hist[n_groups] = n
     t.cur1.alloc(ctx, pl.n_coarse);
     t.cur2.alloc(ctx, (uint64_t) pl.n_groups + 1);
-    t.tile_start.alloc(ctx, (uint64_t) pl.n_coarse + 1);
+    t.seg.alloc(ctx, 3 * (uint64_t) pl.n_coarse);
     LAUNCH(ctx, sp_coarse_cursors_kernel, div_up(pl.n_coarse, 256), 256, 0, hist.p, pl.s, pl.n_coarse, t.cur1.p);
     CUDA_CHECK(cudaMemcpyAsync(t.cur2.p, hist.p, ((size_t) pl.n_groups + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(ctx, sp_tiles_kernel, 1, 1024, 0, hist.p, pl.s, pl.n_coarse, pl.n_groups, (uint32_t) SpCfg<W>::CAP2, t.tile_start.p);
+    LAUNCH(ctx, sp_coarse_segments_kernel, div_up(pl.n_coarse, 256), 256, 0, hist.p, pl.s, pl.n_coarse, pl.n_groups, t.seg.p, t.seg.p + pl.n_coarse,
+           t.seg.p + 2 * (uint64_t) pl.n_coarse);
     uint32_t n32 = 0;
     ctx->fetch(&n32, total_dev.p, 4);
     t.n = n32;
+    staged_tiles<W>(ctx, t.seg.p, t.seg.p + pl.n_coarse, t.seg.p + 2 * (uint64_t) pl.n_coarse, pl.n_coarse, t.n, t.tiles);
 }
 
-// pass 2: mid (grouped by coarse bin) -> out (grouped by fine group)
+// pass 2: mid (runs of records per coarse bin, listed as tiles) -> out (grouped by fine group)
 template<int W>
-static void staged_pass2(sb200_ctx *ctx, const StagedPlan &pl, const StagedTables &t, const uint32_t *fine_start, const GroupSel &gs, uint64_t lw_keep,
-                         const uint64_t *mid, const uint8_t *mid_pay, uint64_t *out, uint8_t *out_pay) {
+static void staged_pass2(sb200_ctx *ctx, int s, const StagedTiles &tl, uint32_t *cur2, const GroupSel &gs, uint64_t lw_keep, const uint64_t *mid,
+                         const uint8_t *mid_pay, uint64_t *out, uint8_t *out_pay) {
     constexpr int CAP2 = SpCfg<W>::CAP2;
     const size_t smem = 2 * (size_t) CAP2 * W * 8 + (size_t) CAP2 * 4 + 2 * (size_t) CAP2 + (size_t) (3 * SP_MAX_BINS + 1) * 4 + 64;
     auto sp_scatter_fine_kernel_ = sp_scatter_fine_kernel<W>;
     CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_fine_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    LAUNCH(ctx, sp_scatter_fine_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem, mid, mid_pay, fine_start, t.tile_start.p, gs, lw_keep, pl.s,
-           pl.n_coarse, pl.n_groups, t.cur2.p, out, out_pay);
+    LAUNCH(ctx, sp_scatter_fine_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem, mid, mid_pay, tl.tiles.p, tl.tile_off.p + tl.n_seg, gs, lw_keep, s,
+           cur2, out, out_pay);
 }
-
 
 // Sort + unique + counts + bucket table of UNGROUPED instances (records that came through an exchange, sb200_count_records): one or two
 // stable counting passes group them by the composite key (radix_sort.cuh), then finish_grouped.  `inst` (n x W) is consumed.
@@ -578,8 +601,8 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
         CUDA_CHECK(cudaFuncSetAttribute(sp_count_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_c));
         CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
         const unsigned grid_c = (unsigned) ctx->num_sms, grid_s = (unsigned) ctx->num_sms * 2;
-        LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, pl.n_groups, hist.p);
-        if (both) LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, pl.n_groups, hist.p);
+        LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, 0, pl.n_groups, hist.p);
+        if (both) LAUNCH(ctx, sp_count_reads_kernel_, grid_c, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, 0, pl.n_groups, hist.p);
         StagedTables t;
         staged_tables<W>(ctx, pl, hist, t);
         const uint64_t n = t.n;
@@ -593,7 +616,7 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
                rounds, t.cur1.p, mid.p);
         if (both) LAUNCH(ctx, sp_scatter_reads_kernel_, grid_s, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, pl.s,
                          pl.n_coarse, rounds, t.cur1.p, mid.p);
-        staged_pass2<W>(ctx, pl, t, hist.p, gs, ~0ULL, mid.p, nullptr, inst.p, nullptr);
+        staged_pass2<W>(ctx, pl.s, t.tiles, t.cur2.p, gs, ~0ULL, mid.p, nullptr, inst.p, nullptr);
         ctx->trace_point("  instances partitioned (staged)");
         return finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, K, B, true, mode == PART_CANON, false, -1, nullptr, 0, B);
     }
@@ -660,7 +683,7 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
         const size_t smem_c = (size_t) pl.n_groups * 4, smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, side_pay);
         CUDA_CHECK(cudaFuncSetAttribute(sp_count_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_c));
         CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
-        LAUNCH(ctx, sp_count_derive_kernel_, (unsigned) ctx->num_sms, SPC_THREADS, smem_c, kp->data.p, kp->size, k, gs, pl.n_groups, hist.p);
+        LAUNCH(ctx, sp_count_derive_kernel_, (unsigned) ctx->num_sms, SPC_THREADS, smem_c, kp->data.p, kp->size, k, gs, 0, pl.n_groups, hist.p);
         StagedTables t;
         staged_tables<W>(ctx, pl, hist, t);
         DevBuf<uint64_t> inst(ctx, n * W), mid(ctx, n * W);
@@ -668,7 +691,7 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
         if (side_pay) { pay.alloc(ctx, n); mid_pay.alloc(ctx, n); }
         LAUNCH(ctx, sp_scatter_derive_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, pshift, gs, pl.s, pl.n_coarse, t.cur1.p,
                mid.p, mid_pay.p);
-        staged_pass2<W>(ctx, pl, t, hist.p, gs, last_word_mask(k), mid.p, mid_pay.p, inst.p, pay.p);
+        staged_pass2<W>(ctx, pl.s, t.tiles, t.cur2.p, gs, last_word_mask(k), mid.p, mid_pay.p, inst.p, pay.p);
         ctx->trace_point("  candidates partitioned (staged)");
         sb200_kmers *s = finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, k, B, false, false, false, pshift, pay.p, 0, B);
         s->instances = 0;
@@ -943,7 +966,7 @@ sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int wan
         s->ctx = ctx; s->k = r->k; s->words = r->words; s->num_buckets = B; s->size = 0;
         s->data.alloc(ctx, 0);
         if (want_counts) s->counts.alloc(ctx, 0);
-        if (r->mask_payload) s->masks_file.alloc(ctx, 4);
+        if (r->mask_payload || r->pay.p) s->masks_file.alloc(ctx, 4);
         s->bucket_starts.alloc(ctx, (uint64_t) B + 1);
         s->bucket_starts.zero();
         s->bucket_starts_host.assign((size_t) B + 1, 0);
@@ -960,6 +983,192 @@ sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int wan
     if (!want_counts) s->instances = 0;
     r->n = 0;
     return s;
+}
+
+// ---- hash-sharded path on the staged kernels -------------------------------------------------------------------------------------------
+// Sender: the producer (reads / own (k+1)-mers) runs the count pass over COARSE bins of the global group key only (G x n_co <= 1024 bins:
+// owner-major, so an owner's records are one contiguous range) and pass 1; records, run sizes (and payload bytes) travel.  Receiver: a
+// count pass over what arrived gives its fine-group starts, pass 2 takes the tiles of every (source, coarse bin) run straight from the
+// receive buffer, then the group kernel as on one GPU.  The owner's two counting passes and the sender's partition pass of round 1 are gone.
+
+template<int W>
+static bool shard_plan_w(sb200_ctx *ctx, uint64_t n_owner_est, uint32_t B, uint32_t G, int K, ShardPlan &pl) {
+    if (ctx->counting_passes || ctx->atomic_partition || 2 * K < 24 || B % G) return false;
+    const uint32_t n_owned = B / G;
+    if (n_owned > SP_MAX_GROUPS) return false;
+    pl.p = choose_prefix_bits<W>(n_owner_est, n_owned, K, ctx->group_chunk ? 0 : 7168);
+    while (pl.p > 0 && ((uint64_t) n_owned << pl.p) > SP_MAX_GROUPS) --pl.p;
+    pl.n_go = (uint32_t) ((uint64_t) n_owned << pl.p);
+    // coarse bins: all owners' bins together are the local bins of a pass-1 tile
+    const uint32_t max_total = std::min<uint32_t>(SP_MAX_BINS, std::max<uint32_t>(SpCfg<W>::CAP / 8, G));
+    pl.s = 0;
+    while (pl.s < pl.p && (uint64_t) (pl.n_go >> pl.s) * G > max_total) ++pl.s;
+    if ((uint64_t) (pl.n_go >> pl.s) * G > SP_MAX_BINS || (1u << pl.s) > (uint32_t) SP_MAX_BINS) return false;
+    pl.n_co = pl.n_go >> pl.s;   // s <= p: n_go = n_owned << p is a multiple of 2^s
+    return pl.n_co >= 1;
+}
+
+bool shard_plan(sb200_ctx *ctx, unsigned W, uint64_t n_owner_est, unsigned B, unsigned G, unsigned K, ShardPlan *pl) {
+    switch (W) {
+        case 1: return shard_plan_w<1>(ctx, n_owner_est, B, G, (int) K, *pl);
+        case 2: return shard_plan_w<2>(ctx, n_owner_est, B, G, (int) K, *pl);
+        case 3: return shard_plan_w<3>(ctx, n_owner_est, B, G, (int) K, *pl);
+        default: return shard_plan_w<4>(ctx, n_owner_est, B, G, (int) K, *pl);
+    }
+}
+
+__global__ void sp_owner_totals_kernel(const uint32_t *__restrict__ cstart, uint32_t n_co, uint32_t G, uint32_t *__restrict__ out /* G + 1 */) {
+    const uint32_t g = threadIdx.x;
+    if (g <= G) out[g] = cstart[(uint64_t) g * n_co];
+}
+
+// after the coarse count: starts, cursors, per-owner totals on the host; counts_keep = the counts themselves (they travel with the records)
+static uint64_t shard_send_tables(sb200_ctx *ctx, uint32_t G, uint32_t n_co, DevBuf<uint32_t> &hist, DevBuf<uint32_t> &counts_keep, DevBuf<uint32_t> &cur1,
+                                  uint64_t *owner_counts) {
+    const uint64_t nb = (uint64_t) G * n_co;
+    counts_keep.alloc(ctx, nb);
+    CUDA_CHECK(cudaMemcpyAsync(counts_keep.p, hist.p, nb * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    exclusive_scan<uint32_t>(ctx, hist.p, nb + 1, nullptr);
+    cur1.alloc(ctx, nb);
+    CUDA_CHECK(cudaMemcpyAsync(cur1.p, hist.p, nb * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DevBuf<uint32_t> tot(ctx, (uint64_t) G + 1);
+    LAUNCH(ctx, sp_owner_totals_kernel, 1, 128, 0, hist.p, n_co, G, tot.p);
+    std::vector<uint32_t> h((size_t) G + 1);
+    ctx->fetch(h.data(), tot.p, ((size_t) G + 1) * 4);
+    for (uint32_t g = 0; g < G; ++g) owner_counts[g] = h[g + 1] - h[g];
+    return h[G];
+}
+
+template<int W>
+static sb200_records *shard_send_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, uint32_t B, uint32_t G, const ShardPlan &pl, uint64_t *owner_counts) {
+    const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * K : 64};
+    const uint32_t n_bins = G * pl.n_co;
+    std::unique_ptr<sb200_records> r(new sb200_records());
+    r->ctx = ctx; r->k = (unsigned) K; r->words = W; r->n = 0; r->double_palindromes = true;
+    DevBuf<uint32_t> hist(ctx, (uint64_t) n_bins + 1), cur1;
+    hist.zero();
+    auto sp_count_reads_kernel_ = sp_count_reads_kernel<W>;
+    auto sp_scatter_reads_kernel_ = sp_scatter_reads_kernel<W>;
+    const size_t smem_c = (size_t) n_bins * 4, smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, false);
+    CUDA_CHECK(cudaFuncSetAttribute(sp_count_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_c, 1024)));
+    CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+    // (the coarse histogram is small: two count CTAs per SM)
+    if (rd->n_reads)
+        LAUNCH(ctx, sp_count_reads_kernel_, (unsigned) ctx->num_sms * 2, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_CANON,
+               gs, pl.s, n_bins, hist.p);
+    const uint64_t n = shard_send_tables(ctx, G, pl.n_co, hist, r->coarse_counts, cur1, owner_counts);
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: use more GPUs");
+    r->n = n;
+    r->data.alloc(ctx, n * W);
+    if (n) {
+        const uint32_t max_nwin = rd->max_len >= (uint32_t) K ? rd->max_len - (uint32_t) K + 1 : 128u;
+        const uint32_t chunk_cap = 32u * std::min<uint32_t>(PART_RUN, (max_nwin + 31u) / 32u);
+        const int rounds = std::max<int>(1, SpCfg<W>::CAP / (int) (SP_WARPS * chunk_cap));
+        LAUNCH(ctx, sp_scatter_reads_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K,
+               (int) PART_CANON, gs, pl.s, n_bins, rounds, cur1.p, r->data.p);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return r.release();
+}
+
+sb200_records *shard_send_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts) {
+    switch ((K + 31) / 32) {
+        case 1: return shard_send_reads_w<1>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        case 2: return shard_send_reads_w<2>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        case 3: return shard_send_reads_w<3>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        default: return shard_send_reads_w<4>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+    }
+}
+
+template<int WS, int W>
+static sb200_records *shard_send_derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B, uint32_t G, const ShardPlan &pl, uint64_t *owner_counts) {
+    const int k = (int) kp->k - 1;
+    const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * k : 64};
+    const uint32_t n_bins = G * pl.n_co;
+    const int used = 2 * (k - 32 * (W - 1));
+    const int pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
+    const bool side_pay = pshift < 0 && !ctx->no_mask_payload;
+    std::unique_ptr<sb200_records> r(new sb200_records());
+    r->ctx = ctx; r->k = (unsigned) k; r->words = W; r->n = 0; r->mask_payload = pshift >= 0;
+    DevBuf<uint32_t> hist(ctx, (uint64_t) n_bins + 1), cur1;
+    hist.zero();
+    auto sp_count_derive_kernel_ = sp_count_derive_kernel<WS, W>;
+    auto sp_scatter_derive_kernel_ = sp_scatter_derive_kernel<WS, W>;
+    const size_t smem_c = (size_t) n_bins * 4, smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, side_pay);
+    CUDA_CHECK(cudaFuncSetAttribute(sp_count_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_c, 1024)));
+    CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+    if (kp->size) LAUNCH(ctx, sp_count_derive_kernel_, (unsigned) ctx->num_sms * 2, SPC_THREADS, smem_c, kp->data.p, kp->size, k, gs, pl.s, n_bins, hist.p);
+    const uint64_t n = shard_send_tables(ctx, G, pl.n_co, hist, r->coarse_counts, cur1, owner_counts);
+    SB200_REQUIRE(n < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: use more GPUs");
+    r->n = n;
+    r->data.alloc(ctx, n * W);
+    if (side_pay) r->pay.alloc(ctx, n + 1);
+    if (n) LAUNCH(ctx, sp_scatter_derive_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, pshift, gs, pl.s, n_bins, cur1.p,
+                  r->data.p, r->pay.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return r.release();
+}
+
+sb200_records *shard_send_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts) {
+    int WS = (int) kp->words, W = (int) ((kp->k - 1 + 31) / 32);
+    if (WS == 1) return shard_send_derive_w<1, 1>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 2 && W == 1) return shard_send_derive_w<2, 1>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 2) return shard_send_derive_w<2, 2>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 3 && W == 2) return shard_send_derive_w<3, 2>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 3) return shard_send_derive_w<3, 3>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 4 && W == 3) return shard_send_derive_w<4, 3>(ctx, kp, B, G, *pl, owner_counts);
+    return shard_send_derive_w<4, 4>(ctx, kp, B, G, *pl, owner_counts);
+}
+
+// Receiver: `got` holds the runs of all sources (run_start: G + 1 record positions), got->coarse_counts the [G x n_co] run sizes that came
+// with them, got->pay the payload bytes if the senders keep them beside the records.  Consumes `got`.
+template<int W>
+static sb200_kmers *shard_receive_w(sb200_ctx *ctx, sb200_records *got, const uint64_t *run_start, uint32_t G, const ShardPlan &pl, uint32_t B,
+                                    uint32_t first_bucket, uint32_t n_owned, bool want_counts) {
+    const uint64_t n = got->n;
+    const int K = (int) got->k;
+    const uint64_t lw_keep = last_word_mask(K);
+    const GroupSel gs{B, first_bucket, pl.p, (W == 1) ? 2 * K : 64};
+    const int pshift = got->mask_payload ? 2 * (K - 32 * (W - 1)) : -1;
+    // fine-group histogram of what arrived
+    DevBuf<uint32_t> hist(ctx, (uint64_t) pl.n_go + 1), cur2(ctx, (uint64_t) pl.n_go + 1);
+    hist.zero();
+    auto sp_count_records_kernel_ = sp_count_records_kernel<W>;
+    const size_t smem_c = (size_t) pl.n_go * 4;
+    CUDA_CHECK(cudaFuncSetAttribute(sp_count_records_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_c, 1024)));
+    LAUNCH(ctx, sp_count_records_kernel_, (unsigned) ctx->num_sms, SPC_THREADS, smem_c, got->data.p, n, gs, lw_keep, pl.n_go, hist.p);
+    exclusive_scan<uint32_t>(ctx, hist.p, (uint64_t) pl.n_go + 1, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(cur2.p, hist.p, ((size_t) pl.n_go + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // segments (source, coarse bin) -> tiles
+    const uint32_t n_seg = G * pl.n_co;
+    DevBuf<uint32_t> seg(ctx, 3 * (uint64_t) n_seg);
+    DevBuf<uint64_t> rs(ctx, (uint64_t) G + 1);
+    CUDA_CHECK(cudaMemcpyAsync(rs.p, run_start, ((size_t) G + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, sp_recv_segments_kernel, G, 32, 0, got->coarse_counts.p, rs.p, G, pl.n_co, pl.s, seg.p, seg.p + n_seg, seg.p + 2 * (uint64_t) n_seg);
+    StagedTiles tl;
+    staged_tiles<W>(ctx, seg.p, seg.p + n_seg, seg.p + 2 * (uint64_t) n_seg, n_seg, n, tl);
+    DevBuf<uint64_t> inst(ctx, n * W);
+    DevBuf<uint8_t> pay;
+    if (got->pay.p) pay.alloc(ctx, n + 1);
+    staged_pass2<W>(ctx, pl.s, tl, cur2.p, gs, lw_keep, got->data.p, got->pay.p, inst.p, pay.p);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // run_start (pageable) has been consumed
+    sb200_kmers *s = finish_grouped<W>(ctx, inst, got->data, n, hist.p, pl.n_go, pl.p, K, B, want_counts, got->double_palindromes, false, pshift, pay.p,
+                                       first_bucket, n_owned);
+    if (!want_counts) s->instances = 0;
+    got->n = 0;
+    return s;
+}
+
+sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
+sb200_kmers *shard_receive(sb200_ctx *ctx, sb200_records *got, const uint64_t *run_start, unsigned G, const ShardPlan *pl, unsigned B, unsigned first_bucket,
+                           unsigned n_owned, int want_counts) {
+    if (got->n == 0) return count_records(ctx, got, B, want_counts, first_bucket, n_owned);   // the empty shard
+    switch (got->words) {
+        case 1: return shard_receive_w<1>(ctx, got, run_start, G, *pl, B, first_bucket, n_owned, want_counts != 0);
+        case 2: return shard_receive_w<2>(ctx, got, run_start, G, *pl, B, first_bucket, n_owned, want_counts != 0);
+        case 3: return shard_receive_w<3>(ctx, got, run_start, G, *pl, B, first_bucket, n_owned, want_counts != 0);
+        default: return shard_receive_w<4>(ctx, got, run_start, G, *pl, B, first_bucket, n_owned, want_counts != 0);
+    }
 }
 
 }  // namespace sb200

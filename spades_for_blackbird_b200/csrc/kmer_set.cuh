@@ -32,6 +32,10 @@ struct sb200_records {   // unsorted k-mer instances / candidates on their way t
     bool marker = false;               // canonical forward-only mode: all-ones records are "filtered out" markers
     bool mask_payload = false;         // derived k-mer candidates: 3 padding bits above the k-mer carry the InOutMask bit (count.cu)
     DevBuf<uint64_t> data;
+    // staged sharded exchange (count.cu shard_send_* / shard_receive): the records are grouped by (owner, coarse bin) and travel with the
+    // sizes of those runs; a k-mer that fills its last word keeps its mask bit in a byte beside the record
+    DevBuf<uint8_t> pay;
+    DevBuf<uint32_t> coarse_counts;    // [n_owners x n_co] on the sender, [n_sources x n_co] on the receiver
 };
 
 struct sb200_mphf {
@@ -82,6 +86,11 @@ struct sb200_unitigs {
 };
 
 namespace sb200 {
+// Grouping plan of the hash-sharded path on the staged kernels (count.cu shard_plan): the same on every rank
+struct ShardPlan {
+    int p = 0, s = 0;              // value-prefix bits of the fine group key; fine groups per coarse bin = 2^s
+    uint32_t n_go = 0, n_co = 0;   // fine groups / coarse bins per owner
+};
 // EarlyTipClipper in three steps (ext.cu): the kill list and the masks span the WHOLE index, the k-mers may be one GPU's shard
 struct TipClipState {
     DevBuf<uint8_t> kill;      // ext->size + 4: k-mers (MPHF index) to isolate

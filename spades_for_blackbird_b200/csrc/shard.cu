@@ -21,6 +21,7 @@
 // Host code is C++ (NCCL C API behind comm.cuh); Python only launches ranks and hands the NCCL id around.
 #include <string.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -38,6 +39,11 @@ sb200_records *extract_records_partitioned(sb200_ctx *ctx, const sb200_reads *rd
 sb200_records *derive_records(sb200_ctx *ctx, const sb200_kmers *kp);
 void partition_records(sb200_ctx *ctx, sb200_records *r, unsigned B, unsigned n_parts, uint64_t *counts_out);
 sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int want_counts, unsigned first_bucket, unsigned n_owned);
+bool shard_plan(sb200_ctx *ctx, unsigned W, uint64_t n_owner_est, unsigned B, unsigned G, unsigned K, ShardPlan *pl);
+sb200_records *shard_send_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
+sb200_records *shard_send_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
+sb200_kmers *shard_receive(sb200_ctx *ctx, sb200_records *got, const uint64_t *run_start, unsigned G, const ShardPlan *pl, unsigned B, unsigned first_bucket,
+                           unsigned n_owned, int want_counts);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
 void mphf_complete(sb200_ctx *ctx, sb200_mphf *m);
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf);
@@ -99,6 +105,42 @@ static sb200_kmers *exchange_and_count(sb200_ctx *ctx, sb200_comm *cm, std::uniq
     return count_records(ctx, got.get(), B, want_counts ? 1 : 0, (unsigned) cm->rank * n_owned, n_owned);
 }
 
+// The same on the staged kernels (count.cu shard_send_* / shard_receive): `rec` is grouped by (owner, coarse bin) and carries the run sizes
+// (and, for k-mers that fill their last word, the mask bits as bytes beside the records); all of it travels, and the owner's pass 2 takes its
+// tiles straight from the receive buffer.
+static sb200_kmers *exchange_and_receive(sb200_ctx *ctx, sb200_comm *cm, std::unique_ptr<sb200_records> rec, const uint64_t *counts, unsigned B,
+                                         const ShardPlan &pl, bool want_counts) {
+    const int G = cm->size;
+    std::vector<uint64_t> all((size_t) G * G);
+    cm->all_gather_host(ctx, counts, (size_t) G, all.data());
+    const uint64_t rb = (uint64_t) rec->words * 8;
+    std::vector<uint64_t> send_off((size_t) G + 1, 0), recv_off((size_t) G + 1, 0), run_start((size_t) G + 1, 0);
+    std::vector<uint64_t> psend((size_t) G + 1, 0), precv((size_t) G + 1, 0), csend((size_t) G + 1, 0), crecv((size_t) G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        const uint64_t out = counts[g], in = all[(size_t) g * G + cm->rank];
+        send_off[(size_t) g + 1] = send_off[(size_t) g] + out * rb;
+        recv_off[(size_t) g + 1] = recv_off[(size_t) g] + in * rb;
+        psend[(size_t) g + 1] = psend[(size_t) g] + out;
+        precv[(size_t) g + 1] = precv[(size_t) g] + in;
+        run_start[(size_t) g + 1] = run_start[(size_t) g] + in;
+        csend[(size_t) g + 1] = csend[(size_t) g] + (uint64_t) pl.n_co * 4;
+        crecv[(size_t) g + 1] = crecv[(size_t) g] + (uint64_t) pl.n_co * 4;
+    }
+    const uint64_t n_recv = run_start[(size_t) G];
+    SB200_REQUIRE(n_recv < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: use more GPUs");
+    std::unique_ptr<sb200_records> got(alloc_records(ctx, n_recv, rec.get()));
+    got->coarse_counts.alloc(ctx, (uint64_t) G * pl.n_co);
+    cm->all_to_all_v(ctx, rec->data.p, send_off.data(), got->data.p, recv_off.data());
+    cm->all_to_all_v(ctx, rec->coarse_counts.p, csend.data(), got->coarse_counts.p, crecv.data());
+    if (rec->pay.p) {
+        got->pay.alloc(ctx, n_recv + 1);
+        cm->all_to_all_v(ctx, rec->pay.p, psend.data(), got->pay.p, precv.data());
+    }
+    rec.reset();
+    const unsigned n_owned = B / (unsigned) G;
+    return shard_receive(ctx, got.get(), run_start.data(), (unsigned) G, &pl, B, (unsigned) cm->rank * n_owned, n_owned, want_counts ? 1 : 0);
+}
+
 static double now_ms() { return sb200_ctx::now_s() * 1e3; }
 
 static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb200_reads *reads, const sb200_construct_params *p, int gather_to) {
@@ -120,18 +162,40 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     };
 
     // ---- 1-2: (k+1)-mers ------------------------------------------------------------------------------------------------------
+    // every rank must take the same grouping plan: it is sized from the job's instance estimate (tiny all-gather)
     {
+        uint64_t mine[2] = {reads->n_bases ? reads->n_bases : reads->n_words * 32, reads->n_reads}, all[2 * 64];
+        cm->all_gather_host(ctx, mine, 2, all);
+        uint64_t bases = 0, nr = 0;
+        for (int g = 0; g < G; ++g) { bases += all[2 * g]; nr += all[2 * g + 1]; }
+        const uint64_t shorter = nr * (uint64_t) k;
+        const uint64_t n_owner_est = std::max<uint64_t>((bases > shorter ? bases - shorter : 1) / (uint64_t) G, 1);
         std::vector<uint64_t> counts((size_t) G, 0);
-        std::unique_ptr<sb200_records> rec(extract_records_partitioned(ctx, reads, k + 1, 1, 1, B, (unsigned) G, counts.data()));
-        res->kpomers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, true);
+        ShardPlan pl;
+        if (shard_plan(ctx, (k + 1 + 31) / 32, n_owner_est, B, (unsigned) G, k + 1, &pl)) {
+            std::unique_ptr<sb200_records> rec(shard_send_reads(ctx, reads, k + 1, B, (unsigned) G, &pl, counts.data()));
+            res->kpomers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, true);
+        } else {
+            std::unique_ptr<sb200_records> rec(extract_records_partitioned(ctx, reads, k + 1, 1, 1, B, (unsigned) G, counts.data()));
+            res->kpomers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, true);
+        }
     }
     lap(0);
     // ---- 3-4: k-mers --------------------------------------------------------------------------------------------------------------
     {
+        uint64_t mine = res->kpomers->size, all[64], total = 0;
+        cm->all_gather_host(ctx, &mine, 1, all);
+        for (int g = 0; g < G; ++g) total += all[g];
         std::vector<uint64_t> counts((size_t) G, 0);
-        std::unique_ptr<sb200_records> rec(derive_records(ctx, res->kpomers));
-        partition_records(ctx, rec.get(), B, (unsigned) G, counts.data());
-        res->kmers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, false);
+        ShardPlan pl;
+        if (shard_plan(ctx, (k + 31) / 32, std::max<uint64_t>(2 * total / (uint64_t) G, 1), B, (unsigned) G, k, &pl)) {
+            std::unique_ptr<sb200_records> rec(shard_send_derive(ctx, res->kpomers, B, (unsigned) G, &pl, counts.data()));
+            res->kmers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, false);
+        } else {
+            std::unique_ptr<sb200_records> rec(derive_records(ctx, res->kpomers));
+            partition_records(ctx, rec.get(), B, (unsigned) G, counts.data());
+            res->kmers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, false);
+        }
     }
     lap(1);
     // ---- 5: global sizes -------------------------------------------------------------------------------------------------------------

@@ -134,13 +134,22 @@ __device__ __forceinline__ void sp_put(const SpStage &st, uint32_t slot, const u
 }
 
 // ---- reads: one warp per chunk of <= 128 windows of a read, every lane rolls through a run of consecutive windows (partition.cuh) ----
-// State of a warp's walk over its reads: read index, first window of the next chunk.
+// State of a warp's walk over its reads: read index, first window of the next chunk, and the length / word offset of the read it is
+// at and of the NEXT read of the warp (loaded one read ahead: a warp meets 650 reads, and three dependent loads per read — length, offset,
+// words — were what the count pass waited on at 32 warps per SM).
 struct SpReadCursor {
     uint64_t rd;
     uint32_t c0;
+    uint32_t len_cur, len_next;
+    uint64_t off_cur, off_next;
+    bool primed;
 };
 
-// Forms the records of the warp's next chunk.  Returns the number of valid records of this LANE (<= PART_RUN); rec / gid hold them.
+__device__ __forceinline__ void sp_cursor_init(SpReadCursor &cur, uint64_t first_read) {
+    cur.rd = first_read; cur.c0 = 0; cur.len_cur = cur.len_next = 0; cur.off_cur = cur.off_next = 0; cur.primed = false;
+}
+
+// Forms the records of the warp's next chunk.  Returns the mask of the valid records of this LANE (<= PART_RUN); rec / gid hold them.
 template<int W>
 __device__ __forceinline__ uint32_t sp_read_chunk(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off, const uint32_t *__restrict__ len,
                                                   uint64_t n_reads, uint64_t warps_total, int K, int mode, const GroupSel &gs, SpReadCursor &cur,
@@ -148,26 +157,32 @@ __device__ __forceinline__ uint32_t sp_read_chunk(const uint64_t *__restrict__ w
     const int lane = threadIdx.x & 31;
     const uint64_t lw_mask = last_word_mask(K);
     uint32_t valid = 0;
+    if (!cur.primed) {
+        cur.primed = true;
+        if (cur.rd < n_reads) { cur.len_cur = __ldg(len + cur.rd); cur.off_cur = __ldg(word_off + cur.rd); }
+        if (cur.rd + warps_total < n_reads) { cur.len_next = __ldg(len + cur.rd + warps_total); cur.off_next = __ldg(word_off + cur.rd + warps_total); }
+    }
     // skip reads that are too short / finished
     while (cur.rd < n_reads) {
-        const uint32_t l = len[cur.rd];
-        if (l >= (uint32_t) K && cur.c0 < l - (uint32_t) K + 1) break;
+        if (cur.len_cur >= (uint32_t) K && cur.c0 < cur.len_cur - (uint32_t) K + 1) break;
         cur.rd += warps_total;
         cur.c0 = 0;
+        cur.len_cur = cur.len_next; cur.off_cur = cur.off_next;
+        if (cur.rd + warps_total < n_reads) { cur.len_next = __ldg(len + cur.rd + warps_total); cur.off_next = __ldg(word_off + cur.rd + warps_total); }
     }
     if (cur.rd >= n_reads) { exhausted = true; return 0; }
-    const uint32_t l = len[cur.rd];
+    const uint32_t l = cur.len_cur;
     const uint32_t nwin = l - (uint32_t) K + 1, nw = (l + 31) >> 5;
-    const uint64_t *seq = words + word_off[cur.rd];
+    const uint64_t *seq = words + cur.off_cur;
     const uint32_t left = nwin - cur.c0;
     const uint32_t run = left >= 32u * PART_RUN ? (uint32_t) PART_RUN : (left + 31u) >> 5;
     const uint32_t p0 = cur.c0 + (uint32_t) lane * run;
     if (p0 < nwin) {
         uint64_t x[W], r[W];
         kmer_window<W>(seq, nw, p0, K, x);
-        kmer_rc<W>(x, K, r);
         uint64_t nxt = 0;
         if (run > 1 && p0 + (uint32_t) K < l) kmer_window<1>(seq, nw, p0 + (uint32_t) K, 32, &nxt);
+        kmer_rc<W>(x, K, r);
 #pragma unroll
         for (int i = 0; i < PART_RUN; ++i) {
             if ((uint32_t) i < run && p0 + (uint32_t) i < nwin) {
@@ -191,13 +206,15 @@ __device__ __forceinline__ uint32_t sp_read_chunk(const uint64_t *__restrict__ w
 template<int W>
 __global__ void __launch_bounds__(SPC_THREADS) sp_count_reads_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
                                                                    const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode, GroupSel gs,
-                                                                   uint32_t n_groups, uint32_t *__restrict__ hist) {
+                                                                   int shift /* counts bins g >> shift: 0 = fine groups */, uint32_t n_groups,
+                                                                   uint32_t *__restrict__ hist) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(sp_smem);
     for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) sh[i] = 0;
     __syncthreads();
     const uint64_t warps_total = (uint64_t) gridDim.x * (SPC_THREADS / 32);
-    SpReadCursor cur{(uint64_t) blockIdx.x * (SPC_THREADS / 32) + (threadIdx.x >> 5), 0u};
+    SpReadCursor cur;
+    sp_cursor_init(cur, (uint64_t) blockIdx.x * (SPC_THREADS / 32) + (threadIdx.x >> 5));
     bool exhausted = false;
     while (!exhausted) {
         uint64_t rec[PART_RUN][W];
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(SPC_THREADS) sp_count_reads_kernel(const uint6
         const uint32_t valid = sp_read_chunk<W>(words, word_off, len, n_reads, warps_total, K, mode, gs, cur, rec, gid, exhausted);
 #pragma unroll
         for (int i = 0; i < PART_RUN; ++i)
-            if ((valid >> i) & 1u) atomicAdd(&sh[gid[i]], 1u);
+            if ((valid >> i) & 1u) atomicAdd(&sh[gid[i] >> shift], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) {
@@ -225,7 +242,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const u
     const SpStage st = sp_carve<W>(sp_smem, SpCfg<W>::CAP, false);
     const int lane = threadIdx.x & 31;
     const uint64_t warps_total = (uint64_t) gridDim.x * SP_WARPS;
-    SpReadCursor cur{(uint64_t) blockIdx.x * SP_WARPS + (threadIdx.x >> 5), 0u};
+    SpReadCursor cur;
+    sp_cursor_init(cur, (uint64_t) blockIdx.x * SP_WARPS + (threadIdx.x >> 5));
     bool exhausted = false;
     while (true) {
         if (threadIdx.x == 0) s_fill = 0;
@@ -260,8 +278,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const u
 
 // ---- k-mer candidates of (k+1)-mers (partition.cuh derive_candidates) -----------------------------------------------------------------
 template<int WS, int W>
-__global__ void __launch_bounds__(SPC_THREADS) sp_count_derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, GroupSel gs, uint32_t n_groups,
-                                                                    uint32_t *__restrict__ hist) {
+__global__ void __launch_bounds__(SPC_THREADS) sp_count_derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, GroupSel gs, int shift,
+                                                                    uint32_t n_groups, uint32_t *__restrict__ hist) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(sp_smem);
     for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) sh[i] = 0;
@@ -271,8 +289,8 @@ __global__ void __launch_bounds__(SPC_THREADS) sp_count_derive_kernel(const uint
         uint32_t bit[2];
         load_rec<WS>(kp, i, x);
         derive_candidates<WS, W>(x, k, a, bit);
-        atomicAdd(&sh[group_of<W>(a[0], gs)], 1u);
-        atomicAdd(&sh[group_of<W>(a[1], gs)], 1u);
+        atomicAdd(&sh[group_of<W>(a[0], gs) >> shift], 1u);
+        atomicAdd(&sh[group_of<W>(a[1], gs) >> shift], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) {
@@ -337,35 +355,73 @@ __device__ __forceinline__ void sp_mbar_wait(uint64_t *bar, uint32_t phase) {
         "}\n" ::"r"(sp_smem_addr(bar)), "r"(phase) : "memory");
 }
 
-// tile_start[c] = first tile of coarse bin c (tiles of CAP2 records), tile_start[n_coarse] = number of tiles
-__global__ void sp_tiles_kernel(const uint32_t *__restrict__ fine_start, int s, uint32_t n_coarse, uint32_t n_groups, uint32_t cap2,
-                                uint32_t *__restrict__ tile_start) {
-    // one CTA: n_coarse <= 1024
-    __shared__ uint32_t sm[1024 / 32 + 1];
-    const uint32_t c = threadIdx.x;
-    uint32_t t = 0;
-    if (c < n_coarse) {
-        const uint32_t lo = fine_start[(uint64_t) c << s];
-        const uint64_t hi_g = ((uint64_t) c + 1) << s;
-        const uint32_t hi = fine_start[hi_g < n_groups ? hi_g : n_groups];
-        t = (hi - lo + cap2 - 1) / cap2;
+// Pass 2 works on SEGMENTS of the pass-1 output: runs of records that share one coarse bin (one GPU: the coarse bins themselves;
+// hash-sharded: the part of a coarse bin that arrived from one source GPU).  A tile = up to CAP2 consecutive records of one segment.
+struct SpTile {
+    uint32_t begin, cnt;   // records [begin, begin + cnt) of the pass-1 output
+    uint32_t gbase;        // first fine group of the segment's coarse bin (= local bin 0 of the tile)
+    uint32_t pad;
+};
+
+// one GPU: segment c = coarse bin c
+__global__ void sp_coarse_segments_kernel(const uint32_t *__restrict__ fine_start, int s, uint32_t n_coarse, uint32_t n_groups,
+                                          uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_cnt, uint32_t *__restrict__ seg_gbase) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_coarse) return;
+    const uint32_t lo = fine_start[(uint64_t) c << s];
+    const uint64_t hi_g = ((uint64_t) c + 1) << s;
+    const uint32_t hi = fine_start[hi_g < n_groups ? hi_g : n_groups];
+    seg_begin[c] = lo; seg_cnt[c] = hi - lo; seg_gbase[c] = c << s;
+}
+
+// hash-sharded receiver: segment (src, c) = the records of coarse bin c that arrived from rank src.  cnt[src * n_co + c] came with the
+// records; run_start[src] = first record of rank src's run in the receive buffer.  One warp per source scans its row.
+__global__ void sp_recv_segments_kernel(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ run_start, uint32_t n_src, uint32_t n_co, int s,
+                                        uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_cnt, uint32_t *__restrict__ seg_gbase) {
+    const uint32_t src = blockIdx.x;
+    const int lane = threadIdx.x;   // 32 threads
+    if (src >= n_src) return;
+    uint32_t run = (uint32_t) run_start[src];
+    for (uint32_t c0 = 0; c0 < n_co; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const uint32_t v = c < n_co ? cnt[(uint64_t) src * n_co + c] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (c < n_co) {
+            const uint64_t i = (uint64_t) src * n_co + c;
+            seg_begin[i] = run + incl - v; seg_cnt[i] = v; seg_gbase[i] = c << s;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan<uint32_t, 1024>(t, &total, sm);
-    if (c < n_coarse) tile_start[c] = ex;
-    if (c == 0) tile_start[n_coarse] = total;
+}
+
+__global__ void sp_seg_tiles_kernel(const uint32_t *__restrict__ seg_cnt, uint32_t n_seg, uint32_t cap2, uint32_t *__restrict__ n_tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_seg) n_tiles[i] = i < n_seg ? (seg_cnt[i] + cap2 - 1) / cap2 : 0u;
+}
+
+__global__ void sp_tile_fill_kernel(const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ seg_cnt, const uint32_t *__restrict__ seg_gbase,
+                                    const uint32_t *__restrict__ tile_off, uint32_t n_seg, uint32_t cap2, SpTile *__restrict__ tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    const uint32_t b = seg_begin[i], c = seg_cnt[i], g = seg_gbase[i];
+    uint32_t t = tile_off[i];
+    for (uint32_t o = 0; o < c; o += cap2, ++t) tiles[t] = SpTile{b + o, (c - o) < cap2 ? (c - o) : cap2, g, 0u};
 }
 
 template<int W>
 __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const uint64_t *__restrict__ mid, const uint8_t *__restrict__ mid_pay,
-                                                                    const uint32_t *__restrict__ fine_start, const uint32_t *__restrict__ tile_start,
-                                                                    GroupSel gs, uint64_t lw_keep, int s, uint32_t n_coarse, uint32_t n_groups,
-                                                                    uint32_t *__restrict__ gcursor, uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay) {
+                                                                       const SpTile *__restrict__ tiles, const uint32_t *__restrict__ n_tiles_dev,
+                                                                       GroupSel gs, uint64_t lw_keep, int s, uint32_t *__restrict__ gcursor,
+                                                                       uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay) {
     extern __shared__ __align__(128) unsigned char sp_smem[];
     __shared__ uint32_t s_scan[SP_THREADS / 32 + 1];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_tile_c[2], s_tile_lo[2], s_tile_n[2];
-    __shared__ uint32_t s_tstart[SP_MAX_BINS + 1], s_cstart[SP_MAX_BINS + 1];   // first tile / first record of every coarse bin
+    __shared__ SpTile s_tile[2];
     constexpr int CAP2 = SpCfg<W>::CAP2;
     const bool with_pay = mid_pay != nullptr;
     // two record buffers (bulk-copy destinations), then ONE set of ordering arrays: a tile is ordered and written out before the next
@@ -380,31 +436,16 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const ui
     st.cursor = st.bstart + SP_MAX_BINS + 1;
     st.gdelta = st.cursor + SP_MAX_BINS;
     const uint32_t n_local = 1u << s;
-    for (uint32_t c = threadIdx.x; c <= n_coarse; c += SP_THREADS) {
-        s_tstart[c] = tile_start[c];
-        const uint64_t g = (uint64_t) c << s;
-        s_cstart[c] = fine_start[g < n_groups ? g : n_groups];
-    }
-    __syncthreads();
-    const uint32_t n_tiles = s_tstart[n_coarse];
+    const uint32_t n_tiles = *n_tiles_dev;
 
-    auto issue = [&](uint32_t t, int b) {   // thread 0: locate tile t (coarse bin by binary search over the tile table) and start its copy into buffer b
-        uint32_t lo = 0, hi = n_coarse;     // last c with s_tstart[c] <= t
-        while (hi - lo > 1) {
-            const uint32_t mid_c = (lo + hi) >> 1;
-            if (s_tstart[mid_c] <= t) lo = mid_c; else hi = mid_c;
-        }
-        const uint32_t c = lo;
-        const uint32_t first = s_cstart[c], last = s_cstart[c + 1];
-        const uint32_t begin = first + (t - s_tstart[c]) * (uint32_t) CAP2;
-        const uint32_t cnt = (last - begin) < (uint32_t) CAP2 ? (last - begin) : (uint32_t) CAP2;
-        s_tile_c[b] = c; s_tile_lo[b] = begin; s_tile_n[b] = cnt;
+    auto issue = [&](const SpTile &d, int b) {   // thread 0: start the copy of a tile into buffer b
+        s_tile[b] = d;
         // bulk copies need 16-byte aligned addresses and sizes: record arrays are 256-byte aligned and W * 8 = 16 or 32 (W = 2, 4) keeps
         // every record boundary aligned; odd W and the payload bytes take plain loads (below)
         if (W % 2 == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
-            sp_mbar_expect(&s_bar[b], cnt * (uint32_t) (W * 8));
-            sp_bulk_g2s(buf[b], mid + (uint64_t) begin * W, cnt * (uint32_t) (W * 8), &s_bar[b]);
+            sp_mbar_expect(&s_bar[b], d.cnt * (uint32_t) (W * 8));
+            sp_bulk_g2s(buf[b], mid + (uint64_t) d.begin * W, d.cnt * (uint32_t) (W * 8), &s_bar[b]);
         }
     };
 
@@ -415,14 +456,21 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const ui
     }
     __syncthreads();
     uint32_t t = blockIdx.x;
-    if (t < n_tiles && threadIdx.x == 0) issue(t, 0);
+    SpTile next{0u, 0u, 0u, 0u};   // thread 0: descriptor of the tile after the one in flight, loaded one iteration ahead
+    if (threadIdx.x == 0 && t < n_tiles) {
+        issue(tiles[t], 0);
+        if (t + gridDim.x < n_tiles) next = tiles[t + gridDim.x];
+    }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     for (; t < n_tiles; t += gridDim.x, b ^= 1) {
-        __syncthreads();   // the previous iteration's flush is done with the ordering arrays; s_tile_*[b] is visible
+        __syncthreads();   // the previous iteration's flush is done with the ordering arrays; s_tile[b] is visible
         const uint32_t tn = t + gridDim.x;
-        if (tn < n_tiles && threadIdx.x == 0) issue(tn, b ^ 1);   // prefetch the next tile while this one is ordered
-        const uint32_t c = s_tile_c[b], begin = s_tile_lo[b], cnt = s_tile_n[b];
+        if (threadIdx.x == 0 && tn < n_tiles) {   // prefetch the next tile while this one is ordered
+            issue(next, b ^ 1);
+            if (tn + gridDim.x < n_tiles) next = tiles[tn + gridDim.x];
+        }
+        const uint32_t begin = s_tile[b].begin, cnt = s_tile[b].cnt, gbase = s_tile[b].gbase;
         st.rec = reinterpret_cast<uint64_t *>(buf[b]);
         st.pay = with_pay ? paybuf[b] : nullptr;
         if (W % 2 == 0) {
@@ -434,7 +482,6 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const ui
         if (with_pay)
             for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) st.pay[q] = mid_pay[begin + q];
         if (W % 2 != 0) __syncthreads();
-        const uint32_t gbase = c << s;
         for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) {
             uint64_t r[W];
 #pragma unroll
@@ -444,6 +491,27 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const ui
         }
         __syncthreads();
         sp_flush<W>(st, cnt, n_local, gcursor, gbase, out, out_pay, s_scan);
+    }
+}
+
+// count of the fine groups of records that already exist (the receiving side of the hash-sharded path): shared-memory histogram
+template<int W>
+__global__ void __launch_bounds__(SPC_THREADS) sp_count_records_kernel(const uint64_t *__restrict__ recs, uint64_t n, GroupSel gs, uint64_t lw_keep,
+                                                                      uint32_t n_groups, uint32_t *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(sp_smem);
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t) blockIdx.x * SPC_THREADS + threadIdx.x; i < n; i += (uint64_t) gridDim.x * SPC_THREADS) {
+        uint64_t r[W];
+        load_rec<W>(recs, i, r);
+        r[W - 1] &= lw_keep;
+        atomicAdd(&sh[group_of<W>(r, gs)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_groups; i += SPC_THREADS) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 

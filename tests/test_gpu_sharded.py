@@ -125,18 +125,20 @@ def test_sharded_no_kmers_fails_on_every_rank():
         run_sharded(2, ["ACGT", "GGCA"], 21, 4)
 
 
-@pytest.mark.parametrize("env", ["SB200_NO_FUSED_PARTITION", "SB200_NO_PLACE", "SB200_NO_MASK_PAYLOAD"])
+@pytest.mark.parametrize("env", ["SB200_COUNTING_PASSES", "SB200_COUNTING_PASSES,SB200_NO_FUSED_PARTITION", "SB200_NO_PLACE", "SB200_NO_MASK_PAYLOAD"])
 def test_sharded_alternative_paths_agree(monkeypatch, env):
-    """The sharded path with one of its shortcuts switched off — extraction straight into the owner groups (then: extract, partition
-    pass), k-mer indices from the build's placement record and one-read ranks (then: lookups, rank samples), masks through the k-mer
-    sort + all-gather of slices (then: lookups + all-reduce) — gives the same shards, masks and unitigs."""
+    """The sharded path with one of its shortcuts switched off — the staged sender / receiver kernels (then: round 1's extraction straight
+    into the owner groups + the owner's counting passes; with NO_FUSED_PARTITION: extract, partition pass), k-mer indices from the build's
+    placement record and one-read ranks (then: lookups, rank samples), masks through the k-mer sort + all-gather of slices (then: lookups
+    + all-reduce) — gives the same shards, masks and unitigs."""
     k, nb, G = 33, 40, 4
     genome = synth.random_genome(12000, 321)
     reads = synth.codes_to_strings(synth.sample_pairs(genome, 900, 120, 300, 0.005, 322))
     w = O.gbuilder(reads, k, nb)
     want = dict(kpomers=w["kpomers"].data.reshape(-1), coverage=w["kpomers"].counts, kmers=w["kmers"].data.reshape(-1), idx=w["idx"],
                 masks_idx=w["masks_idx"], index_bin=w["index_bin"], unitigs=w["unitigs"])
-    monkeypatch.setenv(env, "1")
+    for e in env.split(","):
+        monkeypatch.setenv(e, "1")
     res = run_sharded(G, reads, k, nb)
     check(res, want, G, nb)
 
