@@ -71,6 +71,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->no_fused_partition = getenv("SB200_NO_FUSED_PARTITION") != nullptr;
         ctx->atomic_partition = getenv("SB200_ATOMIC_PARTITION") != nullptr;
         ctx->counting_passes = getenv("SB200_COUNTING_PASSES") != nullptr;
+        ctx->mphf_state_per_key = getenv("SB200_MPHF_STATE_PER_KEY") != nullptr;
         ctx->group_chunk = getenv("SB200_GROUP_KERNEL") && !strcmp(getenv("SB200_GROUP_KERNEL"), "chunk");
         ctx->trace_t0 = sb200_ctx::now_s();
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -426,7 +426,7 @@ static void staged_tiles(sb200_ctx *ctx, const uint32_t *seg_begin, const uint32
     t.tiles.alloc(ctx, n / CAP2 + n_seg + 1);   // ceil(c_i / CAP2) summed over the segments is at most n / CAP2 + n_seg
     LAUNCH(ctx, sp_seg_tiles_kernel, div_up((uint64_t) n_seg + 1, 256), 256, 0, seg_cnt, n_seg, CAP2, t.tile_off.p);
     exclusive_scan<uint32_t>(ctx, t.tile_off.p, (uint64_t) n_seg + 1, nullptr);
-    LAUNCH(ctx, sp_tile_fill_kernel, div_up(n_seg, 256), 256, 0, seg_begin, seg_cnt, seg_gbase, t.tile_off.p, n_seg, CAP2, t.tiles.p);
+    LAUNCH(ctx, sp_tile_fill_kernel, div_up(n / CAP2 + n_seg + 1, 256), 256, 0, seg_begin, seg_cnt, seg_gbase, t.tile_off.p, n_seg, CAP2, t.tiles.p);
 }
 
 // After the count pass: group starts, cursors of both passes, tiles of pass 2.  hist (n_groups + 1 counts) becomes the fine starts.

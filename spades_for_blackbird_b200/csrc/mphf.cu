@@ -49,7 +49,77 @@ __global__ void __launch_bounds__(256) mphf_level0_kernel(const uint64_t *__rest
     unsigned long long bit = 1ULL << (pos & 63);
     unsigned long long old = atomicOr(&bits[w], bit);
     if (old & bit) atomicOr(&coll[w], bit);
-    active[i] = a;
+    if (active) active[i] = a;   // nullptr: level 1 starts from the keys again (mphf_level1_kernel) instead of from a 24-byte state per key
+}
+
+// level 1 straight from the keys: the state of a key after level 0 is a function of the key, so instead of writing 24 bytes per key in
+// level 0 and reading them back here (3.5 GB for 73 M keys), level 1 reads the 16-byte keys again and recomputes bucket + XXH3_128; only
+// the survivors (22 %) get a state record.  Placement test, level-1 insertion and the block-aggregated append are those of
+// mphf_level_kernel below.
+constexpr int MPHF_L1_ITEMS = 4;
+template<int W>
+__global__ void __launch_bounds__(256) mphf_level1_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t B, ActiveKey *__restrict__ out,
+                                                         uint32_t *__restrict__ n_out, const uint64_t *__restrict__ domain,
+                                                         const uint64_t *__restrict__ word_off, unsigned long long *__restrict__ bits,
+                                                         unsigned long long *__restrict__ coll, uint32_t *__restrict__ place /* or nullptr */) {
+    constexpr int ITEMS = MPHF_L1_ITEMS;
+    __shared__ uint32_t s_wcnt[8];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t) blockDim.x * ITEMS;
+    for (uint64_t base = (uint64_t) blockIdx.x * tile; base < n; base += (uint64_t) gridDim.x * tile) {
+        ActiveKey a[ITEMS];
+        bool keep[ITEMS];
+        uint32_t before[ITEMS];
+        uint32_t wtotal = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint64_t i = base + (uint64_t) j * blockDim.x + threadIdx.x;
+            keep[j] = false;
+            if (i < n) {
+                uint64_t r[W];
+                load_rec<W>(keys, i, r);
+                a[j].bucket = kmer_bucket<W>(r, B);
+                a[j].pad = (uint32_t) i;
+                xxh3_128<W>(r, a[j].s0, a[j].s1);
+                const uint64_t t = (uint64_t) a[j].bucket * MPHF_LEVELS;
+                const uint64_t pos = __umul64hi(a[j].s0, domain[t]);
+                const uint64_t w = word_off[t] + (pos >> 6);
+                const unsigned long long bit = 1ULL << (pos & 63);
+                const bool placed = (bits[w] & bit) && !(coll[w] & bit);
+                keep[j] = !placed;
+                if (placed && place) place[i] = (uint32_t) ((w << 6) | (pos & 63));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t m = __ballot_sync(0xffffffffu, keep[j]);
+            before[j] = wtotal + (uint32_t) __popc(m & ((1u << lane) - 1u));
+            wtotal += (uint32_t) __popc(m);
+        }
+        if (lane == 0) s_wcnt[warp] = wtotal;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(n_out, tot) : 0u;
+        }
+        __syncthreads();
+        const uint32_t wbase = s_base + s_wcnt[warp];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (!keep[j]) continue;
+            const uint64_t t = (uint64_t) a[j].bucket * MPHF_LEVELS + 1;
+            const uint64_t pos = __umul64hi(a[j].s1, domain[t]);
+            const uint64_t w = word_off[t] + (pos >> 6);
+            const unsigned long long bit = 1ULL << (pos & 63);
+            const unsigned long long old = atomicOr(&bits[w], bit);
+            if (old & bit) atomicOr(&coll[w], bit);
+            out[wbase + before[j]] = a[j];
+        }
+        __syncthreads();
+    }
 }
 
 // level l >= 1: keep the keys that were not placed at level l-1, insert them into level l (if l is a bit level).
@@ -229,15 +299,36 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     // (a shard records them too: the bit positions are global, and sb200_mphf_complete builds pc_scan once the index is whole)
     const bool keep_place = (words + 1) * 64 < (1ull << 32) && n > 0;
     if (keep_place) m->place.alloc(ctx, n);
-    DevBuf<ActiveKey> act_a(ctx, n), act_b(ctx, n);
-    DevBuf<uint32_t> counters(ctx, MPHF_LEVELS + 1); counters.zero();
+    // state records exist from level 1 on, for the keys level 0 did not place (~22 % of the keys at gamma = 4); the lists are sized for
+    // all keys (address space of the caching allocator, never touched beyond the survivors)
+    const uint64_t cap_a = n;
     uint32_t n32 = (uint32_t) n;
-    CUDA_CHECK(cudaMemcpyAsync(counters.p, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (n) LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
-                  (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
-    ActiveKey *src = act_a.p, *dst = act_b.p;
+    DevBuf<uint32_t> counters(ctx, MPHF_LEVELS + 1);
+    DevBuf<ActiveKey> act_a, act_b;
+    ActiveKey *src = nullptr, *dst = nullptr;
     unsigned grid = (unsigned) std::min<uint64_t>(div_up(n, 256 * MPHF_LEVEL_ITEMS), (uint64_t) ctx->num_sms * 16);
-    for (int l = 1; l < MPHF_LEVELS && n; ++l) {   // (a rank that owns no k-mer at all only contributes zeroed arrays)
+    int first_level = 1;
+    if (n && !ctx->mphf_state_per_key) {
+        act_a.alloc(ctx, cap_a); act_b.alloc(ctx, cap_a);
+        counters.zero();
+        LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, (ActiveKey *) nullptr);
+        auto mphf_level1_kernel_ = mphf_level1_kernel<W>;
+        LAUNCH(ctx, mphf_level1_kernel_, grid, 256, 0, ks->data.p, n, B, act_a.p, counters.p + 1, m->domain.p, m->word_off.p,
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
+        src = act_a.p; dst = act_b.p;
+        first_level = 2;
+    }
+    if (n && ctx->mphf_state_per_key) {
+        act_a.alloc(ctx, n); act_b.alloc(ctx, n);
+        counters.zero();
+        CUDA_CHECK(cudaMemcpyAsync(counters.p, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
+        src = act_a.p; dst = act_b.p;
+    }
+    if (!n) counters.zero();
+    for (int l = first_level; l < MPHF_LEVELS && n; ++l) {   // (a rank that owns no k-mer at all only contributes zeroed arrays)
         LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
                (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
         std::swap(src, dst);

@@ -68,15 +68,17 @@ __device__ __forceinline__ SpStage sp_carve(unsigned char *raw, int cap, bool wi
     return s;
 }
 
+// Before a tile is filled: clears the bin counts (all threads; a barrier must follow before the first sp_put)
+__device__ __forceinline__ void sp_stage_reset(const SpStage &st, uint32_t n_bins) {
+    for (uint32_t b = threadIdx.x; b <= n_bins; b += SP_THREADS) st.bstart[b] = 0;
+}
+
 // Orders the n staged records by local bin and writes every bin's run to out[] at a position claimed from gcursor[first_bin + bin].
-// All threads of the CTA call it; the stage may be refilled when it returns.
+// All threads of the CTA call it after a barrier that follows the last sp_put; the stage may be reset and refilled when it returns.
 template<int W>
 __device__ __forceinline__ void sp_flush(const SpStage &st, uint32_t n, uint32_t n_bins, uint32_t *__restrict__ gcursor, uint32_t first_bin,
                                          uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay, uint32_t *s_scan) {
-    for (uint32_t b = threadIdx.x; b <= n_bins; b += SP_THREADS) st.bstart[b] = 0;
-    __syncthreads();
-    for (uint32_t q = threadIdx.x; q < n; q += SP_THREADS) atomicAdd(&st.bstart[st.bin[q]], 1u);
-    __syncthreads();
+    // (the bin counts were accumulated in st.bstart while the tile was filled: sp_put / sp_stage_reset)
     {   // exclusive scan of up to 1024 bin counts: two per thread
         const uint32_t b0 = 2u * threadIdx.x, b1 = b0 + 1u;
         const uint32_t c0 = b0 < n_bins ? st.bstart[b0] : 0u, c1 = b1 < n_bins ? st.bstart[b1] : 0u;
@@ -131,6 +133,7 @@ __device__ __forceinline__ void sp_put(const SpStage &st, uint32_t slot, const u
         for (int j = 0; j < W; ++j) st.rec[(size_t) slot * W + j] = r[j];
     }
     st.bin[slot] = (uint16_t) bin;
+    atomicAdd(&st.bstart[bin], 1u);   // the tile's bin histogram grows with the tile
 }
 
 // ---- reads: one warp per chunk of <= 128 windows of a read, every lane rolls through a run of consecutive windows (partition.cuh) ----
@@ -168,8 +171,13 @@ __device__ __forceinline__ uint32_t sp_read_chunk(const uint64_t *__restrict__ w
         cur.rd += warps_total;
         cur.c0 = 0;
         cur.len_cur = cur.len_next; cur.off_cur = cur.off_next;
-        if (cur.rd + warps_total < n_reads) { cur.len_next = __ldg(len + cur.rd + warps_total); cur.off_next = __ldg(word_off + cur.rd + warps_total); }
+        if (cur.rd + warps_total < n_reads) {
+            cur.len_next = __ldg(len + cur.rd + warps_total); cur.off_next = __ldg(word_off + cur.rd + warps_total);
+        }
     }
+    // the words of the read AFTER this one are on their way while this one is processed (its offset arrived one read ago)
+    if (cur.c0 == 0 && cur.rd + warps_total < n_reads && lane < 2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(words + cur.off_next + (uint64_t) lane * 16));
     if (cur.rd >= n_reads) { exhausted = true; return 0; }
     const uint32_t l = cur.len_cur;
     const uint32_t nwin = l - (uint32_t) K + 1, nw = (l + 31) >> 5;
@@ -247,6 +255,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const u
     bool exhausted = false;
     while (true) {
         if (threadIdx.x == 0) s_fill = 0;
+        sp_stage_reset(st, n_coarse);
         __syncthreads();
         for (int round = 0; round < rounds; ++round) {
             if (exhausted) continue;
@@ -310,6 +319,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_derive_kernel(const 
     const SpStage st = sp_carve<W>(sp_smem, CAP, out_pay != nullptr);
     for (uint64_t t0 = (uint64_t) blockIdx.x * SRC_PER_TILE; t0 < n; t0 += (uint64_t) gridDim.x * SRC_PER_TILE) {
         const uint32_t cnt = (uint32_t) ((n - t0) < SRC_PER_TILE ? (n - t0) : SRC_PER_TILE);
+        sp_stage_reset(st, n_coarse);
+        __syncthreads();
         for (uint32_t j = threadIdx.x; j < cnt; j += SP_THREADS) {
             uint64_t x[WS], a[2][W];
             uint32_t bit[2];
@@ -404,13 +415,18 @@ __global__ void sp_seg_tiles_kernel(const uint32_t *__restrict__ seg_cnt, uint32
     if (i <= n_seg) n_tiles[i] = i < n_seg ? (seg_cnt[i] + cap2 - 1) / cap2 : 0u;
 }
 
+// one thread per TILE: its segment by binary search over the scanned tile counts
 __global__ void sp_tile_fill_kernel(const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ seg_cnt, const uint32_t *__restrict__ seg_gbase,
                                     const uint32_t *__restrict__ tile_off, uint32_t n_seg, uint32_t cap2, SpTile *__restrict__ tiles) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_seg) return;
-    const uint32_t b = seg_begin[i], c = seg_cnt[i], g = seg_gbase[i];
-    uint32_t t = tile_off[i];
-    for (uint32_t o = 0; o < c; o += cap2, ++t) tiles[t] = SpTile{b + o, (c - o) < cap2 ? (c - o) : cap2, g, 0u};
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tile_off[n_seg]) return;
+    uint32_t lo = 0, hi = n_seg;   // last segment with tile_off[seg] <= t (segments without tiles share their successor's offset)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tile_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t o = (t - tile_off[lo]) * cap2, c = seg_cnt[lo];
+    tiles[t] = SpTile{seg_begin[lo] + o, (c - o) < cap2 ? (c - o) : cap2, seg_gbase[lo], 0u};
 }
 
 template<int W>
@@ -481,13 +497,16 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_fine_kernel(const ui
         }
         if (with_pay)
             for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) st.pay[q] = mid_pay[begin + q];
-        if (W % 2 != 0) __syncthreads();
+        sp_stage_reset(st, n_local);
+        __syncthreads();
         for (uint32_t q = threadIdx.x; q < cnt; q += SP_THREADS) {
             uint64_t r[W];
 #pragma unroll
             for (int j = 0; j < W; ++j) r[j] = st.rec[(size_t) q * W + j];
             r[W - 1] &= lw_keep;   // the group key ignores a mask-bit payload in the padding
-            st.bin[q] = (uint16_t) (group_of<W>(r, gs) - gbase);
+            const uint32_t bin = group_of<W>(r, gs) - gbase;
+            st.bin[q] = (uint16_t) bin;
+            atomicAdd(&st.bstart[bin], 1u);
         }
         __syncthreads();
         sp_flush<W>(st, cnt, n_local, gcursor, gbase, out, out_pay, s_scan);

@@ -408,6 +408,7 @@ def test_baseline_config2_full_size(monkeypatch):
     monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
     monkeypatch.setenv("SB200_NO_PLACE", "1")            # and k-mer indices by MPHF lookups instead of the build's placement record
     monkeypatch.setenv("SB200_COUNTING_PASSES", "1")     # and extract / derive + counting passes instead of the staged producer-fused partition
+    monkeypatch.setenv("SB200_MPHF_STATE_PER_KEY", "1")  # and a state record per key out of MPHF level 0 instead of level 1 re-reading the keys
     ctx2 = B.Context(0)
     try:
         streams, index, kp, (w, off, ln) = run(ctx2)
