@@ -33,6 +33,12 @@ namespace sb200 {
 #ifndef GH_UMAX
 #define GH_UMAX 4096
 #endif
+// GH_INLINE_PHASES (tools/gh_test.cu only): the two phases inlined into the kernel body, the variant that was miscompiled (see above)
+#ifdef GH_INLINE_PHASES
+#define GH_PHASE __forceinline__
+#else
+#define GH_PHASE __noinline__
+#endif
 #ifndef GH_THREADS
 #define GH_THREADS 512
 #endif
@@ -134,7 +140,7 @@ __device__ __forceinline__ GhSmem<IdxT> gh_views(unsigned char *raw) {
 // Phase 1+2: stream the records of the group whose tag falls into the round's range through the hash table, then compact the occupied
 // slots to the list (lq, lc).  Returns the number of distinct records, or ~0u when the table got crowded (more than UMAX distinct).
 template<int W, int MODE, typename IdxT, bool SEG>
-__device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const GhAddr<SEG> ga, uint32_t gcnt, int shift2,
+__device__ GH_PHASE uint32_t gh_dedup(unsigned char *raw, const GhAddr<SEG> ga, uint32_t gcnt, int shift2,
                                           uint64_t lw_keep, int pshift, int lgR, uint32_t round, uint32_t *s_U, uint32_t *s_overflow) {
     const uint64_t *__restrict__ g = ga.recs;
     const uint8_t *__restrict__ gpay = ga.pay;
@@ -233,7 +239,7 @@ __device__ __noinline__ uint32_t gh_dedup(unsigned char *raw, const GhAddr<SEG> 
 
 // Phase 3+4: order the U distinct records (bins over the tag, rank inside the bin) and write them (+ counts) to out[obase ...).
 template<int W, int MODE, typename IdxT, bool SEG>
-__device__ __noinline__ void gh_emit(unsigned char *raw, const GhAddr<SEG> ga, uint32_t U, int shift2, uint64_t lw_keep, int lgR,
+__device__ GH_PHASE void gh_emit(unsigned char *raw, const GhAddr<SEG> ga, uint32_t U, int shift2, uint64_t lw_keep, int lgR,
                                      uint64_t *__restrict__ out, uint32_t *__restrict__ out_cnt, unsigned long long obase, uint32_t *s_wtot) {
     const uint64_t *__restrict__ g = ga.recs;
     constexpr int THREADS = HashCfg::THREADS, BINS = HashCfg::BINS;

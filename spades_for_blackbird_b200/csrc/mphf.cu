@@ -480,16 +480,19 @@ uint64_t mphf_seq_idx_host(sb200_mphf *m, const uint64_t *rec) {
 // KMerIndex::serialize (kmer_index.hpp:99-105) of per-bucket mphf::save (BooPHF.h:514-532) of bitVector::save (:316-323)
 uint64_t mphf_serialize_host(const sb200_mphf *m, const uint64_t *bits_host, const uint64_t *ranks_host, uint8_t *out);
 
+void mphf_serialize_device(sb200_ctx *ctx, const sb200_mphf *m, uint8_t *out_dev);
+
+// The byte stream is assembled on the device (every bit-vector and rank array copied to its place) and comes home as ONE copy straight
+// into the caller's buffer (pinned or not); the host then fills in the few small fields between the arrays.
 uint64_t mphf_serialize(const sb200_mphf *m, uint8_t *out) {
     sb200_ctx *ctx = m->ctx;
-    std::vector<uint64_t> bits, ranks;
-    if (out) {
-        bits.resize(m->total_words + 1); ranks.resize(m->total_ranks + 1);
-        CUDA_CHECK(cudaMemcpyAsync(bits.data(), m->bits.p, m->total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(ranks.data(), m->ranks.p, m->total_ranks * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    }
-    return mphf_serialize_host(m, bits.data(), ranks.data(), out);
+    const uint64_t size = mphf_serialize_host(m, nullptr, nullptr, nullptr);
+    if (!out) return size;
+    DevBuf<uint8_t> dev(ctx, size + 8);
+    mphf_serialize_device(ctx, m, dev.p);
+    CUDA_CHECK(cudaMemcpyAsync(out, dev.p, size, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return mphf_serialize_host(m, nullptr, nullptr, out);   // small fields only; the bulk areas are skipped over
 }
 
 // bits_host / ranks_host: host copies of the device arrays.  out == nullptr: size query.  out != nullptr with bits_host ==

@@ -1,5 +1,6 @@
 // Standalone harness for group_hash_kernel (grouphash.cuh): random groups vs a CPU sort/unique.  Debug tool, not part of the library.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I spades_for_blackbird_b200/csrc -I include tools/gh_test.cu -o variants/gh_test
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -I spades_for_blackbird_b200/csrc -I include tools/gh_test.cu -o tools/gh_test
+//   (profiles/r2_racecheck_gh_test.log: compute-sanitizer --tool racecheck on this harness)
 #include "grouphash.cuh"
 #include <algorithm>
 #include <cstdio>
@@ -39,13 +40,13 @@ int main(int argc, char **argv) {
     cudaMalloc(&d_gu, (G + 1) * 4); cudaMalloc(&d_ctrl, 16); cudaMalloc(&d_cnt, n * 4);
     cudaMemcpy(d_recs, recs.data(), n * W * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(d_ranges, ranges.data(), G * sizeof(ChunkRange), cudaMemcpyHostToDevice);
-    auto kern = group_hash_kernel<W, 1, uint16_t>;
+    auto kern = group_hash_kernel<W, 1, uint16_t, false>;
     size_t smem = group_hash_smem<uint16_t>();
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int total_bad = 0;
     for (int rep = 0; rep < reps; ++rep) {
         cudaMemset(d_out, 0xEE, n * W * 8); cudaMemset(d_cnt, 0, n * 4); cudaMemset(d_ctrl, 0, 16);
-        kern<<<G, HashCfg::THREADS, smem>>>(d_recs, d_ranges, d_gu, d_ctrl, d_out, d_cnt, 64, ~0ULL, 0);
+        kern<<<G, HashCfg::THREADS, smem>>>(d_recs, d_ranges, d_gu, d_ctrl, d_out, d_cnt, 64, ~0ULL, 0, (const uint8_t *) nullptr, GroupParts{nullptr, nullptr, 1u, (uint32_t) G});
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("rep %d: CUDA error %s\n", rep, cudaGetErrorString(e)); return 1; }
         std::vector<uint64_t> out(n * W); std::vector<uint32_t> gu(G), cnt(n), ctrl(4);
