@@ -94,7 +94,8 @@ def main():
         for b, v in per.items():
             traffic[b] = sum(v) / len(v)
     # keys as sb200_profile_report() prints them (the LAUNCH macro's kernel expression)
-    names = {"seg_chunk_kernel": "seg_chunk_kernel_", "group_chunk_kernel": "seg_chunk_kernel_", "group_hash_kernel": "seg_chunk_kernel_", "links_kernel": "links_kernel<W>", "index_from_place_kernel": "index_from_place_kernel",
+    names = {"seg_chunk_kernel": "seg_chunk_kernel_", "group_chunk_kernel": "seg_chunk_kernel_", "group_hash_kernel": "group_hash_kernel_", "sp_scatter_fine_kernel": "sp_scatter_fine_kernel_", "sp_scatter_reads_kernel": "sp_scatter_reads_kernel_", "sp_count_reads_kernel": "sp_count_reads_kernel_", "sp_scatter_derive_kernel": "sp_scatter_derive_kernel_", "sp_count_derive_kernel": "sp_count_derive_kernel_", "mphf_level1_kernel": "mphf_level1_kernel_",
+             "links_kernel": "links_kernel<W>", "index_from_place_kernel": "index_from_place_kernel",
              "walk_measure_links_kernel": "walk_measure_links_kernel<W>", "walk_emit_links_kernel": "walk_emit_links_kernel<W>", "rs_scatter_kernel": "rs_scatter_kernel<W>", "rs_hist_kernel": "rs_hist_kernel<W>",
              "walk_measure_kernel": "walk_measure_kernel<W>", "walk_emit_kernel": "walk_emit_kernel<W>", "fill_masks_kernel": "fill_masks_kernel_",
              "extract_reads_kernel": "extract_reads_kernel<W>", "derive_kernel": "derive_kernel_", "index_of_kmers_kernel": "index_of_kmers_kernel<W>",
