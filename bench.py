@@ -589,6 +589,15 @@ def main():
         add("group_hash_kernel_", n_inst * W1 + n_kp * (W1 + 4) + 2 * n_kp * W0 + n_km * (W0 + 1))
         add("group_chunk_kernel_", n_inst * W1 + n_kp * (W1 + 4) + 2 * n_kp * W0 + n_km * (W0 + 1))
         add("derive_kernel_", n_kp * W1 + 2 * n_kp * W0)
+        # staged producer-fused grouping (csrc/staged_partition.cuh): the reads are produced twice (count, pass 1), the instances cross
+        # HBM in pass 1 (write) and pass 2 (read + write)
+        add("sp_count_reads_kernel_", total_bases / 4)
+        add("sp_scatter_reads_kernel_", total_bases / 4 + n_inst * W1)
+        add("sp_scatter_fine_kernel_", 2 * (n_inst * W1 + 2 * n_kp * W0))
+        add("sp_count_derive_kernel_", n_kp * W1)
+        add("sp_scatter_derive_kernel_", n_kp * W1 + 2 * n_kp * W0)
+        add("mphf_level1_kernel_", n_km * W0 + 0.22 * n_km * 24)      # keys in; a state record for the keys level 0 did not place
+        add("walk_emit_captured_kernel<W>", 2 * n_words_out)          # captured nucleotides in, packed unitigs out
         add("fill_masks_kernel_", n_kp * W1 + n_km)
         add("index_of_kmers_kernel<W>", n_km * (W0 + 8 + 2))
         add("index_from_place_kernel", n_km * (4 + 8 + 2))            # placement in; idx, inv, mask byte (read + write) out

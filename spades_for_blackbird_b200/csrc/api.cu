@@ -65,7 +65,9 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->num_sms = prop.multiProcessorCount;
         ctx->trace = getenv("SB200_TRACE") != nullptr;
         ctx->force_jump_path = getenv("SB200_FORCE_JUMP") != nullptr;
-        ctx->no_links = getenv("SB200_NO_LINKS") != nullptr;
+        ctx->links = getenv("SB200_LINKS") != nullptr;
+        ctx->no_walk_blocks = getenv("SB200_NO_WALK_BLOCKS") != nullptr;
+        if (const char *v = getenv("SB200_WALK_CAPTURE_WORDS")) ctx->walk_capture_words = (size_t) atoi(v);
         ctx->no_mask_payload = getenv("SB200_NO_MASK_PAYLOAD") != nullptr;
         ctx->no_place = getenv("SB200_NO_PLACE") != nullptr;
         ctx->no_fused_partition = getenv("SB200_NO_FUSED_PARTITION") != nullptr;

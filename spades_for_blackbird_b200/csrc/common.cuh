@@ -75,7 +75,10 @@ struct sb200_ctx {
     bool no_place = false;          // SB200_NO_PLACE=1: k-mer indices by MPHF lookups even when the build recorded the placements (cross-check)
     bool no_mask_payload = false;   // SB200_NO_MASK_PAYLOAD=1: masks by MPHF lookups (fill_masks_kernel) even when the k-mer sort could carry them
     bool mphf_state_per_key = false;  // SB200_MPHF_STATE_PER_KEY=1: level 0 writes a 24-byte state per key for level 1 (round 1) instead of level 1 re-reading the keys (cross-check)
-    bool no_links = false;          // SB200_NO_LINKS=1: direct walks by MPHF lookup even when the link table applies (tests cover both)
+    bool no_walk_blocks = false;    // SB200_NO_WALK_BLOCKS=1: lookup walks read bit-vector, rank and mask separately (cross-check)
+    size_t walk_capture_words = 0;  // SB200_WALK_CAPTURE_WORDS=n: cap of the measuring walks' capture buffer per start edge (tests: force the re-walk)
+    bool links = false;             // SB200_LINKS=1: direct walks by pointer chasing over a link table (one lookup per vertex up front) instead of a lookup
+                                    // through the walk blocks per step — the round-1 scheme, slower since the blocks exist (tests cover both)
     bool force_jump_path = false;   // SB200_FORCE_JUMP=1: always extract unitigs by pointer jumping (tests cover both paths)
     static double now_s() {
         timespec ts;

@@ -403,6 +403,7 @@ MphfDev mphf_dev(const sb200_mphf *m) {
     d.domain = m->domain.p; d.word_off = m->word_off.p; d.rank_off = m->rank_off.p; d.segment_starts = m->segment_starts.p;
     d.bits = m->bits.p; d.ranks = m->ranks.p; d.num_buckets = m->num_buckets;
     d.pc_scan = (m->pc_scan.p && !m->ctx->no_place) ? m->pc_scan.p : nullptr;
+    d.wblk = nullptr;
     return d;
 }
 

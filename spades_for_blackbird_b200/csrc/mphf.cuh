@@ -15,8 +15,19 @@ struct MphfDev {
     const uint64_t *bits;
     const uint64_t *ranks;
     const uint32_t *pc_scan;         // set bits before every word of `bits` (whole-table builds on one GPU), or nullptr
+    const uint64_t *wblk;            // walk blocks (below), or nullptr
     uint32_t num_buckets;
 };
+
+// Walk blocks: what a walk step needs from the index AND the extension masks in ONE 128-byte line — the unit DRAM serves a random
+// access in anyway.  Line b holds words 3b..3b+2 of the index's bit string (bytes 0-23), the number of set bits before them
+// (bytes 24-27; bit 31: the line places more than WB_MASKS keys, their masks stay in the mask array) and the mask bytes of the keys
+// those 192 bits place, in bit order (bytes 28-127) — MPHF indices follow the bit order, so they are a contiguous run of the mask array.
+// A step of a lookup walk then costs one DRAM access instead of three (bit-vector word, rank, mask byte): what bounds the walks of a
+// shard, whose index (all GPUs' buckets) is far larger than L2.
+constexpr uint32_t WB_WORDS = 3;
+constexpr uint32_t WB_MASKS = 100;
+constexpr uint32_t WB_LINE_WORDS = 16;
 
 // XorshiftHashFunctors::next (BooPHF.h:94-100)
 DEVINL uint64_t xs_next(uint64_t &s0, uint64_t &s1) {
@@ -56,6 +67,35 @@ __device__ __forceinline__ uint64_t mphf_lookup(const MphfDev &m, const uint64_t
         }
     }
     return ~0ULL;
+}
+
+// Extension mask of a stored (canonical) key through the walk blocks; 0 if the key falls through all bit levels.
+template<int W>
+__device__ __forceinline__ uint32_t mphf_lookup_mask(const MphfDev &m, const uint8_t *__restrict__ masks, const uint64_t *rec) {
+    const uint32_t b = kmer_bucket<W>(rec, m.num_buckets);
+    uint64_t s0, s1;
+    xxh3_128<W>(rec, s0, s1);
+    const uint64_t *dom = m.domain + (uint64_t) b * MPHF_LEVELS;
+    const uint64_t *wo = m.word_off + (uint64_t) b * MPHF_LEVELS;
+    for (int l = 0; l < MPHF_LEVELS - 1; ++l) {
+        const uint64_t h = (l == 0) ? s0 : (l == 1) ? s1 : xs_next(s0, s1);
+        const uint64_t d = __ldg(dom + l);
+        if (d == 0) return 0u;
+        const uint64_t pos = __umul64hi(h, d);
+        const uint32_t gw = (uint32_t) (__ldg(wo + l) + (pos >> 6));
+        const uint32_t line = gw / WB_WORDS, j = gw - line * WB_WORDS;
+        const uint64_t *lp = m.wblk + (uint64_t) line * WB_LINE_WORDS;
+        const uint64_t word = __ldg(lp + j);
+        if ((word >> (pos & 63)) & 1ULL) {
+            uint32_t r = (uint32_t) __popcll(word & ((1ULL << (pos & 63)) - 1ULL));
+            if (j > 0) r += (uint32_t) __popcll(__ldg(lp));
+            if (j > 1) r += (uint32_t) __popcll(__ldg(lp + 1));
+            const uint32_t hdr = __ldg(reinterpret_cast<const uint32_t *>(lp) + 2 * WB_WORDS);
+            if (hdr >> 31) return __ldg(masks + (hdr & 0x7FFFFFFFu) + r);
+            return __ldg(reinterpret_cast<const uint8_t *>(lp) + 8 * WB_WORDS + 4 + r);
+        }
+    }
+    return 0u;
 }
 
 // Index of a k-mer in reading orientation: canonicalise, look up (InvertableKeyWithHash::CountIdx,

@@ -18,10 +18,42 @@ constexpr uint32_t WALK_LIMIT = 1024;
 
 template<int W>
 __device__ __forceinline__ uint32_t walk_mask(const MphfDev &m, const uint8_t *__restrict__ masks, const uint64_t *y, int k) {
-    bool minimal;
-    uint32_t idy = (uint32_t) mphf_lookup_oriented<W>(m, y, k, &minimal);
-    uint32_t raw = __ldg(masks + idy);
+    uint64_t c[W];
+    const bool minimal = kmer_canonical<W>(y, k, c);
+    const uint32_t raw = m.wblk ? mphf_lookup_mask<W>(m, masks, c) : (uint32_t) __ldg(masks + (uint32_t) mphf_lookup<W>(m, c));
     return minimal ? raw : mask_conj(raw);
+}
+
+// Builds the walk blocks (mphf.cuh) from the complete index and the masks in index order: one thread per 16-byte piece of a line.
+__global__ void __launch_bounds__(256) walk_blocks_kernel(const uint64_t *__restrict__ bits, const uint32_t *__restrict__ pc_scan, uint64_t words,
+                                                         const uint8_t *__restrict__ masks, uint64_t n_lines, uint4 *__restrict__ out) {
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t line = t >> 3;
+    if (line >= n_lines) return;
+    const uint32_t piece = (uint32_t) t & 7u;
+    const uint64_t w0 = line * WB_WORDS;
+    const uint32_t rank = __ldg(pc_scan + w0);
+    const uint64_t wend = w0 + WB_WORDS < words ? w0 + WB_WORDS : words;
+    const uint32_t cnt = __ldg(pc_scan + wend) - rank;   // pc_scan has words + 1 entries
+    const bool spill = cnt > WB_MASKS;
+    union { uint4 v; uint64_t q[2]; uint32_t d[4]; uint8_t b[16]; } u;
+    u.v = make_uint4(0u, 0u, 0u, 0u);
+    int mfirst = 0;   // first byte of this piece that holds a mask
+    if (piece == 0) {
+        u.q[0] = w0 < words ? __ldg(bits + w0) : 0ULL;
+        u.q[1] = w0 + 1 < words ? __ldg(bits + w0 + 1) : 0ULL;
+        mfirst = 16;
+    } else if (piece == 1) {
+        u.q[0] = w0 + 2 < words ? __ldg(bits + w0 + 2) : 0ULL;
+        u.d[2] = rank | (spill ? 0x80000000u : 0u);
+        mfirst = 12;
+    }
+    if (!spill) {
+        const int j0 = (int) piece * 16 - (int) (8 * WB_WORDS + 4);   // mask number of byte 0 of this piece
+        for (int i = mfirst; i < 16; ++i)
+            if ((uint32_t) (j0 + i) < cnt) u.b[i] = __ldg(masks + rank + (uint32_t) (j0 + i));
+    }
+    out[t] = u.v;
 }
 
 // Work list of start edges, in the reference's discovery order: every outgoing edge of every oriented junction, t = 2 * (file index -
@@ -106,35 +138,71 @@ __device__ __forceinline__ uint32_t claim_work(bool need, uint32_t *__restrict__
     return (need && item < n) ? item : NO_WORK;
 }
 
+// A lane's walk ends at a junction; what follows (orientation filter against the start k-mer, result stores) and the start of its next
+// walk (work claim, k-mer load, first shift) are long code paths that few lanes need at a time: they run in SERVICE ROUNDS, once at
+// least WALK_SERVICE_MIN lanes of the warp wait for one, so that the step code — the part every walk spends its time in — runs with most
+// lanes active (ncu r2l: 17.9 of 32 threads active per instruction with a service check in every iteration).
+constexpr int WALK_SERVICE_MIN = 8;
+
 template<int W>
-__global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+__global__ void __launch_bounds__(256, 5) walk_measure_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                           uint32_t n_e, const uint8_t *__restrict__ masks, uint32_t *__restrict__ elen,
                                                           uint32_t *__restrict__ kflag, unsigned long long *__restrict__ ewords,
-                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases */,
-                                                          uint32_t *__restrict__ work) {
-    unsigned long long chain_nodes = 0, kept_bases = 0;
-    uint32_t too_long = 0;
-    bool active = false, exhausted = false;
+                                                          unsigned long long *__restrict__ totals /* [0] chain vertices seen, [1] long chains, [4] kept bases, [5] kept paths longer than the capture */,
+                                                          uint32_t *__restrict__ work, unsigned long long *__restrict__ escr, uint32_t cw) {
+    uint32_t chain_nodes = 0, kept_bases = 0;   // per lane: far below 2^32
+    uint32_t too_long = 0, uncaptured = 0;
+    unsigned long long cap = 0;
+    bool active = false, pending = false, exhausted = false;   // pending: the walk ended, its result is not written yet
     uint32_t cnext = 0, cend = 0;
-    uint32_t e = 0, c = 0, nn = 0, prev_first = 0;
-    uint64_t x[W], y[W];
+    uint32_t e = 0, nn = 0, prev_first = 0;
+    uint64_t y[W];
 #pragma unroll
-    for (int q = 0; q < W; ++q) { x[q] = 0; y[q] = 0; }
+    for (int q = 0; q < W; ++q) y[q] = 0;
     while (true) {
-        const bool need = !active && !exhausted;
-        const uint32_t item = claim_work(need, work, n_e, cnext, cend);
-        if (need) {
-            if (item == NO_WORK) exhausted = true;
-            else {
-                e = item;
-                const uint32_t code = elist[e];
-                const uint32_t t = code >> 2;
-                c = code & 3u;
-                oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
-                kmer_shl<W>(x, k, c, y);
-                prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
-                nn = 1;
-                active = true;
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (__popc(idle) >= WALK_SERVICE_MIN && __any_sync(0xffffffffu, pending || (!active && !exhausted))) {
+            if (pending) {
+                uint32_t len = 0;
+                if (nn == 0) too_long += 1;
+                else {
+                    chain_nodes += nn - 1;
+                    const uint32_t code = elist[e];
+                    const uint32_t t = code >> 2, c = code & 3u;
+                    uint64_t x[W], rcn[W];
+                    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+                    kmer_rc<W>(y, k, rcn);
+                    const int cmp = kmer_lex_cmp<W>(x, rcn);
+                    const bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
+                    if (keep) {
+                        len = nn;
+                        kept_bases += (uint32_t) k + nn;
+                        const uint32_t s = nn - 1;   // nucleotides appended after c
+                        if (s > 32u * cw) uncaptured = 1;
+                        else if (s & 31u) escr[(uint64_t) e * cw + (s >> 5)] = cap;
+                    }
+                }
+                elen[e] = len;
+                kflag[e] = len ? 1u : 0u;
+                ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
+                pending = false;
+            }
+            const bool need = !active && !exhausted;
+            const uint32_t item = claim_work(need, work, n_e, cnext, cend);
+            if (need) {
+                if (item == NO_WORK) exhausted = true;
+                else {
+                    e = item;
+                    const uint32_t code = elist[e];
+                    const uint32_t t = code >> 2;
+                    uint64_t x[W];
+                    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+                    kmer_shl<W>(x, k, code & 3u, y);
+                    prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
+                    nn = 1;
+                    cap = 0;
+                    active = true;
+                }
             }
         }
         if (!__any_sync(0xffffffffu, active)) break;
@@ -142,24 +210,20 @@ __global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint
             const uint32_t mk = walk_mask<W>(m, masks, y, k);
             const bool junction = mask_is_junction(mk);
             if (junction || nn > WALK_LIMIT) {
-                uint32_t len = 0;
-                if (!junction) too_long += 1;
-                else {
-                    chain_nodes += nn - 1;
-                    uint64_t rcn[W];
-                    kmer_rc<W>(y, k, rcn);
-                    const int cmp = kmer_lex_cmp<W>(x, rcn);
-                    const bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
-                    if (keep) { len = nn; kept_bases += (unsigned long long) k + nn; }
-                }
-                elen[e] = len;
-                kflag[e] = len ? 1u : 0u;
-                ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
+                if (!junction) nn = 0;   // marks a chain beyond the limit (a finished walk has nn >= 1)
                 active = false;
+                pending = true;
             } else {
                 uint64_t z[W];
                 prev_first = kmer_base(y, 0);
-                kmer_shl<W>(y, k, nib_next(mk & 15u), z);
+                const uint32_t b = nib_next(mk & 15u);
+                // the nucleotides the chain appends after c are left for the emitting pass: 32 to a word, `cw` words per start edge
+                const uint32_t s = nn - 1;
+                if ((s >> 5) < cw) {
+                    cap |= (unsigned long long) b << (2 * (s & 31u));
+                    if ((s & 31u) == 31u) { escr[(uint64_t) e * cw + (s >> 5)] = cap; cap = 0; }
+                }
+                kmer_shl<W>(y, k, b, z);
 #pragma unroll
                 for (int q = 0; q < W; ++q) y[q] = z[q];
                 ++nn;
@@ -167,20 +231,22 @@ __global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint
         }
     }
     // one atomic per warp and counter
+    unsigned long long chain_sum = chain_nodes, kept_sum = kept_bases;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        chain_nodes += __shfl_down_sync(0xffffffffu, chain_nodes, d);
-        kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
+        chain_sum += __shfl_down_sync(0xffffffffu, chain_sum, d);
+        kept_sum += __shfl_down_sync(0xffffffffu, kept_sum, d);
         too_long += __shfl_down_sync(0xffffffffu, too_long, d);
     }
+    if (__any_sync(0xffffffffu, uncaptured != 0) && (threadIdx.x & 31) == 0) atomicAdd(&totals[5], 1ULL);   // rare
     // one set of global atomics per CTA (per-warp atomics on three addresses serialise in L2)
     __shared__ unsigned long long s_tot[3];
     if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
     __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-        if (chain_nodes) atomicAdd(&s_tot[0], chain_nodes);
+        if (chain_sum) atomicAdd(&s_tot[0], chain_sum);
         if (too_long) atomicAdd(&s_tot[1], (unsigned long long) too_long);
-        if (kept_bases) atomicAdd(&s_tot[2], kept_bases);
+        if (kept_sum) atomicAdd(&s_tot[2], kept_sum);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -188,6 +254,53 @@ __global__ void __launch_bounds__(256) walk_measure_kernel(MphfDev m, const uint
         if (s_tot[1]) atomicAdd(&totals[1], s_tot[1]);
         if (s_tot[2]) atomicAdd(&totals[4], s_tot[2]);
     }
+}
+
+// Emitting pass over the kept edges when the measuring walk captured every kept path: no lookups, no link reads — the start k-mer, the
+// edge nucleotide and the captured words, re-aligned to the output's word grid.
+template<int W>
+__global__ void __launch_bounds__(256) walk_emit_captured_kernel(const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
+                                                                const uint32_t *__restrict__ klist, uint32_t n_kept, const uint32_t *__restrict__ elen,
+                                                                const unsigned long long *__restrict__ escr, uint32_t cw,
+                                                                const unsigned long long *__restrict__ ewords_scan, uint32_t *__restrict__ seq_len,
+                                                                uint64_t *__restrict__ seq_word_off, uint64_t *__restrict__ out_words) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_kept) return;
+    const uint32_t e = klist[q];
+    const uint32_t code = elist[e];
+    const uint32_t t = code >> 2, c = code & 3u;
+    const uint32_t nn = elen[e];
+    const unsigned long long woff = ewords_scan[e];
+    seq_len[q] = (uint32_t) k + nn;
+    seq_word_off[q] = woff;
+    uint64_t x[W];
+    oriented_kmer<W>(kmers, t >> 1, (int) (t & 1), k, x);
+    uint32_t pos = 0;
+    uint64_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if ((w + 1) * 32 <= k) { out_words[woff + w] = x[w]; pos = (w + 1) * 32; }
+    }
+    if (pos < (uint32_t) k) { acc = x[W - 1]; pos = (uint32_t) k; }   // padding bits of x are zero
+    acc |= (uint64_t) c << (2 * (pos & 31));
+    ++pos;
+    if ((pos & 31) == 0) { out_words[woff + (pos >> 5) - 1] = acc; acc = 0; }
+    // the captured nucleotides start at output position k + 1: shift every captured word by that offset
+    const uint32_t n_cap = nn - 1, sh = 2 * (pos & 31);
+    const unsigned long long *src = escr + (uint64_t) e * cw;
+    for (uint32_t j = 0; 32 * j < n_cap; ++j) {
+        uint64_t wv = src[j];
+        const uint32_t cnt = n_cap - 32 * j < 32 ? n_cap - 32 * j : 32;   // nucleotides in this word
+        if (cnt < 32) wv &= (1ULL << (2 * cnt)) - 1ULL;
+        acc |= wv << sh;
+        const uint32_t room = 32 - (pos & 31);
+        if (cnt >= room) {
+            out_words[woff + (pos >> 5)] = acc;
+            acc = sh ? wv >> (64 - sh) : 0ULL;
+        }
+        pos += cnt;
+    }
+    if (pos & 31) out_words[woff + (pos >> 5)] = acc;
 }
 
 __global__ void __launch_bounds__(256) kept_list_kernel(const uint32_t *__restrict__ kflag_scan, const uint32_t *__restrict__ elen, uint32_t n_e,
@@ -239,11 +352,11 @@ template<int W>
 __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                                 uint32_t n_e, const uint32_t *__restrict__ inv, const uint32_t *__restrict__ link,
                                                                 uint32_t *__restrict__ elen, uint32_t *__restrict__ efirst,
-                                                                unsigned long long *__restrict__ ebases, uint32_t *__restrict__ kflag,
+                                                                unsigned long long *__restrict__ escr, uint32_t cw, uint32_t *__restrict__ kflag,
                                                                 unsigned long long *__restrict__ ewords, unsigned long long *__restrict__ totals) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long chain_nodes = 0, kept_bases = 0;
-    uint32_t too_long = 0;
+    uint32_t too_long = 0, uncaptured = 0;
     if (e < n_e) {
         uint32_t code = elist[e];
         uint32_t t = code >> 2, c = code & 3u;
@@ -257,10 +370,14 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         uint32_t prev_first = kmer_base(x, 0);   // first base of the vertex before the current one
         uint32_t nn = 1;
         uint32_t L = __ldg(link + v);
-        unsigned long long bases = 0;   // the first 32 nucleotides the chain appends after c: the emitting walk of a short path needs no link reads
+        unsigned long long cap = 0;   // the nucleotides the chain appends after c, 32 to a word, `cw` words per start edge: the emitting pass reads no links
         while (L != LINK_JUNCTION) {
             if (nn > WALK_LIMIT) { too_long = 1; break; }
-            if (nn <= 32) bases |= (unsigned long long) ((L >> 28) & 3u) << (2 * (nn - 1));
+            const uint32_t s = nn - 1;
+            if ((s >> 5) < cw) {
+                cap |= (unsigned long long) ((L >> 28) & 3u) << (2 * (s & 31u));
+                if ((s & 31u) == 31u) { escr[(uint64_t) e * cw + (s >> 5)] = cap; cap = 0; }
+            }
             prev_first = L >> 30;
             v = L & LINK_POS_MASK;
             L = __ldg(link + v);
@@ -273,10 +390,15 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
             oriented_kmer<W>(kmers, __ldg(inv + (v >> 1)), (v & 1) ? 0 : 1, k, rcn);   // rc of the end vertex (file position of its index)
             int cmp = kmer_lex_cmp<W>(x, rcn);
             bool keep = cmp > 0 || (cmp == 0 && c >= 3u - prev_first);   // tie: first edge nucleotide of the reverse path
-            if (keep) { len = nn; kept_bases = (unsigned long long) k + nn; }
+            if (keep) {
+                len = nn;
+                kept_bases = (unsigned long long) k + nn;
+                const uint32_t s = nn - 1;
+                if (s > 32u * cw) uncaptured = 1;
+                else if (s & 31u) escr[(uint64_t) e * cw + (s >> 5)] = cap;
+            }
         }
         elen[e] = len;
-        if (len) ebases[e] = bases;
         kflag[e] = len ? 1u : 0u;
         ewords[e] = len ? (((unsigned long long) k + len + 31) >> 5) : 0ULL;
     }
@@ -286,6 +408,7 @@ __global__ void __launch_bounds__(256) walk_measure_links_kernel(MphfDev m, cons
         kept_bases += __shfl_down_sync(0xffffffffu, kept_bases, d);
         too_long += __shfl_down_sync(0xffffffffu, too_long, d);
     }
+    if (__any_sync(0xffffffffu, uncaptured != 0) && (threadIdx.x & 31) == 0) atomicAdd(&totals[5], 1ULL);   // rare
     // one set of global atomics per CTA (per-warp atomics on three addresses serialise in L2)
     __shared__ unsigned long long s_tot[3];
     if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
@@ -307,7 +430,7 @@ template<int W>
 __global__ void __launch_bounds__(256) walk_emit_links_kernel(const uint64_t *__restrict__ kmers, int k, const uint32_t *__restrict__ elist,
                                                              const uint32_t *__restrict__ klist, uint32_t n_kept, const uint32_t *__restrict__ link,
                                                              const uint32_t *__restrict__ elen, const uint32_t *__restrict__ efirst,
-                                                             const unsigned long long *__restrict__ ebases,
+                                                             const unsigned long long *__restrict__ escr, uint32_t cw,
                                                              const unsigned long long *__restrict__ ewords_scan, uint32_t *__restrict__ seq_len,
                                                              uint64_t *__restrict__ seq_word_off, uint64_t *__restrict__ out_words) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,7 +459,7 @@ __global__ void __launch_bounds__(256) walk_emit_links_kernel(const uint64_t *__
     };
     push(c);
     if (nn <= 33) {   // short path: the measuring walk left its nucleotides
-        unsigned long long bases = ebases[e];
+        unsigned long long bases = escr[(uint64_t) e * cw];
         for (uint32_t s = 1; s < nn; ++s) { push((uint32_t) bases & 3u); bases >>= 2; }
     } else {
         uint32_t v = efirst[e];
@@ -456,7 +579,11 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     totals.zero();
     DevBuf<uint32_t> work(ctx, 4);               // work-queue heads of the persistent walk kernels: [0] measure, [1] emit
     work.zero();
-    const unsigned walk_grid = (unsigned) ctx->num_sms * 6;
+    // persistent walk kernels: exactly the CTAs that are resident at once
+    int per_sm_measure = 4, per_sm_emit = 4;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_measure, walk_measure_kernel<W>, 256, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_emit, walk_emit_kernel<W>, 256, 0));
+    const unsigned walk_grid = (unsigned) (ctx->num_sms * std::max(per_sm_measure, 1)), emit_grid = (unsigned) (ctx->num_sms * std::max(per_sm_emit, 1));
     if (nt) LAUNCH(ctx, junction_degree_kernel, n_tiles, 256, 0, n_range, ext->idx.p + first, ext->masks.p, fm, deg.p);
     else deg.zero();
     exclusive_scan<uint32_t>(ctx, deg.p, n_tiles, tot32.p);
@@ -466,23 +593,34 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     DevBuf<uint32_t> elist(ctx, (uint64_t) n_e + 1), elen(ctx, (uint64_t) n_e + 1), kflag(ctx, (uint64_t) n_e + 1);
     DevBuf<unsigned long long> ewords(ctx, (uint64_t) n_e + 1);
     const uint64_t *kbase = kmers->data.p + first * W;
-    // pointer-chasing walks need the whole k-mer table and the inverse permutation on this GPU; a shard (or a table too
-    // large for 28-bit positions) walks by MPHF lookups instead
-    const bool use_links = !ctx->no_links && first == 0 && last == n && ext->n_local == ext->size && ext->inv.p != nullptr && 2 * n <= LINK_POS_MASK;
+    // Default: one lookup through the walk blocks per step (5.5 ms at config 2).  The link-table walks (SB200_LINKS=1: 3.7 ms of lookups
+    // up front + 4.1 ms of pointer chasing) need the whole k-mer table and the inverse permutation on this GPU.
+    const bool use_links = ctx->links && first == 0 && last == n && ext->n_local == ext->size && ext->inv.p != nullptr && 2 * n <= LINK_POS_MASK;
     DevBuf<uint32_t> link, efirst;
-    DevBuf<unsigned long long> ebases;
+    // capture buffer of the measuring walks: `cw` words (32 nucleotides each) per start edge, the whole WALK_LIMIT when that fits 16 GB
+    uint32_t cw = WALK_LIMIT / 32;
+    while (cw > 1 && (uint64_t) n_e * cw * 8 > (16ull << 30)) cw >>= 1;
+    if (ctx->walk_capture_words) cw = (uint32_t) std::min<size_t>(cw, ctx->walk_capture_words);
+    DevBuf<unsigned long long> escr(ctx, (uint64_t) n_e * cw + 1);
+    DevBuf<uint4> wblk;
+    if (n_e && !use_links && mphf->pc_scan.p && !ctx->no_place && !ctx->no_walk_blocks) {
+        // lookup walks: index bits, rank and masks of a step in one 128-byte line (mphf.cuh)
+        const uint64_t n_lines = div_up(mphf->total_words, WB_WORDS);
+        wblk.alloc(ctx, n_lines * 8);
+        LAUNCH(ctx, walk_blocks_kernel, div_up(n_lines * 8, 256), 256, 0, mphf->bits.p, mphf->pc_scan.p, mphf->total_words, ext->masks.p, n_lines, wblk.p);
+        m.wblk = reinterpret_cast<const uint64_t *>(wblk.p);
+    }
     if (n_e) {
         LAUNCH(ctx, edge_list_kernel, n_tiles, 256, 0, n_range, ext->idx.p + first, ext->masks.p, fm, deg.p, elist.p);
         if (use_links) {
             link.alloc(ctx, 2 * n);
             efirst.alloc(ctx, (uint64_t) n_e + 1);
-            ebases.alloc(ctx, (uint64_t) n_e + 1);
             LAUNCH(ctx, links_kernel<W>, div_up(2 * n, 256), 256, 0, m, kmers->data.p, n, k, ext->idx.p, ext->masks.p, fm, link.p);
             LAUNCH(ctx, walk_measure_links_kernel<W>, div_up(n_e, 256), 256, 0, m, kbase, k, elist.p, n_e, ext->inv.p, link.p, elen.p, efirst.p,
-                   ebases.p, kflag.p, ewords.p, totals.p);
+                   escr.p, cw, kflag.p, ewords.p, totals.p);
         } else {
             LAUNCH(ctx, walk_measure_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, n_e, ext->masks.p, elen.p, kflag.p, ewords.p, totals.p,
-                   work.p);
+                   work.p, escr.p, cw);
         }
     }
     if (check_loops) LAUNCH(ctx, count_nonjunction_kernel, (unsigned) ctx->num_sms * 8, 256, 0, ext->masks.p, n, totals.p + 3);
@@ -505,11 +643,14 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
     if (st.n_kept) {
         DevBuf<uint32_t> klist(ctx, st.n_kept);
         LAUNCH(ctx, kept_list_kernel, div_up(n_e, 256), 256, 0, kflag.p, elen.p, n_e, klist.p);
-        if (use_links)
+        if (th[5] == 0)   // every kept path was captured by the measuring walk
+            LAUNCH(ctx, walk_emit_captured_kernel<W>, div_up(st.n_kept, 256), 256, 0, kbase, k, elist.p, klist.p, st.n_kept, elen.p, escr.p, cw,
+                   ewords.p, out->len.p, out->word_off.p, out->words.p);
+        else if (use_links)
             LAUNCH(ctx, walk_emit_links_kernel<W>, div_up(st.n_kept, 256), 256, 0, kbase, k, elist.p, klist.p, st.n_kept, link.p, elen.p, efirst.p,
-                   ebases.p, ewords.p, out->len.p, out->word_off.p, out->words.p);
+                   escr.p, cw, ewords.p, out->len.p, out->word_off.p, out->words.p);
         else
-            LAUNCH(ctx, walk_emit_kernel<W>, walk_grid, 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
+            LAUNCH(ctx, walk_emit_kernel<W>, emit_grid, 256, 0, m, kbase, k, elist.p, klist.p, st.n_kept, ext->masks.p, elen.p, ewords.p,
                    out->len.p, out->word_off.p, out->words.p, work.p + 1);
     }
     uint64_t tw = st.words;

@@ -231,10 +231,14 @@ def test_long_chains_and_forced_pointer_jumping(ctx, monkeypatch):
         ctx2.close()
 
 
-def test_direct_walks_by_lookup(monkeypatch):
-    """SB200_NO_LINKS=1: the direct walks resolve every step by MPHF lookup (what a table shard does) instead of following
-    the link table — same unitigs, same order."""
-    monkeypatch.setenv("SB200_NO_LINKS", "1")
+@pytest.mark.parametrize("env", [("SB200_LINKS",), ("SB200_NO_WALK_BLOCKS",), ("SB200_WALK_CAPTURE_WORDS",), ("SB200_LINKS", "SB200_WALK_CAPTURE_WORDS")])
+def test_direct_walk_variants(monkeypatch, env):
+    """The direct walks resolve every step by an MPHF lookup through the walk blocks (default, and what a table shard does).
+    Variants with the same unitigs in the same order: SB200_LINKS=1 follows a link table instead (one lookup per vertex up front);
+    SB200_NO_WALK_BLOCKS=1 reads bit-vector, rank and mask array separately; a capture buffer of one word per start edge makes the
+    emitting pass re-walk longer kept paths (lookup walks and link walks)."""
+    for e in env:
+        monkeypatch.setenv(e, "1")
     ctx2 = B.Context(0)
     try:
         from conftest import load_golden
@@ -404,7 +408,7 @@ def test_baseline_config2_full_size(monkeypatch):
     finally:
         ctx1.close()
     monkeypatch.setenv("SB200_NO_MASK_PAYLOAD", "1")
-    monkeypatch.setenv("SB200_NO_LINKS", "1")
+    monkeypatch.setenv("SB200_LINKS", "1")               # the link-table walks instead of lookups through the walk blocks
     monkeypatch.setenv("SB200_GROUP_KERNEL", "chunk")   # and the sorting group kernel instead of the hashing one
     monkeypatch.setenv("SB200_NO_PLACE", "1")            # and k-mer indices by MPHF lookups instead of the build's placement record
     monkeypatch.setenv("SB200_COUNTING_PASSES", "1")     # and extract / derive + counting passes instead of the staged producer-fused partition
