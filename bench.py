@@ -419,6 +419,18 @@ def main_sharded(a, world, rank, local_rank):
     launches = ctx.kernel_launches()
     clocks = sampler.stop()
     xb, xm = xchg["bytes"] / a.steps, xchg["ms"] / a.steps
+    if a.breakdown:   # one more step with per-kernel CUDA events: rank 0's kernels against its stage times (the rest is exchange + waiting)
+        ctx.profile(True)
+        stage_acc.clear()
+        step(False)
+        torch.cuda.synchronize()
+        rep = ctx.profile_report()
+        ctx.profile(False)
+        if rank == 0:
+            print("stage_ms (profiled step): %s" % json.dumps({k_: round(v_, 3) for k_, v_ in stage_acc.items()}), file=sys.stderr)
+            for name, n, t in rep:
+                print("%-40s %6d launches %10.3f ms/step" % (name, n, t), file=sys.stderr)
+        dist.barrier()
     ms_e2e, d2h = (None, 0) if a.no_e2e else timed(True)
 
     parity = None

@@ -67,6 +67,7 @@ int sb200_create(int device, sb200_ctx **out) {
         ctx->force_jump_path = getenv("SB200_FORCE_JUMP") != nullptr;
         ctx->links = getenv("SB200_LINKS") != nullptr;
         ctx->no_walk_blocks = getenv("SB200_NO_WALK_BLOCKS") != nullptr;
+        ctx->no_peer_stores = getenv("SB200_NO_PEER_STORES") != nullptr;
         if (const char *v = getenv("SB200_WALK_CAPTURE_WORDS")) ctx->walk_capture_words = (size_t) atoi(v);
         ctx->no_mask_payload = getenv("SB200_NO_MASK_PAYLOAD") != nullptr;
         ctx->no_place = getenv("SB200_NO_PLACE") != nullptr;

@@ -111,6 +111,11 @@ __global__ void or_bytes_kernel(uint32_t *__restrict__ dst, const uint32_t *__re
 using namespace sb200;
 
 sb200_comm::~sb200_comm() {
+    for (PeerSlot &ps : peer) {
+        for (size_t r = 0; r < ps.mapped.size(); ++r)
+            if (ps.ipc[r] && ps.mapped[r]) cudaIpcCloseMemHandle(ps.mapped[r]);
+        if (ps.mine) cudaFree(ps.mine);
+    }
     if (nccl) nccl_api().CommDestroy((ncclComm_t) nccl);
 }
 
@@ -186,6 +191,85 @@ void sb200_comm::all_to_all_v(sb200_ctx *ctx, const void *send, const uint64_t *
     ctx->event_pool.push_back(e1);
 }
 
+bool sb200_comm::peer_buffers(sb200_ctx *ctx, int slot, const uint64_t *need, void **ptrs) {
+    if (peer_failed) return false;
+    PeerSlot &ps = peer[slot];
+    if (ps.cap.empty()) { ps.cap.assign((size_t) size, 0); ps.mapped.assign((size_t) size, nullptr); ps.ipc.assign((size_t) size, false); }
+    bool grow = false;
+    for (int r = 0; r < size; ++r) grow = grow || need[r] > ps.cap[(size_t) r];
+    if (grow) {
+        // nobody may still address a buffer that is about to be replaced
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < size; ++r) {
+            if (need[r] <= ps.cap[(size_t) r]) continue;
+            if (ps.ipc[(size_t) r] && ps.mapped[(size_t) r]) CUDA_CHECK(cudaIpcCloseMemHandle(ps.mapped[(size_t) r]));
+            ps.mapped[(size_t) r] = nullptr; ps.ipc[(size_t) r] = false;
+        }
+        barrier(ctx);
+        std::vector<bool> grew((size_t) size, false);
+        for (int r = 0; r < size; ++r) {
+            if (need[r] <= ps.cap[(size_t) r]) continue;
+            grew[(size_t) r] = true;
+            ps.cap[(size_t) r] = need[r] + need[r] / 4 + (1u << 20);
+            if (r == rank) {
+                if (ps.mine) CUDA_CHECK(cudaFree(ps.mine));
+                ps.mine = nullptr;
+                CUDA_CHECK(cudaSetDevice(ctx->device));
+                CUDA_CHECK(cudaMalloc(&ps.mine, ps.cap[(size_t) r]));
+                ps.mapped[(size_t) r] = ps.mine;
+            }
+        }
+        uint64_t ok = 1;
+        if (local) {
+            local->ptr[(size_t) rank] = ps.mine;
+            local->barrier();
+            for (int r = 0; r < size; ++r) {
+                if (r == rank || !grew[(size_t) r]) continue;
+                void *q = const_cast<void *>(local->ptr[(size_t) r]);
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
+                if (at.device != ctx->device) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, ctx->device, at.device);
+                    if (!can) { ok = 0; continue; }
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                    cudaGetLastError();
+                }
+                ps.mapped[(size_t) r] = q;
+            }
+            local->barrier();
+        } else {
+            // one CUDA IPC handle (64 bytes) per rank goes round; only the buffers that were replaced are (re)opened
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+            uint64_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            std::vector<uint64_t> all((size_t) size * 8);
+            if (grew[(size_t) rank]) {
+                cudaIpcMemHandle_t hd;
+                CUDA_CHECK(cudaIpcGetMemHandle(&hd, ps.mine));
+                memcpy(h, &hd, 64);
+            }
+            all_gather_host(ctx, h, 8, all.data());
+            for (int r = 0; r < size; ++r) {
+                if (r == rank || !grew[(size_t) r]) continue;
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, all.data() + (size_t) r * 8, 64);
+                void *q = nullptr;
+                if (cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
+                ps.mapped[(size_t) r] = q; ps.ipc[(size_t) r] = true;
+            }
+        }
+        // all or nothing
+        std::vector<uint64_t> oks((size_t) size);
+        all_gather_host(ctx, &ok, 1, oks.data());
+        for (int r = 0; r < size; ++r)
+            if (!oks[(size_t) r]) peer_failed = true;
+        if (peer_failed) return false;
+    }
+    for (int r = 0; r < size; ++r) ptrs[r] = ps.mapped[(size_t) r];
+    return true;
+}
+
 void sb200_comm::all_gather_v_inplace(sb200_ctx *ctx, void *buf, const uint64_t *off) {
     if (size == 1) return;
     uint8_t *b = (uint8_t *) buf;
@@ -203,10 +287,15 @@ void sb200_comm::all_gather_v_inplace(sb200_ctx *ctx, void *buf, const uint64_t 
         local->barrier();
         return;
     }
+    // point-to-point in one group: every rank hands its slice to every peer and takes theirs — NVSwitch carries all pairs at once
+    // (a group of `size` broadcasts ran at about a third of the all-to-all's bandwidth, profiles/r2n)
+    const uint64_t mine = off[rank + 1] - off[rank];
     NCCL_CHECK(nccl_api().GroupStart());
-    for (int r = 0; r < size; ++r) {
-        const uint64_t bytes = off[r + 1] - off[r];
-        if (bytes) NCCL_CHECK(nccl_api().Broadcast(b + off[r], b + off[r], bytes, ncclUint8, r, (ncclComm_t) nccl, ctx->stream));
+    for (int d = 1; d < size; ++d) {
+        const int to = (rank + d) % size, from = (rank - d + size) % size;
+        const uint64_t nb = off[from + 1] - off[from];
+        if (mine) NCCL_CHECK(nccl_api().Send(b + off[rank], mine, ncclUint8, to, (ncclComm_t) nccl, ctx->stream));
+        if (nb) NCCL_CHECK(nccl_api().Recv(b + off[from], nb, ncclUint8, from, (ncclComm_t) nccl, ctx->stream));
     }
     NCCL_CHECK(nccl_api().GroupEnd());
 }

@@ -39,12 +39,26 @@ struct sb200_comm {
     std::shared_ptr<sb200::LocalShared> local;     // virtual ranks
     uint64_t bytes_sent = 0;                       // bytes this rank handed to other ranks since the last reset (NVLink roofline of the bench)
     double exchange_ms = 0;                        // device time of the record exchanges (all-to-all) since the last reset
+    struct PeerSlot {
+        void *mine = nullptr;
+        std::vector<uint64_t> cap;                 // capacity of every rank's buffer (the same bookkeeping on every rank)
+        std::vector<void *> mapped;                // how this rank addresses every rank's buffer
+        std::vector<bool> ipc;                     // mapped[r] came from cudaIpcOpenMemHandle
+    };
+    PeerSlot peer[2];
+    bool peer_failed = false;                      // some pair cannot map: the exchanges go through NCCL / copies
     ~sb200_comm();
 
     // every rank contributes n host values; out[r * n + i] = value i of rank r
     void all_gather_host(sb200_ctx *ctx, const uint64_t *in, size_t n, uint64_t *out);
     // send[send_off[r], send_off[r + 1]) goes to rank r; recv[recv_off[s], recv_off[s + 1]) arrives from rank s (byte offsets)
     void all_to_all_v(sb200_ctx *ctx, const void *send, const uint64_t *send_off, void *recv, const uint64_t *recv_off);
+    // Peer-visible receive buffers, one per slot and rank, kept for the life of the communicator: ptrs[r] = rank r's buffer of `slot`
+    // as THIS rank addresses it (its own allocation; a CUDA IPC mapping when r is another process; the plain pointer when r is a
+    // virtual rank of this process, with peer access enabled between the devices).  need[r] = bytes rank r's buffer must hold — every rank
+    // passes the same array, so all of them know without talking when somebody has to grow and the handles have to go round again
+    // (steady state: no communication at all).  Returns false on every rank when some pair of GPUs cannot map each other's memory.
+    bool peer_buffers(sb200_ctx *ctx, int slot, const uint64_t *need, void **ptrs);
     // every rank holds the same layout; rank r's slice buf[off[r], off[r + 1]) is valid on r and is copied to everybody else (bytes)
     void all_gather_v_inplace(sb200_ctx *ctx, void *buf, const uint64_t *off);
     // rank r's `bytes` bytes land at recv[recv_off[r] ...) on `root` (recv / recv_off only read on root)

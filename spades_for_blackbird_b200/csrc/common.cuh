@@ -75,6 +75,7 @@ struct sb200_ctx {
     bool no_place = false;          // SB200_NO_PLACE=1: k-mer indices by MPHF lookups even when the build recorded the placements (cross-check)
     bool no_mask_payload = false;   // SB200_NO_MASK_PAYLOAD=1: masks by MPHF lookups (fill_masks_kernel) even when the k-mer sort could carry them
     bool mphf_state_per_key = false;  // SB200_MPHF_STATE_PER_KEY=1: level 0 writes a 24-byte state per key for level 1 (round 1) instead of level 1 re-reading the keys (cross-check)
+    bool no_peer_stores = false;    // SB200_NO_PEER_STORES=1: the sharded path's record exchanges through send buffers + all-to-all instead of peer stores from pass 1
     bool no_walk_blocks = false;    // SB200_NO_WALK_BLOCKS=1: lookup walks read bit-vector, rank and mask separately (cross-check)
     size_t walk_capture_words = 0;  // SB200_WALK_CAPTURE_WORDS=n: cap of the measuring walks' capture buffer per start edge (tests: force the re-walk)
     bool links = false;             // SB200_LINKS=1: direct walks by pointer chasing over a link table (one lookup per vertex up front) instead of a lookup
@@ -199,11 +200,13 @@ struct DevBuf {
     DevBuf(sb200_ctx *ctx, size_t count) { alloc(ctx, count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), c(o.c) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), c(o.c), own(o.own) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; c = o.c; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; c = o.c; own = o.own; o.p = nullptr; o.n = 0; }
         return *this;
     }
+    bool own = true;   // false: a view of memory somebody else keeps (a peer-visible receive buffer of the communicator)
+    void borrow(sb200_ctx *ctx, T *ptr, size_t count) { release(); c = ctx; p = ptr; n = count; own = false; }
     ~DevBuf() { release(); }
     void alloc(sb200_ctx *ctx, size_t count) {
         release();
@@ -212,8 +215,8 @@ struct DevBuf {
         p = (T *) ctx->dev_alloc((count ? count : 1) * sizeof(T));
     }
     void release() {
-        if (p) c->dev_free(p);
-        p = nullptr; n = 0;
+        if (p && own) c->dev_free(p);
+        p = nullptr; n = 0; own = true;
     }
     void zero() { CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), c->stream)); }
     size_t bytes() const { return n * sizeof(T); }

@@ -613,9 +613,9 @@ static sb200_kmers *count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, 
         const uint32_t chunk_cap = 32u * std::min<uint32_t>(PART_RUN, (max_nwin + 31u) / 32u);
         const int rounds = std::max<int>(1, SpCfg<W>::CAP / (int) (SP_WARPS * chunk_cap));
         LAUNCH(ctx, sp_scatter_reads_kernel_, grid_s, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, mode, gs, pl.s, pl.n_coarse,
-               rounds, t.cur1.p, mid.p);
+               rounds, t.cur1.p, mid.p, SpPeers());
         if (both) LAUNCH(ctx, sp_scatter_reads_kernel_, grid_s, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_REV, gs, pl.s,
-                         pl.n_coarse, rounds, t.cur1.p, mid.p);
+                         pl.n_coarse, rounds, t.cur1.p, mid.p, SpPeers());
         staged_pass2<W>(ctx, pl.s, t.tiles, t.cur2.p, gs, ~0ULL, mid.p, nullptr, inst.p, nullptr);
         ctx->trace_point("  instances partitioned (staged)");
         return finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, K, B, true, mode == PART_CANON, false, -1, nullptr, 0, B);
@@ -690,7 +690,7 @@ static sb200_kmers *derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B) 
         DevBuf<uint8_t> pay, mid_pay;
         if (side_pay) { pay.alloc(ctx, n); mid_pay.alloc(ctx, n); }
         LAUNCH(ctx, sp_scatter_derive_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, pshift, gs, pl.s, pl.n_coarse, t.cur1.p,
-               mid.p, mid_pay.p);
+               mid.p, mid_pay.p, SpPeers());
         staged_pass2<W>(ctx, pl.s, t.tiles, t.cur2.p, gs, last_word_mask(k), mid.p, mid_pay.p, inst.p, pay.p);
         ctx->trace_point("  candidates partitioned (staged)");
         sb200_kmers *s = finish_grouped<W>(ctx, inst, mid, n, hist.p, pl.n_groups, pl.p, k, B, false, false, false, pshift, pay.p, 0, B);
@@ -1065,7 +1065,7 @@ static sb200_records *shard_send_reads_w(sb200_ctx *ctx, const sb200_reads *rd, 
         const uint32_t chunk_cap = 32u * std::min<uint32_t>(PART_RUN, (max_nwin + 31u) / 32u);
         const int rounds = std::max<int>(1, SpCfg<W>::CAP / (int) (SP_WARPS * chunk_cap));
         LAUNCH(ctx, sp_scatter_reads_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K,
-               (int) PART_CANON, gs, pl.s, n_bins, rounds, cur1.p, r->data.p);
+               (int) PART_CANON, gs, pl.s, n_bins, rounds, cur1.p, r->data.p, SpPeers());
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return r.release();
@@ -1078,6 +1078,148 @@ sb200_records *shard_send_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned 
         case 3: return shard_send_reads_w<3>(ctx, rd, (int) K, B, G, *pl, owner_counts);
         default: return shard_send_reads_w<4>(ctx, rd, (int) K, B, G, *pl, owner_counts);
     }
+}
+
+// ---- the same with the exchange inside pass 1: the runs go straight into the owners' receive buffers (SpPeers, staged_partition.cuh) ----
+__global__ void sp_owner_relative_kernel(const uint32_t *__restrict__ start /* exclusive scan over [G][n_co], + total */, uint32_t n_co, uint32_t G,
+                                         uint32_t *__restrict__ cur1, uint32_t *__restrict__ tot /* G + 1 */) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G * n_co) cur1[i] = start[i] - start[(i / n_co) * n_co];
+    if (i <= G) tot[i] = start[(uint64_t) i * n_co];
+}
+
+struct SpPeerCounts { uint32_t *dst[64]; };
+__global__ void sp_peer_counts_kernel(const uint32_t *__restrict__ raw, uint32_t n_co, const __grid_constant__ SpPeerCounts pc) {
+    uint32_t *d = pc.dst[blockIdx.x];
+    for (uint32_t b = threadIdx.x; b < n_co; b += blockDim.x) d[b] = raw[(uint64_t) blockIdx.x * n_co + b];
+}
+
+// after the coarse count: per-owner totals on the host, cursors relative to the owner's run
+static void shard_peer_tables(sb200_ctx *ctx, uint32_t G, uint32_t n_co, ShardPeerSend *st, uint64_t *owner_counts) {
+    const uint64_t nb = (uint64_t) G * n_co;
+    DevBuf<uint32_t> start(ctx, nb + 1), tot(ctx, (uint64_t) G + 1);
+    CUDA_CHECK(cudaMemcpyAsync(start.p, st->raw.p, (nb + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    exclusive_scan<uint32_t>(ctx, start.p, nb + 1, nullptr);
+    st->cur1.alloc(ctx, nb);
+    LAUNCH(ctx, sp_owner_relative_kernel, div_up(nb + 1, 256), 256, 0, start.p, n_co, G, st->cur1.p, tot.p);
+    std::vector<uint32_t> h((size_t) G + 1);
+    ctx->fetch(h.data(), tot.p, ((size_t) G + 1) * 4);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t g = 0; g < G; ++g) owner_counts[g] = h[g + 1] - h[g];
+}
+
+template<int W>
+static ShardPeerSend *shard_peer_count_reads_w(sb200_ctx *ctx, const sb200_reads *rd, int K, uint32_t B, uint32_t G, const ShardPlan &pl, uint64_t *owner_counts) {
+    const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * K : 64};
+    const uint32_t n_bins = G * pl.n_co;
+    std::unique_ptr<ShardPeerSend> st(new ShardPeerSend());
+    st->k = (unsigned) K; st->words = W; st->double_palindromes = true; st->pl = pl;
+    st->raw.alloc(ctx, (uint64_t) n_bins + 1);
+    st->raw.zero();
+    auto sp_count_reads_kernel_ = sp_count_reads_kernel<W>;
+    const size_t smem_c = (size_t) n_bins * 4;
+    CUDA_CHECK(cudaFuncSetAttribute(sp_count_reads_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_c, 1024)));
+    if (rd->n_reads)
+        LAUNCH(ctx, sp_count_reads_kernel_, (unsigned) ctx->num_sms * 2, SPC_THREADS, smem_c, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K, (int) PART_CANON,
+               gs, pl.s, n_bins, st->raw.p);
+    shard_peer_tables(ctx, G, pl.n_co, st.get(), owner_counts);
+    return st.release();
+}
+
+template<int W>
+static void shard_peer_scatter_reads_w(sb200_ctx *ctx, const sb200_reads *rd, uint32_t B, uint32_t G, ShardPeerSend *st, const SpPeers &peers) {
+    const int K = (int) st->k;
+    const GroupSel gs{B, 0u, st->pl.p, (W == 1) ? 2 * K : 64};
+    auto sp_scatter_reads_peer_kernel_ = sp_scatter_reads_kernel<W, true>;
+    const size_t smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, false);
+    CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_reads_peer_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+    const uint32_t max_nwin = rd->max_len >= (uint32_t) K ? rd->max_len - (uint32_t) K + 1 : 128u;
+    const uint32_t chunk_cap = 32u * std::min<uint32_t>(PART_RUN, (max_nwin + 31u) / 32u);
+    const int rounds = std::max<int>(1, SpCfg<W>::CAP / (int) (SP_WARPS * chunk_cap));
+    if (rd->n_reads)
+        LAUNCH(ctx, sp_scatter_reads_peer_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, rd->words.p, rd->word_off.p, rd->len.p, rd->n_reads, K,
+               (int) PART_CANON, gs, st->pl.s, G * st->pl.n_co, rounds, st->cur1.p, (uint64_t *) nullptr, peers);
+}
+
+template<int WS, int W>
+static ShardPeerSend *shard_peer_count_derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B, uint32_t G, const ShardPlan &pl, uint64_t *owner_counts) {
+    const int k = (int) kp->k - 1;
+    const GroupSel gs{B, 0u, pl.p, (W == 1) ? 2 * k : 64};
+    const uint32_t n_bins = G * pl.n_co;
+    const int used = 2 * (k - 32 * (W - 1));
+    std::unique_ptr<ShardPeerSend> st(new ShardPeerSend());
+    st->k = (unsigned) k; st->words = W; st->pl = pl;
+    st->pshift = (used + 3 <= 64 && !ctx->no_mask_payload) ? used : -1;
+    st->side_pay = st->pshift < 0 && !ctx->no_mask_payload;
+    st->mask_payload = st->pshift >= 0;
+    st->raw.alloc(ctx, (uint64_t) n_bins + 1);
+    st->raw.zero();
+    auto sp_count_derive_kernel_ = sp_count_derive_kernel<WS, W>;
+    const size_t smem_c = (size_t) n_bins * 4;
+    CUDA_CHECK(cudaFuncSetAttribute(sp_count_derive_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem_c, 1024)));
+    if (kp->size) LAUNCH(ctx, sp_count_derive_kernel_, (unsigned) ctx->num_sms * 2, SPC_THREADS, smem_c, kp->data.p, kp->size, k, gs, pl.s, n_bins, st->raw.p);
+    shard_peer_tables(ctx, G, pl.n_co, st.get(), owner_counts);
+    return st.release();
+}
+
+template<int WS, int W>
+static void shard_peer_scatter_derive_w(sb200_ctx *ctx, const sb200_kmers *kp, uint32_t B, uint32_t G, ShardPeerSend *st, const SpPeers &peers) {
+    const int k = (int) st->k;
+    const GroupSel gs{B, 0u, st->pl.p, (W == 1) ? 2 * k : 64};
+    auto sp_scatter_derive_peer_kernel_ = sp_scatter_derive_kernel<WS, W, true>;
+    const size_t smem_s = sp_stage_bytes<W>(SpCfg<W>::CAP, st->side_pay);
+    CUDA_CHECK(cudaFuncSetAttribute(sp_scatter_derive_peer_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_s));
+    // (out_pay only tells the kernel whether the stage carries payload bytes; the peers' pointers are what it stores through)
+    if (kp->size)
+        LAUNCH(ctx, sp_scatter_derive_peer_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, st->pshift, gs, st->pl.s,
+               G * st->pl.n_co, st->cur1.p, (uint64_t *) nullptr, st->side_pay ? peers.pay[0] : (uint8_t *) nullptr, peers);
+}
+
+ShardPeerSend *shard_peer_count_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts) {
+    switch ((K + 31) / 32) {
+        case 1: return shard_peer_count_reads_w<1>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        case 2: return shard_peer_count_reads_w<2>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        case 3: return shard_peer_count_reads_w<3>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+        default: return shard_peer_count_reads_w<4>(ctx, rd, (int) K, B, G, *pl, owner_counts);
+    }
+}
+
+void shard_peer_scatter_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned B, unsigned G, ShardPeerSend *st, const SpPeers *peers) {
+    switch (st->words) {
+        case 1: shard_peer_scatter_reads_w<1>(ctx, rd, B, G, st, *peers); break;
+        case 2: shard_peer_scatter_reads_w<2>(ctx, rd, B, G, st, *peers); break;
+        case 3: shard_peer_scatter_reads_w<3>(ctx, rd, B, G, st, *peers); break;
+        default: shard_peer_scatter_reads_w<4>(ctx, rd, B, G, st, *peers); break;
+    }
+}
+
+ShardPeerSend *shard_peer_count_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts) {
+    int WS = (int) kp->words, W = (int) ((kp->k - 1 + 31) / 32);
+    if (WS == 1) return shard_peer_count_derive_w<1, 1>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 2 && W == 1) return shard_peer_count_derive_w<2, 1>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 2) return shard_peer_count_derive_w<2, 2>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 3 && W == 2) return shard_peer_count_derive_w<3, 2>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 3) return shard_peer_count_derive_w<3, 3>(ctx, kp, B, G, *pl, owner_counts);
+    if (WS == 4 && W == 3) return shard_peer_count_derive_w<4, 3>(ctx, kp, B, G, *pl, owner_counts);
+    return shard_peer_count_derive_w<4, 4>(ctx, kp, B, G, *pl, owner_counts);
+}
+
+void shard_peer_scatter_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, ShardPeerSend *st, const SpPeers *peers) {
+    int WS = (int) kp->words, W = (int) st->words;
+    if (WS == 1) return shard_peer_scatter_derive_w<1, 1>(ctx, kp, B, G, st, *peers);
+    if (WS == 2 && W == 1) return shard_peer_scatter_derive_w<2, 1>(ctx, kp, B, G, st, *peers);
+    if (WS == 2) return shard_peer_scatter_derive_w<2, 2>(ctx, kp, B, G, st, *peers);
+    if (WS == 3 && W == 2) return shard_peer_scatter_derive_w<3, 2>(ctx, kp, B, G, st, *peers);
+    if (WS == 3) return shard_peer_scatter_derive_w<3, 3>(ctx, kp, B, G, st, *peers);
+    if (WS == 4 && W == 3) return shard_peer_scatter_derive_w<4, 3>(ctx, kp, B, G, st, *peers);
+    return shard_peer_scatter_derive_w<4, 4>(ctx, kp, B, G, st, *peers);
+}
+
+// the coarse counts of every owner's part, stored into the heads of the owners' buffers
+void shard_peer_send_counts(sb200_ctx *ctx, unsigned G, const ShardPeerSend *st, uint32_t *const *dst) {
+    SpPeerCounts pc;
+    for (unsigned g = 0; g < 64; ++g) pc.dst[g] = g < G ? dst[g] : nullptr;
+    LAUNCH(ctx, sp_peer_counts_kernel, G, 128, 0, st->raw.p, st->pl.n_co, pc);
 }
 
 template<int WS, int W>
@@ -1104,7 +1246,7 @@ static sb200_records *shard_send_derive_w(sb200_ctx *ctx, const sb200_kmers *kp,
     r->data.alloc(ctx, n * W);
     if (side_pay) r->pay.alloc(ctx, n + 1);
     if (n) LAUNCH(ctx, sp_scatter_derive_kernel_, (unsigned) ctx->num_sms * 2, SP_THREADS, smem_s, kp->data.p, kp->size, k, pshift, gs, pl.s, n_bins, cur1.p,
-                  r->data.p, r->pay.p);
+                  r->data.p, r->pay.p, SpPeers());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return r.release();
 }

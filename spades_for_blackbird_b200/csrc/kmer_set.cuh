@@ -1,6 +1,8 @@
 // kmer_set.cuh — device-resident sorted-unique k-mer sets (the GPU counterpart of kmers::KMerDiskStorage,
 // C/utils/kmer_mph/kmer_index_builder.hpp:48-191) and the handles the C ABI passes around.
 #pragma once
+#include <memory>
+#include <vector>
 #include "common.cuh"
 
 struct sb200_reads {
@@ -90,6 +92,26 @@ namespace sb200 {
 struct ShardPlan {
     int p = 0, s = 0;              // value-prefix bits of the fine group key; fine groups per coarse bin = 2^s
     uint32_t n_go = 0, n_co = 0;   // fine groups / coarse bins per owner
+};
+// Hash-sharded sender (PEER instances of the pass-1 kernels): the runs of owner o's coarse bins are stored straight into o's receive
+// buffer — peer memory over NVLink (CUDA IPC mapping, or a plain pointer when the owner is this GPU) — instead of into a local send buffer
+// that an all-to-all would then move: the exchange IS the pass-1 kernel's output.  rec[o] / pay[o] point at the place of THIS rank's run
+// in owner o's buffer (the cursors are relative to it); bins are owner-major, n_co per owner.
+struct SpPeers {
+    uint64_t *rec[64];
+    uint8_t *pay[64];
+    uint32_t n_co;
+};
+
+// Sender state of a record exchange through peer stores (count.cu shard_peer_*): after the count pass every size is known, the
+// owners' buffers are addressed, and pass 1 writes into them.
+struct ShardPeerSend {
+    unsigned k = 0, words = 0;
+    bool double_palindromes = false, mask_payload = false, side_pay = false;
+    int pshift = -1;
+    ShardPlan pl;
+    DevBuf<uint32_t> raw;     // [G][n_co] records per (owner, coarse bin)
+    DevBuf<uint32_t> cur1;    // [G][n_co] pass-1 cursors, relative to this rank's run in the owner's buffer
 };
 // EarlyTipClipper in three steps (ext.cu): the kill list and the masks span the WHOLE index, the k-mers may be one GPU's shard
 struct TipClipState {

@@ -42,6 +42,11 @@ sb200_kmers *count_records(sb200_ctx *ctx, sb200_records *r, unsigned B, int wan
 bool shard_plan(sb200_ctx *ctx, unsigned W, uint64_t n_owner_est, unsigned B, unsigned G, unsigned K, ShardPlan *pl);
 sb200_records *shard_send_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
 sb200_records *shard_send_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
+ShardPeerSend *shard_peer_count_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned K, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
+ShardPeerSend *shard_peer_count_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, const ShardPlan *pl, uint64_t *owner_counts);
+void shard_peer_scatter_reads(sb200_ctx *ctx, const sb200_reads *rd, unsigned B, unsigned G, ShardPeerSend *st, const SpPeers *peers);
+void shard_peer_scatter_derive(sb200_ctx *ctx, const sb200_kmers *kp, unsigned B, unsigned G, ShardPeerSend *st, const SpPeers *peers);
+void shard_peer_send_counts(sb200_ctx *ctx, unsigned G, const ShardPeerSend *st, uint32_t *const *dst);
 sb200_kmers *shard_receive(sb200_ctx *ctx, sb200_records *got, const uint64_t *run_start, unsigned G, const ShardPlan *pl, unsigned B, unsigned first_bucket,
                            unsigned n_owned, int want_counts);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
@@ -141,6 +146,76 @@ static sb200_kmers *exchange_and_receive(sb200_ctx *ctx, sb200_comm *cm, std::un
     return shard_receive(ctx, got.get(), run_start.data(), (unsigned) G, &pl, B, (unsigned) cm->rank * n_owned, n_owned, want_counts ? 1 : 0);
 }
 
+// A record exchange with no exchange step: after the count pass every rank knows every size (one tiny all-gather), the owners' receive
+// buffers are peer-visible (sb200_comm::peer_buffers), and pass 1 of the grouping writes each owner's runs straight into the owner's HBM
+// over NVLink (SpPeers, staged_partition.cuh).  What remains is a barrier.  `reads` (first exchange: (k+1)-mer instances) or `kp` (second
+// exchange: k-mer candidates of the own (k+1)-mers).  *done = false: some pair of GPUs cannot map each other — the caller takes the
+// all-to-all path (and keeps taking it: the communicator remembers).
+static sb200_kmers *peer_exchange(sb200_ctx *ctx, sb200_comm *cm, int slot, const sb200_reads *reads, const sb200_kmers *kp, unsigned K, unsigned B,
+                                  const ShardPlan &pl, bool want_counts, bool *done) {
+    const int G = cm->size, me = cm->rank;
+    *done = false;
+    if (cm->peer_failed || ctx->no_peer_stores) return nullptr;
+    std::vector<uint64_t> counts((size_t) G, 0), all((size_t) G * G);
+    std::unique_ptr<ShardPeerSend> st(reads ? shard_peer_count_reads(ctx, reads, K, B, (unsigned) G, &pl, counts.data())
+                                            : shard_peer_count_derive(ctx, kp, B, (unsigned) G, &pl, counts.data()));
+    cm->all_gather_host(ctx, counts.data(), (size_t) G, all.data());
+    const uint64_t rb = (uint64_t) st->words * 8;
+    auto align256 = [](uint64_t v) { return (v + 255) & ~(uint64_t) 255; };
+    const uint64_t cc_bytes = align256((uint64_t) G * pl.n_co * 4);
+    uint64_t n_recv[64], dst_start[64], need[64];
+    for (int g = 0; g < G; ++g) {
+        n_recv[g] = 0; dst_start[g] = 0;
+        for (int src = 0; src < G; ++src) {
+            if (src == me) dst_start[g] = n_recv[g];
+            n_recv[g] += all[(size_t) src * G + g];
+        }
+        SB200_REQUIRE(n_recv[g] < (1ull << 32), "more than 2^32-1 k-mer instances on one GPU: use more GPUs");
+        need[g] = cc_bytes + align256(n_recv[g] * rb) + (st->side_pay ? align256(n_recv[g] + 4) : 0);
+    }
+    void *ptrs[64];
+    if (!cm->peer_buffers(ctx, slot, need, ptrs)) return nullptr;
+    SpPeers peers;
+    memset(&peers, 0, sizeof peers);
+    peers.n_co = pl.n_co;
+    uint32_t *cdst[64];
+    uint64_t out_bytes = 0;
+    for (int g = 0; g < G; ++g) {
+        uint8_t *base = (uint8_t *) ptrs[g];
+        cdst[g] = reinterpret_cast<uint32_t *>(base) + (uint64_t) me * pl.n_co;
+        peers.rec[g] = reinterpret_cast<uint64_t *>(base + cc_bytes + dst_start[g] * rb);
+        peers.pay[g] = st->side_pay ? base + cc_bytes + align256(n_recv[g] * rb) + dst_start[g] : nullptr;
+        if (g != me) out_bytes += counts[(size_t) g] * (rb + (st->side_pay ? 1 : 0)) + (uint64_t) pl.n_co * 4;
+    }
+    cudaEvent_t e0 = ctx->get_event(), e1 = ctx->get_event();
+    CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+    shard_peer_send_counts(ctx, (unsigned) G, st.get(), cdst);
+    if (reads) shard_peer_scatter_reads(ctx, reads, B, (unsigned) G, st.get(), &peers);
+    else shard_peer_scatter_derive(ctx, kp, B, (unsigned) G, st.get(), &peers);
+    CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));   // my stores have been performed at their owners
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ctx->event_pool.push_back(e0);
+    ctx->event_pool.push_back(e1);
+    cm->bytes_sent += out_bytes;
+    cm->exchange_ms += ms;
+    cm->barrier(ctx);                        // ... and everybody else's at mine
+    std::unique_ptr<sb200_records> got(new sb200_records());
+    got->ctx = ctx; got->k = st->k; got->words = st->words; got->n = n_recv[me];
+    got->double_palindromes = st->double_palindromes; got->mask_payload = st->mask_payload;
+    uint8_t *mine = (uint8_t *) ptrs[me];
+    got->coarse_counts.borrow(ctx, reinterpret_cast<uint32_t *>(mine), (size_t) G * pl.n_co);
+    got->data.borrow(ctx, reinterpret_cast<uint64_t *>(mine + cc_bytes), (size_t) (n_recv[me] * st->words));
+    if (st->side_pay) got->pay.borrow(ctx, mine + cc_bytes + align256(n_recv[me] * rb), (size_t) n_recv[me] + 1);
+    std::vector<uint64_t> run_start((size_t) G + 1, 0);
+    for (int src = 0; src < G; ++src) run_start[(size_t) src + 1] = run_start[(size_t) src] + all[(size_t) src * G + me];
+    st.reset();
+    *done = true;
+    const unsigned n_owned = B / (unsigned) G;
+    return shard_receive(ctx, got.get(), run_start.data(), (unsigned) G, &pl, B, (unsigned) me * n_owned, n_owned, want_counts ? 1 : 0);
+}
+
 static double now_ms() { return sb200_ctx::now_s() * 1e3; }
 
 static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb200_reads *reads, const sb200_construct_params *p, int gather_to) {
@@ -160,6 +235,16 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         res->stage_ms[stage] += t - t0;
         t0 = t;
     };
+    // SB200_SHARD_TRACE=1: rank 0 prints finer laps (each one synchronises the stream: a diagnostic, not the timed configuration)
+    const bool trace = me == 0 && getenv("SB200_SHARD_TRACE") != nullptr;
+    double tt = t0;
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const double t = now_ms();
+        fprintf(stderr, "[sb200 shard trace] %-28s %8.3f ms\n", what, t - tt);
+        tt = t;
+    };
 
     // ---- 1-2: (k+1)-mers ------------------------------------------------------------------------------------------------------
     // every rank must take the same grouping plan: it is sized from the job's instance estimate (tiny all-gather)
@@ -173,8 +258,15 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         std::vector<uint64_t> counts((size_t) G, 0);
         ShardPlan pl;
         if (shard_plan(ctx, (k + 1 + 31) / 32, n_owner_est, B, (unsigned) G, k + 1, &pl)) {
-            std::unique_ptr<sb200_records> rec(shard_send_reads(ctx, reads, k + 1, B, (unsigned) G, &pl, counts.data()));
-            res->kpomers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, true);
+            mark("plan (k+1)");
+            bool done = false;
+            if (G > 1) res->kpomers = peer_exchange(ctx, cm, 0, reads, nullptr, k + 1, B, pl, true, &done);
+            if (!done) {
+                std::unique_ptr<sb200_records> rec(shard_send_reads(ctx, reads, k + 1, B, (unsigned) G, &pl, counts.data()));
+                mark("send side (k+1)");
+                res->kpomers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, true);
+            }
+            mark("exchange + receive (k+1)");
         } else {
             std::unique_ptr<sb200_records> rec(extract_records_partitioned(ctx, reads, k + 1, 1, 1, B, (unsigned) G, counts.data()));
             res->kpomers = exchange_and_count(ctx, cm, std::move(rec), counts.data(), B, true);
@@ -189,8 +281,15 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         std::vector<uint64_t> counts((size_t) G, 0);
         ShardPlan pl;
         if (shard_plan(ctx, (k + 31) / 32, std::max<uint64_t>(2 * total / (uint64_t) G, 1), B, (unsigned) G, k, &pl)) {
-            std::unique_ptr<sb200_records> rec(shard_send_derive(ctx, res->kpomers, B, (unsigned) G, &pl, counts.data()));
-            res->kmers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, false);
+            mark("plan k");
+            bool done = false;
+            if (G > 1) res->kmers = peer_exchange(ctx, cm, 1, nullptr, res->kpomers, k, B, pl, false, &done);
+            if (!done) {
+                std::unique_ptr<sb200_records> rec(shard_send_derive(ctx, res->kpomers, B, (unsigned) G, &pl, counts.data()));
+                mark("send side k");
+                res->kmers = exchange_and_receive(ctx, cm, std::move(rec), counts.data(), B, pl, false);
+            }
+            mark("exchange + receive k");
         } else {
             std::unique_ptr<sb200_records> rec(derive_records(ctx, res->kpomers));
             partition_records(ctx, rec.get(), B, (unsigned) G, counts.data());
@@ -214,8 +313,10 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         SB200_REQUIRE(res->total_kmers > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     }
     // ---- 6: index ----------------------------------------------------------------------------------------------------------------------
+    mark("sizes");
     res->mphf = mphf_build(ctx, res->kmers, sizes.data());
     sb200_mphf *m = res->mphf;
+    mark("mphf build");
     if (G > 1) {
         std::vector<uint64_t> woff((size_t) G + 1), roff((size_t) G + 1);
         for (int g = 0; g <= G; ++g) {
@@ -226,7 +327,9 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         cm->all_gather_v_inplace(ctx, m->bits.p, woff.data());
         cm->all_gather_v_inplace(ctx, m->ranks.p, roff.data());
     }
+    mark("mphf slices");
     mphf_complete(ctx, m);
+    mark("mphf complete");
     lap(2);
     // ---- 7: masks ------------------------------------------------------------------------------------------------------------------------
     // The masks a rank's k-mer sort OR-ed together are complete for its own k-mers; if ANY rank's set came without them (no padding bits
@@ -238,7 +341,9 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         for (int g = 0; g < G; ++g) all_payload = all_payload && all[g];
         if (!all_payload) res->kmers->masks_file.release();
     }
+    mark("payload consensus");
     res->ext = build_ext(ctx, res->kpomers, res->kmers, m);
+    mark("build_ext");
     std::vector<uint64_t> idx_off((size_t) G + 1, 0);   // rank g's k-mers hold the MPHF indices [idx_off[g], idx_off[g + 1])
     for (int g = 0; g < G; ++g) {
         uint64_t s = 0;
@@ -249,6 +354,7 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         if (all_payload) cm->all_gather_v_inplace(ctx, res->ext->masks.p, idx_off.data());
         else cm->all_reduce_or_bytes(ctx, res->ext->masks.p, res->ext->size, false);
     }
+    mark("mask slices");
     lap(3);
     // ---- 8: tip clipper --------------------------------------------------------------------------------------------------------------------
     if (p->tip_clip) {
@@ -266,6 +372,7 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     // ---- 9: unitigs -------------------------------------------------------------------------------------------------------------------------
     uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
     res->unitigs = extract_unitigs_local(ctx, res->kmers, m, res->ext, stats);
+    mark("local walks");
     res->walk_stats.assign((size_t) G * 6, 0);
     cm->all_gather_host(ctx, stats, 6, res->walk_stats.data());
     uint64_t chain_seen = 0, long_chains = 0;
@@ -311,6 +418,7 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
             res->total_unitigs += all[3 * g]; res->total_unitig_bases += all[3 * g + 1]; res->n_loops += all[3 * g + 2];
         }
     }
+    mark("walk consensus");
     lap(5);
     // ---- 10: gather ---------------------------------------------------------------------------------------------------------------------------
     if (gather_to >= 0 && G > 1 && !res->whole_set_fallback) {

@@ -73,11 +73,13 @@ __device__ __forceinline__ void sp_stage_reset(const SpStage &st, uint32_t n_bin
     for (uint32_t b = threadIdx.x; b <= n_bins; b += SP_THREADS) st.bstart[b] = 0;
 }
 
+// (SpPeers — the owners' receive buffers the PEER instances store through — is declared in kmer_set.cuh)
 // Orders the n staged records by local bin and writes every bin's run to out[] at a position claimed from gcursor[first_bin + bin].
 // All threads of the CTA call it after a barrier that follows the last sp_put; the stage may be reset and refilled when it returns.
-template<int W>
+template<int W, bool PEER = false>
 __device__ __forceinline__ void sp_flush(const SpStage &st, uint32_t n, uint32_t n_bins, uint32_t *__restrict__ gcursor, uint32_t first_bin,
-                                         uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay, uint32_t *s_scan) {
+                                         uint64_t *__restrict__ out, uint8_t *__restrict__ out_pay, uint32_t *s_scan,
+                                         const SpPeers *peers = nullptr, uint8_t *s_own = nullptr) {
     // (the bin counts were accumulated in st.bstart while the tile was filled: sp_put / sp_stage_reset)
     {   // exclusive scan of up to 1024 bin counts: two per thread
         const uint32_t b0 = 2u * threadIdx.x, b1 = b0 + 1u;
@@ -96,7 +98,10 @@ __device__ __forceinline__ void sp_flush(const SpStage &st, uint32_t n, uint32_t
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < n_bins; b += SP_THREADS) {   // one global atomic per non-empty bin of the tile
         const uint32_t c = st.cursor[b];
-        if (c) st.gdelta[b] = atomicAdd(&gcursor[first_bin + b], c) - st.bstart[b];
+        if (c) {
+            st.gdelta[b] = atomicAdd(&gcursor[first_bin + b], c) - st.bstart[b];
+            if (PEER) s_own[b] = (uint8_t) ((first_bin + b) / peers->n_co);
+        }
     }
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < n; d += SP_THREADS) {        // consecutive d of one bin -> consecutive records in HBM
@@ -114,8 +119,14 @@ __device__ __forceinline__ void sp_flush(const SpStage &st, uint32_t n, uint32_t
 #pragma unroll
             for (int j = 0; j < W; ++j) r[j] = st.rec[(size_t) q * W + j];
         }
-        store_rec<W>(out, g, r);
-        if (out_pay) out_pay[g] = st.pay[q];
+        if (PEER) {
+            const uint32_t o = s_own[st.bin[q]];
+            store_rec<W>(peers->rec[o], g, r);
+            if (st.pay) peers->pay[o][g] = st.pay[q];
+        } else {
+            store_rec<W>(out, g, r);
+            if (out_pay) out_pay[g] = st.pay[q];
+        }
     }
     __syncthreads();
 }
@@ -240,13 +251,14 @@ __global__ void __launch_bounds__(SPC_THREADS) sp_count_reads_kernel(const uint6
 }
 
 // pass 1: tiles of <= rounds x 16 chunks, ordered by coarse bin c = g >> s, runs written at the bins' cursors
-template<int W>
+template<int W, bool PEER = false>
 __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ word_off,
                                                                      const uint32_t *__restrict__ len, uint64_t n_reads, int K, int mode, GroupSel gs,
                                                                      int s, uint32_t n_coarse, int rounds, uint32_t *__restrict__ gcursor,
-                                                                     uint64_t *__restrict__ out) {
+                                                                     uint64_t *__restrict__ out, const __grid_constant__ SpPeers peers) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ uint32_t s_fill, s_scan[SP_THREADS / 32 + 1];
+    __shared__ uint8_t s_own[PEER ? SP_MAX_BINS : 4];
     const SpStage st = sp_carve<W>(sp_smem, SpCfg<W>::CAP, false);
     const int lane = threadIdx.x & 31;
     const uint64_t warps_total = (uint64_t) gridDim.x * SP_WARPS;
@@ -280,7 +292,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_reads_kernel(const u
         }
         __syncthreads();
         const uint32_t n = s_fill;
-        if (n) sp_flush<W>(st, n, n_coarse, gcursor, 0u, out, nullptr, s_scan);
+        if (n) sp_flush<W, PEER>(st, n, n_coarse, gcursor, 0u, out, nullptr, s_scan, &peers, s_own);
         if (__syncthreads_and(exhausted ? 1 : 0)) break;
     }
 }
@@ -308,12 +320,13 @@ __global__ void __launch_bounds__(SPC_THREADS) sp_count_derive_kernel(const uint
     }
 }
 
-template<int WS, int W>
+template<int WS, int W, bool PEER = false>
 __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_derive_kernel(const uint64_t *__restrict__ kp, uint64_t n, int k, int pshift, GroupSel gs, int s,
                                                                       uint32_t n_coarse, uint32_t *__restrict__ gcursor, uint64_t *__restrict__ out,
-                                                                      uint8_t *__restrict__ out_pay) {
+                                                                      uint8_t *__restrict__ out_pay, const __grid_constant__ SpPeers peers) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ uint32_t s_scan[SP_THREADS / 32 + 1];
+    __shared__ uint8_t s_own[PEER ? SP_MAX_BINS : 4];
     constexpr int CAP = SpCfg<W>::CAP;
     constexpr uint64_t SRC_PER_TILE = CAP / 2;
     const SpStage st = sp_carve<W>(sp_smem, CAP, out_pay != nullptr);
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sp_scatter_derive_kernel(const 
             sp_put<W>(st, 2 * j + 1, a[1], g1 >> s);
         }
         __syncthreads();
-        sp_flush<W>(st, 2 * cnt, n_coarse, gcursor, 0u, out, out_pay, s_scan);
+        sp_flush<W, PEER>(st, 2 * cnt, n_coarse, gcursor, 0u, out, out_pay, s_scan, &peers, s_own);
     }
 }
 

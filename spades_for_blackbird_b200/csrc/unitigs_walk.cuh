@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t walk_mask(const MphfDev &m, const uint8_t *_
 
 // Builds the walk blocks (mphf.cuh) from the complete index and the masks in index order: one thread per 16-byte piece of a line.
 __global__ void __launch_bounds__(256) walk_blocks_kernel(const uint64_t *__restrict__ bits, const uint32_t *__restrict__ pc_scan, uint64_t words,
-                                                         const uint8_t *__restrict__ masks, uint64_t n_lines, uint4 *__restrict__ out) {
+                                                         const uint8_t *__restrict__ masks, uint64_t n_masks, uint64_t n_lines, uint4 *__restrict__ out) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t line = t >> 3;
     if (line >= n_lines) return;
@@ -48,10 +48,27 @@ __global__ void __launch_bounds__(256) walk_blocks_kernel(const uint64_t *__rest
         u.d[2] = rank | (spill ? 0x80000000u : 0u);
         mfirst = 12;
     }
-    if (!spill) {
-        const int j0 = (int) piece * 16 - (int) (8 * WB_WORDS + 4);   // mask number of byte 0 of this piece
-        for (int i = mfirst; i < 16; ++i)
-            if ((uint32_t) (j0 + i) < cnt) u.b[i] = __ldg(masks + rank + (uint32_t) (j0 + i));
+    const int j0 = (int) piece * 16 - (int) (8 * WB_WORDS + 4);   // mask number of byte 0 of this piece
+    if (!spill && j0 + 16 > 0 && j0 + mfirst < (int) cnt) {
+        // bytes [o, o + 16) of the mask array through aligned 32-bit loads and funnel shifts (o may be negative in piece 1: those bytes
+        // are overwritten below), then cut to the masks of this line
+        const int64_t o = (int64_t) rank + j0;
+        const int64_t a = o & ~(int64_t) 3;
+        const uint32_t sh = (uint32_t) (o & 3) * 8;
+        const uint32_t *mw = reinterpret_cast<const uint32_t *>(masks);
+        const int64_t last = (int64_t) ((n_masks + 3) / 4);   // the array is padded to a multiple of 4 bytes
+        uint32_t w[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int64_t wi = a / 4 + q;
+            w[q] = (wi >= 0 && wi < last) ? __ldg(mw + wi) : 0u;
+        }
+        union { uint4 v; uint32_t d[4]; uint8_t b[16]; } mk;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk.d[q] = __funnelshift_r(w[q], w[q + 1], sh);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i >= mfirst && (uint32_t) (j0 + i) < cnt) u.b[i] = mk.b[i];
     }
     out[t] = u.v;
 }
@@ -541,8 +558,20 @@ __global__ void __launch_bounds__(256) walk_emit_kernel(MphfDev m, const uint64_
 __global__ void __launch_bounds__(256) count_nonjunction_kernel(const uint8_t *__restrict__ masks, uint64_t n, unsigned long long *__restrict__ total) {
     __shared__ uint32_t sm[256 / 32 + 1];
     uint32_t c = 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
-        c += mask_is_junction(masks[i]) ? 0u : 1u;
+    // 16 masks per load (cudaMalloc'ed arrays are 256-byte aligned), the tail byte by byte
+    const uint64_t n16 = n / 16, tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t) gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15u) == 0;
+    if (aligned) {
+        for (uint64_t i = tid; i < n16; i += nth) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(masks) + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) c += mask_is_junction((w[q] >> (8 * b)) & 255u) ? 0u : 1u;
+        }
+    }
+    for (uint64_t i = (aligned ? n16 * 16 : 0) + tid; i < n; i += nth) c += mask_is_junction(masks[i]) ? 0u : 1u;
     uint32_t block_total;
     block_exclusive_scan<uint32_t, 256>(c, &block_total, sm);
     if (threadIdx.x == 0 && block_total) atomicAdd(total, (unsigned long long) block_total);   // one atomic per CTA
@@ -607,7 +636,7 @@ static sb200_unitigs *unitigs_walk_w(sb200_ctx *ctx, const sb200_kmers *kmers, c
         // lookup walks: index bits, rank and masks of a step in one 128-byte line (mphf.cuh)
         const uint64_t n_lines = div_up(mphf->total_words, WB_WORDS);
         wblk.alloc(ctx, n_lines * 8);
-        LAUNCH(ctx, walk_blocks_kernel, div_up(n_lines * 8, 256), 256, 0, mphf->bits.p, mphf->pc_scan.p, mphf->total_words, ext->masks.p, n_lines, wblk.p);
+        LAUNCH(ctx, walk_blocks_kernel, div_up(n_lines * 8, 256), 256, 0, mphf->bits.p, mphf->pc_scan.p, mphf->total_words, ext->masks.p, ext->size, n_lines, wblk.p);
         m.wblk = reinterpret_cast<const uint64_t *>(wblk.p);
     }
     if (n_e) {

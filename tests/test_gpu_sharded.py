@@ -125,7 +125,8 @@ def test_sharded_no_kmers_fails_on_every_rank():
         run_sharded(2, ["ACGT", "GGCA"], 21, 4)
 
 
-@pytest.mark.parametrize("env", ["SB200_COUNTING_PASSES", "SB200_COUNTING_PASSES,SB200_NO_FUSED_PARTITION", "SB200_NO_PLACE", "SB200_NO_MASK_PAYLOAD"])
+@pytest.mark.parametrize("env", ["SB200_COUNTING_PASSES", "SB200_COUNTING_PASSES,SB200_NO_FUSED_PARTITION", "SB200_NO_PLACE", "SB200_NO_MASK_PAYLOAD",
+                                 "SB200_NO_PEER_STORES"])
 def test_sharded_alternative_paths_agree(monkeypatch, env):
     """The sharded path with one of its shortcuts switched off — the staged sender / receiver kernels (then: round 1's extraction straight
     into the owner groups + the owner's counting passes; with NO_FUSED_PARTITION: extract, partition pass), k-mer indices from the build's
@@ -138,7 +139,7 @@ def test_sharded_alternative_paths_agree(monkeypatch, env):
     want = dict(kpomers=w["kpomers"].data.reshape(-1), coverage=w["kpomers"].counts, kmers=w["kmers"].data.reshape(-1), idx=w["idx"],
                 masks_idx=w["masks_idx"], index_bin=w["index_bin"], unitigs=w["unitigs"])
     for e in env.split(","):
-        monkeypatch.setenv(e, "1")
+        monkeypatch.setenv(e.split("=")[0], e.split("=")[1] if "=" in e else "1")
     res = run_sharded(G, reads, k, nb)
     check(res, want, G, nb)
 
