@@ -19,8 +19,12 @@
 // beyond that the fail flag sends the set to the LSD path (radix_sort.cuh).
 // Groups of 65535+ records need 64-bit slot words: the 32-bit instance skips them and raises ctrl[1], the host then launches the
 // 64-bit instance for those groups only.
-// The phases are separate __noinline__ functions on purpose: as one function body nvcc 12.9 -O3 produced code that lost shared-memory
-// updates between phases (correct at -G, -Xcicc -O0 and -Xptxas -O0; tools/gh_test.cu is the harness that showed it).
+// The phases are separate __noinline__ functions on purpose.  What is known (profiles/r2s_gh_test_variants.log, r2t_pytest_inline_variant.log):
+// built with the phases inlined (-DGH_INLINE_PHASES) the kernel passes the stand-alone harness (tools/gh_test.cu: W = 2, counting mode) and
+// 142 of the GPU tests, but the plain-dedup instance (MODE 0: k-mers without mask payload, tests/test_gpu_sharded.py
+// [SB200_NO_MASK_PAYLOAD]) dies with "misaligned address"; as separate functions every instance passes the whole suite.  Whether the
+// inlined form exposes a flaw of this code or of nvcc 12.9's code generation is open: compute-sanitizer (racecheck / memcheck) is closed
+// on the pool this was developed on.  The inlined form is 2 % faster (7.04 against 7.19 ms per step at config 2), not worth the doubt.
 #pragma once
 #include "common.cuh"
 #include "kmer_ops.cuh"
