@@ -271,31 +271,43 @@ bool sb200_comm::peer_buffers(sb200_ctx *ctx, int slot, const uint64_t *need, vo
 }
 
 void sb200_comm::all_gather_v_inplace(sb200_ctx *ctx, void *buf, const uint64_t *off) {
+    void *bufs[1] = {buf};
+    const uint64_t *offs[1] = {off};
+    all_gather_v_inplace_multi(ctx, 1, bufs, offs);
+}
+
+void sb200_comm::all_gather_v_inplace_multi(sb200_ctx *ctx, int n_bufs, void *const *bufs, const uint64_t *const *offs) {
     if (size == 1) return;
-    uint8_t *b = (uint8_t *) buf;
-    bytes_sent += (off[rank + 1] - off[rank]) * (uint64_t) (size - 1);
+    for (int i = 0; i < n_bufs; ++i) bytes_sent += (offs[i][rank + 1] - offs[i][rank]) * (uint64_t) (size - 1);
     if (local) {
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        local->ptr[(size_t) rank] = buf;
-        local->barrier();
-        for (int r = 0; r < size; ++r) {
-            const uint64_t bytes = off[r + 1] - off[r];
-            if (r != rank && bytes)
-                CUDA_CHECK(cudaMemcpyAsync(b + off[r], (const uint8_t *) local->ptr[(size_t) r] + off[r], bytes, cudaMemcpyDefault, ctx->stream));
+        for (int i = 0; i < n_bufs; ++i) {
+            uint8_t *b = (uint8_t *) bufs[i];
+            const uint64_t *off = offs[i];
+            local->ptr[(size_t) rank] = b;
+            local->barrier();
+            for (int r = 0; r < size; ++r) {
+                const uint64_t bytes = off[r + 1] - off[r];
+                if (r != rank && bytes)
+                    CUDA_CHECK(cudaMemcpyAsync(b + off[r], (const uint8_t *) local->ptr[(size_t) r] + off[r], bytes, cudaMemcpyDefault, ctx->stream));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            local->barrier();
         }
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        local->barrier();
         return;
     }
-    // point-to-point in one group: every rank hands its slice to every peer and takes theirs — NVSwitch carries all pairs at once
-    // (a group of `size` broadcasts ran at about a third of the all-to-all's bandwidth, profiles/r2n)
-    const uint64_t mine = off[rank + 1] - off[rank];
+    // point-to-point in one group: every rank hands its slices to every peer and takes theirs — NVSwitch carries all pairs at once
     NCCL_CHECK(nccl_api().GroupStart());
-    for (int d = 1; d < size; ++d) {
-        const int to = (rank + d) % size, from = (rank - d + size) % size;
-        const uint64_t nb = off[from + 1] - off[from];
-        if (mine) NCCL_CHECK(nccl_api().Send(b + off[rank], mine, ncclUint8, to, (ncclComm_t) nccl, ctx->stream));
-        if (nb) NCCL_CHECK(nccl_api().Recv(b + off[from], nb, ncclUint8, from, (ncclComm_t) nccl, ctx->stream));
+    for (int i = 0; i < n_bufs; ++i) {
+        uint8_t *b = (uint8_t *) bufs[i];
+        const uint64_t *off = offs[i];
+        const uint64_t mine = off[rank + 1] - off[rank];
+        for (int d = 1; d < size; ++d) {
+            const int to = (rank + d) % size, from = (rank - d + size) % size;
+            const uint64_t nb = off[from + 1] - off[from];
+            if (mine) NCCL_CHECK(nccl_api().Send(b + off[rank], mine, ncclUint8, to, (ncclComm_t) nccl, ctx->stream));
+            if (nb) NCCL_CHECK(nccl_api().Recv(b + off[from], nb, ncclUint8, from, (ncclComm_t) nccl, ctx->stream));
+        }
     }
     NCCL_CHECK(nccl_api().GroupEnd());
 }

@@ -61,6 +61,8 @@ struct sb200_comm {
     bool peer_buffers(sb200_ctx *ctx, int slot, const uint64_t *need, void **ptrs);
     // every rank holds the same layout; rank r's slice buf[off[r], off[r + 1]) is valid on r and is copied to everybody else (bytes)
     void all_gather_v_inplace(sb200_ctx *ctx, void *buf, const uint64_t *off);
+    // the same for several buffers in ONE exchange (one NCCL group: one kernel, one handshake)
+    void all_gather_v_inplace_multi(sb200_ctx *ctx, int n_bufs, void *const *bufs, const uint64_t *const *offs);
     // rank r's `bytes` bytes land at recv[recv_off[r] ...) on `root` (recv / recv_off only read on root)
     void gather_v(sb200_ctx *ctx, const void *send, uint64_t bytes, void *recv, const uint64_t *recv_off, int root);
     // element-wise OR of byte arrays over all ranks, in place (buffers are readable up to the next multiple of 4 bytes).  NCCL has no OR:

@@ -210,9 +210,9 @@ __global__ void mphf_clear_popc_kernel(unsigned long long *__restrict__ bits, co
 
 // one block per (bucket, level): rank sample j = set bits in the bucket's words before word 8j of this level
 __global__ void mphf_ranks_kernel(const uint32_t *__restrict__ pc_scan, const uint64_t *__restrict__ word_off,
-                                  const uint64_t *__restrict__ rank_off, const uint64_t *__restrict__ nchar, uint64_t n_levels_total,
+                                  const uint64_t *__restrict__ rank_off, const uint64_t *__restrict__ nchar, uint64_t t0, uint64_t n_levels_total,
                                   uint64_t *__restrict__ ranks) {
-    uint64_t t = blockIdx.x;
+    uint64_t t = t0 + blockIdx.x;
     if (t >= n_levels_total) return;
     uint64_t nc = nchar[t];
     if (nc == 0) return;
@@ -230,8 +230,17 @@ __global__ void mphf_bucket_ends_kernel(const uint32_t *__restrict__ pc_scan, co
     ends[b] = pc_scan[b < B ? word_off[(uint64_t) b * MPHF_LEVELS] : total_words];
 }
 
+__global__ void add_u32_kernel(uint32_t *__restrict__ a, uint64_t n, uint32_t v) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += v;
+}
+
+// slice_only (sharded construction, shard.cu): only the words of the shard's own buckets are initialised and processed — every other
+// rank's slice arrives with the all-gather — and pc_scan is valid over the own slice at once (local prefix + the keys of all buckets
+// before it), so that the shard's k-mers get their MPHF indices BEFORE the exchange.  Without it the foreign slices are zero: the
+// contract of sb200_mphf_build_sharded ("sum the arrays over the GPUs").
 template<int W>
-static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) {
+static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes, bool slice_only) {
     // global_sizes != nullptr: `ks` is one GPU's shard (whole buckets); level geometry, rank offsets and segment starts are laid
     // out for ALL buckets, only the shard's keys are inserted.  Bit-vectors and rank samples of different shards are then
     // disjoint, so summing the arrays over the GPUs (all-reduce) yields exactly the single-GPU index.
@@ -290,9 +299,29 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     CUDA_CHECK(cudaMemcpyAsync(m->rank_off.p, m->rank_off_host.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(nchar_dev.p, nchar.data(), NL * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(m->segment_starts.p, m->segment_starts_host.data(), ((size_t) B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    m->bits.alloc(ctx, words + 1); m->bits.zero();
+    // own word range [w0, w1): the buckets this table holds keys of
+    uint64_t w0 = 0, w1 = words;
+    uint32_t b_lo = 0, b_hi = B;
+    if (slice_only) {
+        b_lo = B; b_hi = 0;
+        for (uint32_t b = 0; b < B; ++b)
+            if (ks->bucket_starts_host[b + 1] > ks->bucket_starts_host[b]) { b_lo = std::min(b_lo, b); b_hi = std::max(b_hi, b + 1); }
+        if (b_lo >= b_hi) { b_lo = b_hi = 0; w0 = w1 = 0; }
+        else {
+            w0 = m->word_off_host[(size_t) b_lo * MPHF_LEVELS];
+            w1 = b_hi < B ? m->word_off_host[(size_t) b_hi * MPHF_LEVELS] : words;
+        }
+    }
+    const uint64_t own = w1 - w0;
+    m->bits.alloc(ctx, words + 1);
     m->ranks.alloc(ctx, ranks + 1);
-    DevBuf<uint64_t> coll(ctx, words + 1); coll.zero();
+    DevBuf<uint64_t> coll(ctx, own + 1);
+    coll.zero();
+    if (slice_only) {
+        CUDA_CHECK(cudaMemsetAsync(m->bits.p + w0, 0, own * 8, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(m->bits.p + words, 0, 8, ctx->stream));
+    } else m->bits.zero();
+    uint64_t *coll_base = coll.p - w0;   // indexed by global word like `bits` (only [w0, w1] is ever touched)
 
     uint64_t n = ks->size;
     // whole-table build with 32-bit bit positions: remember where every key lands (see sb200_mphf::place)
@@ -312,10 +341,10 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
         act_a.alloc(ctx, cap_a); act_b.alloc(ctx, cap_a);
         counters.zero();
         LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
-               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, (ActiveKey *) nullptr);
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll_base, (ActiveKey *) nullptr);
         auto mphf_level1_kernel_ = mphf_level1_kernel<W>;
         LAUNCH(ctx, mphf_level1_kernel_, grid, 256, 0, ks->data.p, n, B, act_a.p, counters.p + 1, m->domain.p, m->word_off.p,
-               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll_base, m->place.p);
         src = act_a.p; dst = act_b.p;
         first_level = 2;
     }
@@ -324,13 +353,13 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
         counters.zero();
         CUDA_CHECK(cudaMemcpyAsync(counters.p, &n32, 4, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(ctx, mphf_level0_kernel<W>, div_up(n, 256), 256, 0, ks->data.p, n, B, m->domain.p, m->word_off.p,
-               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, act_a.p);
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll_base, act_a.p);
         src = act_a.p; dst = act_b.p;
     }
     if (!n) counters.zero();
     for (int l = first_level; l < MPHF_LEVELS && n; ++l) {   // (a rank that owns no k-mer at all only contributes zeroed arrays)
         LAUNCH(ctx, mphf_level_kernel, grid, 256, 0, l, src, counters.p + (l - 1), dst, counters.p + l, m->domain.p, m->word_off.p,
-               (unsigned long long *) m->bits.p, (unsigned long long *) coll.p, m->place.p);
+               (unsigned long long *) m->bits.p, (unsigned long long *) coll_base, m->place.p);
         std::swap(src, dst);
     }
     uint32_t final_keys = 0;
@@ -340,18 +369,26 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     if (keep_place) m->pc_scan.alloc(ctx, words + 1);
     else pc.alloc(ctx, words + 1);
     uint32_t *pcp = keep_place ? m->pc_scan.p : pc.p;
-    LAUNCH(ctx, mphf_clear_popc_kernel, div_up(words + 1, 256), 256, 0, (unsigned long long *) m->bits.p,
-           (const unsigned long long *) coll.p, words + 1, pcp);
-    exclusive_scan<uint32_t>(ctx, pcp, words + 1, nullptr);
+    // (entry w1 is the scan's total: a zero input; for a slice it lies in the next rank's region, rebuilt by mphf_complete)
+    LAUNCH(ctx, mphf_clear_popc_kernel, div_up(own + 1, 256), 256, 0, (unsigned long long *) m->bits.p + w0,
+           (const unsigned long long *) coll.p, own + 1, pcp + w0);
+    if (slice_only) CUDA_CHECK(cudaMemsetAsync(pcp + w1, 0, 4, ctx->stream));
+    exclusive_scan<uint32_t>(ctx, pcp + w0, own + 1, nullptr);
+    if (slice_only && own && m->segment_starts_host[b_lo])
+        LAUNCH(ctx, add_u32_kernel, div_up(own + 1, 256), 256, 0, pcp + w0, own + 1, (uint32_t) m->segment_starts_host[b_lo]);
     CUDA_CHECK(cudaMemsetAsync(m->ranks.p, 0, (ranks + 1) * 8, ctx->stream));   // buckets without keys here (other GPUs' shards) leave no garbage
-    LAUNCH(ctx, mphf_ranks_kernel, (unsigned) NL, 128, 0, pcp, m->word_off.p, m->rank_off.p, nchar_dev.p, (uint64_t) NL, m->ranks.p);
-    // _lastbitsetrank per bucket = set bits of the whole bucket
-    std::vector<uint32_t> ends(B + 1, 0);
-    DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
-    LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pcp, m->word_off.p, B, words, ends_dev.p);
-    ctx->fetch(ends.data(), ends_dev.p, ((size_t) B + 1) * 4);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];
+    if (b_hi > b_lo)
+        LAUNCH(ctx, mphf_ranks_kernel, (unsigned) ((b_hi - b_lo) * MPHF_LEVELS), 128, 0, pcp, m->word_off.p, m->rank_off.p, nchar_dev.p,
+               (uint64_t) b_lo * MPHF_LEVELS, (uint64_t) b_hi * MPHF_LEVELS, m->ranks.p);
+    // _lastbitsetrank per bucket = set bits of the whole bucket (a slice: mphf_complete fills them in once the index is whole)
+    if (!slice_only) {
+        std::vector<uint32_t> ends(B + 1, 0);
+        DevBuf<uint32_t> ends_dev(ctx, (size_t) B + 1);
+        LAUNCH(ctx, mphf_bucket_ends_kernel, div_up((uint64_t) B + 1, 256), 256, 0, pcp, m->word_off.p, B, words, ends_dev.p);
+        ctx->fetch(ends.data(), ends_dev.p, ((size_t) B + 1) * 4);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t b = 0; b < B; ++b) m->lastbitsetrank_host[b] = ends[b + 1] - ends[b];
+    } else CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     m->final_level_keys = final_keys;
     if (final_keys != 0) {
         delete m;
@@ -360,14 +397,16 @@ static sb200_mphf *mphf_build_w(sb200_ctx *ctx, const sb200_kmers *ks, const uin
     return m;
 }
 
-sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) {
+static sb200_mphf *mphf_build_any(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes, bool slice_only) {
     switch (ks->words) {
-        case 1: return mphf_build_w<1>(ctx, ks, global_sizes);
-        case 2: return mphf_build_w<2>(ctx, ks, global_sizes);
-        case 3: return mphf_build_w<3>(ctx, ks, global_sizes);
-        default: return mphf_build_w<4>(ctx, ks, global_sizes);
+        case 1: return mphf_build_w<1>(ctx, ks, global_sizes, slice_only);
+        case 2: return mphf_build_w<2>(ctx, ks, global_sizes, slice_only);
+        case 3: return mphf_build_w<3>(ctx, ks, global_sizes, slice_only);
+        default: return mphf_build_w<4>(ctx, ks, global_sizes, slice_only);
     }
 }
+sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) { return mphf_build_any(ctx, ks, global_sizes, false); }
+sb200_mphf *mphf_build_slice(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes) { return mphf_build_any(ctx, ks, global_sizes, true); }
 
 __global__ void mphf_popc_kernel(const uint64_t *__restrict__ bits, uint64_t nwords, uint32_t *__restrict__ pc) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;

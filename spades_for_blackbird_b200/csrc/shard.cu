@@ -31,6 +31,7 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "graph.cuh"
+#include "scan.cuh"
 #include "kmer_set.cuh"
 
 namespace sb200 {
@@ -50,6 +51,7 @@ void shard_peer_send_counts(sb200_ctx *ctx, unsigned G, const ShardPeerSend *st,
 sb200_kmers *shard_receive(sb200_ctx *ctx, sb200_records *got, const uint64_t *run_start, unsigned G, const ShardPlan *pl, unsigned B, unsigned first_bucket,
                            unsigned n_owned, int want_counts);
 sb200_mphf *mphf_build(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
+sb200_mphf *mphf_build_slice(sb200_ctx *ctx, const sb200_kmers *ks, const uint64_t *global_sizes);
 void mphf_complete(sb200_ctx *ctx, sb200_mphf *m);
 sb200_ext *build_ext(sb200_ctx *ctx, const sb200_kmers *kpomers, const sb200_kmers *kmers, const sb200_mphf *mphf);
 sb200_ext *build_ext_from_masks(sb200_ctx *ctx, const sb200_kmers *kmers, const sb200_mphf *mphf, const uint8_t *masks_dev);
@@ -299,8 +301,10 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     lap(1);
     // ---- 5: global sizes -------------------------------------------------------------------------------------------------------------
     std::vector<uint64_t> sizes((size_t) B, 0);   // k-mers per bucket, all buckets
+    bool all_payload = true;
     {
-        std::vector<uint64_t> mine((size_t) n_owned + 3, 0), all(((size_t) n_owned + 3) * G);
+        std::vector<uint64_t> mine((size_t) n_owned + 4, 0), all(((size_t) n_owned + 4) * G);
+        mine[(size_t) n_owned + 3] = res->kmers->masks_file.p ? 1 : 0;   // (see 6-7)
         for (unsigned b = 0; b < n_owned; ++b)
             mine[b] = res->kmers->bucket_starts_host[(size_t) first_bucket + b + 1] - res->kmers->bucket_starts_host[(size_t) first_bucket + b];
         mine[n_owned] = res->kpomers->size; mine[(size_t) n_owned + 1] = res->kpomers->instances; mine[(size_t) n_owned + 2] = res->kmers->size;
@@ -309,52 +313,51 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
             const uint64_t *row = all.data() + (size_t) g * mine.size();
             for (unsigned b = 0; b < n_owned; ++b) sizes[(size_t) g * n_owned + b] = row[b];
             res->total_kpomers += row[n_owned]; res->total_instances += row[(size_t) n_owned + 1]; res->total_kmers += row[(size_t) n_owned + 2];
+            all_payload = all_payload && row[(size_t) n_owned + 3];
         }
         SB200_REQUIRE(res->total_kmers > 0, "No kmers were extracted from reads. Check the read lengths and k-mer length settings");
     }
-    // ---- 6: index ----------------------------------------------------------------------------------------------------------------------
-    mark("sizes");
-    res->mphf = mphf_build(ctx, res->kmers, sizes.data());
-    sb200_mphf *m = res->mphf;
-    mark("mphf build");
-    if (G > 1) {
-        std::vector<uint64_t> woff((size_t) G + 1), roff((size_t) G + 1);
-        for (int g = 0; g <= G; ++g) {
-            const size_t t = (size_t) g * n_owned * 25;   // first (bucket, level) entry of rank g's buckets (mphf.cuh MPHF_LEVELS)
-            woff[(size_t) g] = 8 * (g < G ? m->word_off_host[t] : m->total_words);
-            roff[(size_t) g] = 8 * (g < G ? m->rank_off_host[t] : m->total_ranks);
-        }
-        cm->all_gather_v_inplace(ctx, m->bits.p, woff.data());
-        cm->all_gather_v_inplace(ctx, m->ranks.p, roff.data());
-    }
-    mark("mphf slices");
-    mphf_complete(ctx, m);
-    mark("mphf complete");
-    lap(2);
-    // ---- 7: masks ------------------------------------------------------------------------------------------------------------------------
+    // ---- 6-7: index + masks ----------------------------------------------------------------------------------------------------------
+    // Every rank builds the BooPHF levels of its own buckets inside the global layout (only its own slice of the arrays is touched) and
+    // — the slice's ranks being final at once — moves its k-mers' mask bytes to MPHF order right away; ONE exchange then completes
+    // bit-vectors, rank samples and masks on every GPU.
     // The masks a rank's k-mer sort OR-ed together are complete for its own k-mers; if ANY rank's set came without them (no padding bits
     // for this k, or its groups overflowed into the LSD path), every rank fills by lookups instead — a mix would leave holes.
-    bool all_payload = true;
-    {
-        uint64_t have = res->kmers->masks_file.p ? 1 : 0, all[64];
-        cm->all_gather_host(ctx, &have, 1, all);
-        for (int g = 0; g < G; ++g) all_payload = all_payload && all[g];
-        if (!all_payload) res->kmers->masks_file.release();
+    if (!all_payload) res->kmers->masks_file.release();
+    mark("sizes + payload consensus");
+    res->mphf = mphf_build_slice(ctx, res->kmers, sizes.data());
+    sb200_mphf *m = res->mphf;
+    mark("mphf build");
+    std::vector<uint64_t> woff((size_t) G + 1), roff((size_t) G + 1), idx_off((size_t) G + 1, 0);
+    for (int g = 0; g <= G; ++g) {
+        const size_t t = (size_t) g * n_owned * 25;   // first (bucket, level) entry of rank g's buckets (mphf.cuh MPHF_LEVELS)
+        woff[(size_t) g] = 8 * (g < G ? m->word_off_host[t] : m->total_words);
+        roff[(size_t) g] = 8 * (g < G ? m->rank_off_host[t] : m->total_ranks);
     }
-    mark("payload consensus");
-    res->ext = build_ext(ctx, res->kpomers, res->kmers, m);
-    mark("build_ext");
-    std::vector<uint64_t> idx_off((size_t) G + 1, 0);   // rank g's k-mers hold the MPHF indices [idx_off[g], idx_off[g + 1])
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G; ++g) {   // rank g's k-mers hold the MPHF indices [idx_off[g], idx_off[g + 1])
         uint64_t s = 0;
         for (unsigned b = 0; b < n_owned; ++b) s += sizes[(size_t) g * n_owned + b];
         idx_off[(size_t) g + 1] = idx_off[(size_t) g] + s;
     }
-    if (G > 1) {
-        if (all_payload) cm->all_gather_v_inplace(ctx, res->ext->masks.p, idx_off.data());
-        else cm->all_reduce_or_bytes(ctx, res->ext->masks.p, res->ext->size, false);
+    if (all_payload) {
+        res->ext = build_ext(ctx, res->kpomers, res->kmers, m);   // placement record + the slice's ranks: no lookups, no foreign data
+        mark("build_ext (own slice)");
+        void *bufs[3] = {m->bits.p, m->ranks.p, res->ext->masks.p};
+        const uint64_t *offs[3] = {woff.data(), roff.data(), idx_off.data()};
+        cm->all_gather_v_inplace_multi(ctx, 3, bufs, offs);
+        mark("index + mask slices");
+        mphf_complete(ctx, m);
+        mark("mphf complete");
+        lap(2);
+    } else {
+        void *bufs[2] = {m->bits.p, m->ranks.p};
+        const uint64_t *offs[2] = {woff.data(), roff.data()};
+        cm->all_gather_v_inplace_multi(ctx, 2, bufs, offs);
+        mphf_complete(ctx, m);
+        lap(2);
+        res->ext = build_ext(ctx, res->kpomers, res->kmers, m);
+        if (G > 1) cm->all_reduce_or_bytes(ctx, res->ext->masks.p, res->ext->size, false);
     }
-    mark("mask slices");
     lap(3);
     // ---- 8: tip clipper --------------------------------------------------------------------------------------------------------------------
     if (p->tip_clip) {
@@ -440,10 +443,9 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
         }
         cm->gather_v(ctx, u->words.p, u->total_words * 8, tot ? tot->words.p : nullptr, woff.data(), gather_to);
         cm->gather_v(ctx, u->len.p, u->count * 4, tot ? tot->len.p : nullptr, loff.data(), gather_to);
-        cm->gather_v(ctx, u->word_off.p, u->count * 8, tot ? tot->word_off.p : nullptr, ooff.data(), gather_to);
-        if (tot) {   // the slices' word offsets start at 0: shift every slice by the words before it
-            void shift_word_offsets(sb200_ctx *, uint64_t *, const uint64_t *, const uint64_t *, int, uint64_t);
-            shift_word_offsets(ctx, tot->word_off.p, ooff.data(), woff.data(), G, tot->total_words);
+        if (tot) {   // every sequence is word-aligned and the slices follow each other: the word offsets are a scan of the lengths (no transfer)
+            void word_offsets_from_lengths(sb200_ctx *, const uint32_t *, uint64_t, uint64_t *);
+            word_offsets_from_lengths(ctx, tot->len.p, tot->count, tot->word_off.p);
             delete res->unitigs;
             res->unitigs = tot.release();
             res->gathered = true;
@@ -457,18 +459,16 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     return res.release();
 }
 
-__global__ void shift_offsets_kernel(uint64_t *__restrict__ off, uint64_t first, uint64_t count, uint64_t add) {
+__global__ void words_of_lengths_kernel(const uint32_t *__restrict__ len, uint64_t n, uint64_t *__restrict__ out) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) off[first + i] += add;
+    if (i < n) out[i] = ((uint64_t) len[i] + 31) >> 5;
+    else if (i == n) out[i] = 0;
 }
 
-void shift_word_offsets(sb200_ctx *ctx, uint64_t *word_off, const uint64_t *ooff, const uint64_t *woff, int G, uint64_t total_words) {
-    for (int g = 0; g < G; ++g) {
-        const uint64_t first = ooff[g] / 8, count = (ooff[g + 1] - ooff[g]) / 8;
-        if (count && woff[g]) LAUNCH(ctx, shift_offsets_kernel, div_up(count, 256), 256, 0, word_off, first, count, woff[g] / 8);
-    }
-    CUDA_CHECK(cudaMemcpyAsync(word_off + ooff[G] / 8, &total_words, 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+// word_off[i] = first word of sequence i, word_off[n] = total words
+void word_offsets_from_lengths(sb200_ctx *ctx, const uint32_t *len, uint64_t n, uint64_t *word_off) {
+    LAUNCH(ctx, words_of_lengths_kernel, div_up(n + 1, 256), 256, 0, len, n, word_off);
+    exclusive_scan<uint64_t>(ctx, word_off, n + 1, nullptr);
 }
 
 }  // namespace sb200
