@@ -402,6 +402,9 @@ static bool staged_plan(sb200_ctx *ctx, uint64_t n_est, uint32_t B, int K, Stage
     pl.p = choose_prefix_bits<W>(n_est, B, K, ctx->group_chunk ? 0 : 7168);
     while (pl.p > 0 && ((uint64_t) B << pl.p) > SP_MAX_GROUPS) --pl.p;   // larger groups: the group kernel takes them in rounds
     pl.n_groups = (uint32_t) ((uint64_t) B << pl.p);
+    // the clamp must not leave groups far beyond what the group kernel dedups in one round (GH_UMAX distinct records): an input of that size
+    // (config 5 on one GPU: 633 M instances, 432 M distinct) takes the counting passes, whose group count is not bounded by shared memory
+    if (n_est / std::max<uint64_t>(pl.n_groups, 1) > 10752 && !ctx->group_chunk) return false;
     const uint32_t max_coarse = std::min<uint32_t>(SP_MAX_BINS, SpCfg<W>::CAP / 8);   // >= 8 records per run of a full tile
     pl.s = 0;
     while ((((pl.n_groups - 1) >> pl.s) + 1) > max_coarse) ++pl.s;
@@ -999,10 +1002,13 @@ static bool shard_plan_w(sb200_ctx *ctx, uint64_t n_owner_est, uint32_t B, uint3
     pl.p = choose_prefix_bits<W>(n_owner_est, n_owned, K, ctx->group_chunk ? 0 : 7168);
     while (pl.p > 0 && ((uint64_t) n_owned << pl.p) > SP_MAX_GROUPS) --pl.p;
     pl.n_go = (uint32_t) ((uint64_t) n_owned << pl.p);
+    if (n_owner_est / std::max<uint64_t>(pl.n_go, 1) > 10752 && !ctx->group_chunk) return false;   // (see staged_plan)
     // coarse bins: all owners' bins together are the local bins of a pass-1 tile
     const uint32_t max_total = std::min<uint32_t>(SP_MAX_BINS, std::max<uint32_t>(SpCfg<W>::CAP / 8, G));
+    // (a pass-2 tile orders at most SP_MAX_BINS fine groups: beyond that the coarse bins stay finer than a pass-1 tile would like —
+    //  shorter runs — rather than giving the staged path up; 3- and 4-word records on 8 GPUs are that case)
     pl.s = 0;
-    while (pl.s < pl.p && (uint64_t) (pl.n_go >> pl.s) * G > max_total) ++pl.s;
+    while (pl.s < pl.p && (2u << pl.s) <= (uint32_t) SP_MAX_BINS && (uint64_t) (pl.n_go >> pl.s) * G > max_total) ++pl.s;
     if ((uint64_t) (pl.n_go >> pl.s) * G > SP_MAX_BINS || (1u << pl.s) > (uint32_t) SP_MAX_BINS) return false;
     pl.n_co = pl.n_go >> pl.s;   // s <= p: n_go = n_owned << p is a multiple of 2^s
     return pl.n_co >= 1;
