@@ -354,7 +354,7 @@ def main_sharded(a, world, rank, local_rank):
             if not e2e:
                 for k_, v_ in sh.stage_ms.items():
                     stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
-                xchg["bytes"] += int(sh.info.bytes_sent); xchg["ms"] += float(sh.info.exchange_ms)
+                xchg["bytes"] += int(sh.info.record_bytes); xchg["all"] = xchg.get("all", 0) + int(sh.info.bytes_sent); xchg["ms"] += float(sh.info.exchange_ms)
             info.update(kpomers=int(sh.info.total_kpomers), instances=int(sh.info.total_instances), kmers=int(sh.info.total_kmers),
                         unitigs=int(sh.info.total_unitigs), unitig_bases=int(sh.info.total_unitig_bases),
                         whole_set_fallback=bool(sh.info.whole_set_fallback))
@@ -394,7 +394,7 @@ def main_sharded(a, world, rank, local_rank):
     def timed(e2e):
         for _ in range(a.warmup):
             step(e2e)
-        stage_acc.clear(); xchg["bytes"] = 0; xchg["ms"] = 0.0
+        stage_acc.clear(); xchg["bytes"] = 0; xchg["all"] = 0; xchg["ms"] = 0.0
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -475,10 +475,14 @@ def main_sharded(a, world, rank, local_rank):
         W1 = 8 * ((ks[0] + 1 + 31) // 32)
         nv = xb / (xm * 1e-3) / 1e9 if xm > 0 else None
         roof = {"bound": "nvlink", "achieved": nv, "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": (nv / NVLINK_PEAK_GBS) if nv else None,
-                "traffic": None, "kernel": "record exchanges (2 x NCCL all-to-all: (k+1)-mer instances, k-mer candidates) + slice all-gathers",
-                "bytes_leaving_this_gpu_per_step": xb, "exchange_ms_per_step": xm, "share_of_step": xm / ms_per_step if ms_per_step else None,
-                "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md); 900 GB/s nominal",
-                "note": "achieved = bytes rank 0 handed to other ranks / device time of the two record all-to-alls; instance record = %d B" % W1}
+                "traffic": None,
+                "kernel": "sp_scatter_reads_kernel<W, PEER> + sp_scatter_derive_kernel<WS, W, PEER>: pass 1 of the two groupings, storing every owner's runs "
+                          "into the owner's receive buffer over NVLink (the record exchanges)",
+                "record_bytes_leaving_this_gpu_per_step": xb, "all_bytes_leaving_this_gpu_per_step": xchg.get("all", 0) / a.steps,
+                "exchange_ms_per_step": xm, "share_of_step": xm / ms_per_step if ms_per_step else None,
+                "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md); 900 GB/s nominal; tools/ubench_p2p.cu: 717 GB/s by SM stores, 780 by the copy engine",
+                "note": "achieved = record bytes rank 0 stored into other ranks' HBM / device time of the two kernels that produce AND send them "
+                        "(producer compute included: the kernels are not pure copies); instance record = %d B" % W1}
         line = {"metric": METRIC, "value": total_bases / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
@@ -490,7 +494,7 @@ def main_sharded(a, world, rank, local_rank):
                                                                + ("; every rank also its shard of both k-mer tables" if a.e2e_tables else "")},
                 "roofline": roof, "cpu_baseline": cpu, "stage_ms_rank0": stage_ms, "parity": parity,
                 "counts": {k_: (int(v_) if not isinstance(v_, bool) else v_) for k_, v_ in info.items()},
-                "exchange": "2 x NCCL all-to-all (k-mer instances, k-mer candidates), all-gather of MPHF bit-vector / rank / mask slices, gather of unitigs"}
+                "exchange": "2 x peer-store pass 1 (k-mer instances, k-mer candidates; CUDA IPC mappings over NVLink), one NCCL send/recv group for the MPHF bit-vector / rank / mask slices, gather of unitigs"}
         print(json.dumps(line))
     comm.free()
     dist.destroy_process_group()

@@ -200,8 +200,10 @@ typedef struct {
     int gathered;                /* this rank's unitig handle holds the slices of all ranks                                           */
     uint64_t total_kpomers, total_kmers, total_instances, total_unitigs, total_unitig_bases, n_loops, clipped;
     uint64_t bytes_sent;         /* bytes this rank handed to other ranks (NVLink roofline)                                           */
-    double exchange_ms;          /* device time of the two record all-to-alls                                                        */
+    double exchange_ms;          /* device time of the two record exchanges: the pass-1 kernels that store into the owners' buffers
+                                    over NVLink (or, without peer mappings, the two all-to-alls)                                      */
     double stage_ms[8];          /* count_kpomers, count_kmers, mphf, masks, tipclip, unitigs, gather, total (host wall, stages block) */
+    uint64_t record_bytes;       /* the part of bytes_sent that the two record exchanges moved (what exchange_ms timed)               */
 } sb200_shard_info_t;
 struct sb200_construct_params_s;
 int  sb200_construct_sharded(sb200_ctx *ctx, sb200_comm *comm, const sb200_reads *my_reads, const struct sb200_construct_params_s *params,

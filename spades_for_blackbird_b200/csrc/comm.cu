@@ -151,6 +151,7 @@ void sb200_comm::all_to_all_v(sb200_ctx *ctx, const void *send, const uint64_t *
     const uint8_t *s = (const uint8_t *) send;
     uint8_t *d = (uint8_t *) recv;
     bytes_sent += (send_off[size] - send_off[0]) - (send_off[rank + 1] - send_off[rank]);
+    record_bytes += (send_off[size] - send_off[0]) - (send_off[rank + 1] - send_off[rank]);
     cudaEvent_t e0 = ctx->get_event(), e1 = ctx->get_event();
     if (local) {
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // my send buffer is complete

@@ -38,7 +38,8 @@ struct sb200_comm {
     void *nccl = nullptr;                          // ncclComm_t, or nullptr for a local communicator
     std::shared_ptr<sb200::LocalShared> local;     // virtual ranks
     uint64_t bytes_sent = 0;                       // bytes this rank handed to other ranks since the last reset (NVLink roofline of the bench)
-    double exchange_ms = 0;                        // device time of the record exchanges (all-to-all) since the last reset
+    uint64_t record_bytes = 0;                     // ... of which by the record exchanges (what exchange_ms timed)
+    double exchange_ms = 0;                        // device time of the record exchanges (peer-store pass 1, or all-to-all) since the last reset
     struct PeerSlot {
         void *mine = nullptr;
         std::vector<uint64_t> cap;                 // capacity of every rank's buffer (the same bookkeeping on every rank)

@@ -74,7 +74,7 @@ struct sb200_shard {
     uint64_t clipped = 0, total_kpomers = 0, total_kmers = 0, total_instances = 0, total_unitigs = 0, total_unitig_bases = 0, n_loops = 0;
     bool whole_set_fallback = false, gathered = false;
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // count_kpomers, count_kmers, mphf, masks, tipclip, unitigs, gather, total
-    uint64_t bytes_sent = 0;
+    uint64_t bytes_sent = 0, record_bytes = 0;
     double exchange_ms = 0;
     ~sb200_shard() {
         delete unitigs; delete ext; delete mphf; delete kmers; delete kpomers;
@@ -201,6 +201,7 @@ static sb200_kmers *peer_exchange(sb200_ctx *ctx, sb200_comm *cm, int slot, cons
     ctx->event_pool.push_back(e0);
     ctx->event_pool.push_back(e1);
     cm->bytes_sent += out_bytes;
+    cm->record_bytes += out_bytes;
     cm->exchange_ms += ms;
     cm->barrier(ctx);                        // ... and everybody else's at mine
     std::unique_ptr<sb200_records> got(new sb200_records());
@@ -228,7 +229,7 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     SB200_REQUIRE(G <= 64, "at most 64 ranks");
     std::unique_ptr<sb200_shard> res(new sb200_shard());
     res->ctx = ctx; res->rank = me; res->size = G;
-    cm->bytes_sent = 0; cm->exchange_ms = 0;
+    cm->bytes_sent = 0; cm->record_bytes = 0; cm->exchange_ms = 0;
     const unsigned n_owned = B / (unsigned) G, first_bucket = (unsigned) me * n_owned;
     double t0 = now_ms(), t_start = t0;
     auto lap = [&](int stage) {
@@ -455,6 +456,7 @@ static sb200_shard *construct_sharded(sb200_ctx *ctx, sb200_comm *cm, const sb20
     }
     res->stage_ms[7] = now_ms() - t_start;
     res->bytes_sent = cm->bytes_sent;
+    res->record_bytes = cm->record_bytes;
     res->exchange_ms = cm->exchange_ms;
     return res.release();
 }
@@ -733,7 +735,7 @@ int sb200_shard_info(const sb200_shard *s, sb200_shard_info_t *info) {
     info->total_kpomers = s->total_kpomers; info->total_kmers = s->total_kmers; info->total_instances = s->total_instances;
     info->total_unitigs = s->total_unitigs; info->total_unitig_bases = s->total_unitig_bases; info->n_loops = s->n_loops; info->clipped = s->clipped;
     info->whole_set_fallback = s->whole_set_fallback ? 1 : 0; info->gathered = s->gathered ? 1 : 0;
-    info->bytes_sent = s->bytes_sent; info->exchange_ms = s->exchange_ms;
+    info->bytes_sent = s->bytes_sent; info->record_bytes = s->record_bytes; info->exchange_ms = s->exchange_ms;
     for (int i = 0; i < 8; ++i) info->stage_ms[i] = s->stage_ms[i];
     return 0;
 }

@@ -52,7 +52,7 @@ class ShardInfo(C.Structure):
     _fields_ = [("rank", C.c_int), ("size", C.c_int), ("whole_set_fallback", C.c_int), ("gathered", C.c_int),
                 ("total_kpomers", C.c_uint64), ("total_kmers", C.c_uint64), ("total_instances", C.c_uint64), ("total_unitigs", C.c_uint64),
                 ("total_unitig_bases", C.c_uint64), ("n_loops", C.c_uint64), ("clipped", C.c_uint64), ("bytes_sent", C.c_uint64),
-                ("exchange_ms", C.c_double), ("stage_ms", C.c_double * 8)]
+                ("exchange_ms", C.c_double), ("stage_ms", C.c_double * 8), ("record_bytes", C.c_uint64)]
 
 
 STAGE_NAMES = ("count_kpomers", "count_kmers", "mphf", "masks", "tipclip", "unitigs", "gather", "total")
