@@ -140,7 +140,8 @@ int  sb200_unitigs_coverage(sb200_ctx *ctx, const sb200_covmap *c, const sb200_u
  *      GPU g of G owns the buckets [g*B/G, (g+1)*B/G) of KMerSegmentPolicy — a contiguous range of the reference's file
  *      order — so the shards concatenated in rank order are the single-GPU (= reference) result.  The reference has no
  *      counterpart (it shuffles through kmers_raw<i> files, kmer_splitter.hpp:140-161); the caller moves the byte ranges
- *      between GPUs (NCCL all-to-all / all-reduce; spades_for_blackbird_b200/host/distributed.py).
+ *      between GPUs when using these building blocks directly (any transport; sb200_construct_sharded below is the complete path,
+ *      with the exchanges inside the library).
  *        records_extract_partitioned | records_derive -> records_partition   (grouped by owner, counts per owner)
  *        [exchange into records_alloc] -> count_records_owned            : this GPU's shard of KMerDiskStorage
  *        mphf_build_sharded + [sum bits/ranks over GPUs] + mphf_complete  : the whole KMerIndex on every GPU
@@ -177,7 +178,9 @@ int  sb200_unitigs_extract_local(sb200_ctx *ctx, const sb200_kmers *local_kmers,
                                  sb200_unitigs **out /* NULL if a chain exceeded the walk limit */);
 int  sb200_unitigs_device(const sb200_unitigs *u, uint64_t **words, uint64_t **word_off, uint32_t **len);               /* device */
 
-/* ---- the hash-sharded path as ONE call per rank: host code in C++ over the NCCL C API (csrc/shard.cu, csrc/comm.cu).
+/* ---- the hash-sharded path as ONE call per rank: host code in C++ (csrc/shard.cu, csrc/comm.cu).  The two record exchanges are stores
+ *      of the grouping kernel into the owners' receive buffers over NVLink (peer memory: CUDA IPC mappings between processes, plain
+ *      pointers inside one); the slice exchanges of index and masks and the final gather go through the NCCL C API.
  *      A communicator is either NCCL (one rank per GPU; rank 0 makes the id, the launcher hands its 128 bytes to the others) or
  *      "local" (G virtual ranks = G threads of one process, any placement of contexts on GPUs — the same orchestration on a one-GPU
  *      box).  Every rank calls sb200_construct_sharded with ITS slice of the reads; the result holds this rank's shards of both k-mer
