@@ -2,18 +2,21 @@
 //
 // Rank g of G owns the buckets [g*B/G, (g+1)*B/G) of KMerSegmentPolicy (C/utils/kmer_mph/kmer_buckets.hpp:28-41) — a contiguous
 // range of the reference's file order — so the shards concatenated in rank order ARE the single-GPU (= reference) result.  The
-// reference does the same shuffle through kmers_raw<i> files (kmer_splitter.hpp:140-161); here it is two all-to-alls over NVLink:
-//   1. reads are split by index; every rank extracts canonical (k+1)-mer instances straight into the owner groups (count.cu)
-//   2. all-to-all #1 (instances)             -> owners group / deduplicate / count: their shard of the (k+1)-mer KMerDiskStorage
-//   3. owners derive k-mer candidates (mask bit in the padding), group them by the owner of the K-MER
-//   4. all-to-all #2 (candidates)            -> owners deduplicate + OR the mask bits: their shard of final_kmers
+// reference does the same shuffle through kmers_raw<i> files (kmer_splitter.hpp:140-161); here the shuffle is part of the grouping kernels:
+//   1. reads are split by index; a count pass over the (owner, coarse bin) bins and one tiny all-gather fix every size
+//   2. pass 1 of the grouping stores every owner's runs of canonical (k+1)-mer instances straight into the OWNER's receive buffer over
+//      NVLink (peer_exchange below; peer memory mapped once, sb200_comm::peer_buffers); a barrier; the owners group / deduplicate / count:
+//      their shard of the (k+1)-mer KMerDiskStorage
+//   3. owners derive k-mer candidates (mask bit in the padding, or a byte beside the record)
+//   4. the same peer-store pass 1 by the owner of the K-MER -> owners deduplicate + OR the mask bits: their shard of final_kmers
+//      (without peer mappings, or with SB200_NO_PEER_STORES=1: send buffers + two NCCL all-to-alls, exchange_and_receive)
 //   5. all-gather of bucket sizes (tiny)     -> segment starts / level geometry of the whole KMerIndex on every rank
-//   6. every rank builds the BooPHF levels of its own buckets inside the global layout; an owner's bit-vectors, rank samples and MPHF
-//      indices are CONTIGUOUS ranges, so the index is completed by an all-gather of slices (no zero-padded all-reduce)
-//   7. masks: the same all-gather of slices (mask bits rode through the k-mer sort); only a k-mer set without the payload falls
-//      back to lookups + an all-reduce
+//   6. every rank builds the BooPHF levels of its own buckets inside the global layout (only its own slice of the arrays is touched) and
+//      moves its k-mers' mask bytes to MPHF order at once; an owner's bit-vectors, rank samples and MPHF indices are CONTIGUOUS ranges,
+//      so index and masks are completed by ONE exchange of slices (no zero-padded all-reduce)
+//   7. only a k-mer set without the mask payload falls back to lookups + an all-reduce (decided jointly)
 //   8. [EarlyTipClipper: find over the own junctions, kill lists OR-ed over the ranks, forward links of the own junctions, slices again]
-//   9. every rank walks the start edges of the junctions in its own shard against the global index + masks: its slice of the unitig
+//   9. every rank walks the start edges of the junctions in its own shard through the walk blocks of the global index + masks: its slice of the unitig
 //      list, already in the reference's global order.  Chains beyond the direct-walk limit or perfect loops (no junction to start from)
 //      send the extraction to rank 0, which gathers the k-mer shards and runs the whole-set path (pointer jumping + CollectLoops,
 //      debruijn_graph_constructor.hpp:248-265,308-344) — complete for every input, at one GPU's speed for that stage;

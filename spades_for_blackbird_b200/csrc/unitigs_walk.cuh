@@ -3,10 +3,10 @@
 // When no chain is longer than WALK_LIMIT vertices (every read set with sequencing errors: a branch every few bases),
 // list ranking is overkill.  Every outgoing edge of every oriented junction is a work item, listed in the reference's
 // discovery order (file order of the canonical k-mer, forward strand then reverse strand, A,C,G,T).  A thread follows its
-// edge with one MPHF lookup per step — bit-vectors, rank samples and masks together are ~130 MB and stay L2-resident —
+// edge with one MPHF lookup per step — through the walk blocks (mphf.cuh): index bits, rank and masks of a step in one 128-byte line —
 // exactly like the reference's ConstructSequenceWithEdge (debruijn_graph_constructor.hpp:236-245), but for all ~10^7
-// start edges at once.  The first walk measures (length, end k-mer -> `!(s < !s)`); after two scans a second walk over the
-// kept edges re-traces the path and emits the 2-bit packed sequence directly, 32 bases per stored word.  Only the masks,
+// start edges at once.  The first walk measures (length, end k-mer -> `!(s < !s)`) and captures the path's nucleotides; after two scans
+// the kept edges emit the 2-bit packed sequence from the capture (a second walk only for paths beyond the capture).  Only the masks,
 // the MPHF and the junction's own k-mer are needed: nothing indexed by "all vertices" is built, which is also what lets
 // several GPUs extract disjoint file ranges of junctions independently (tests/test_gpu_sharded.py).  A chain longer than
 // WALK_LIMIT, or vertices no walk reached (perfect loops), send the whole extraction to the pointer-jumping path.
