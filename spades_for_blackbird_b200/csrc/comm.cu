@@ -222,6 +222,7 @@ bool sb200_comm::peer_buffers(sb200_ctx *ctx, int slot, const uint64_t *need, vo
         }
         uint64_t ok = 1;
         if (local) {
+            CUDA_CHECK(cudaSetDevice(ctx->device));   // peer access is a property of the calling thread's current device
             local->ptr[(size_t) rank] = ps.mine;
             local->barrier();
             for (int r = 0; r < size; ++r) {
